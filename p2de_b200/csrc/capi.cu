@@ -1,0 +1,652 @@
+// capi.cu — C ABI of libp2de_b200.so (include/p2de_b200.h): handle, setup, launches.
+//
+// Host language note: the reference's host is Julia (absent from this image); this layer is what
+// Julia reaches through `ccall` (julia/P2DEB200.jl) and what the Python mirror (p2de_b200/) and
+// the tests reach through ctypes.  No torch types, no exceptions across the boundary.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "../../include/p2de_b200.h"
+#include "kernels2d.cuh"
+
+using namespace p2de;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DeviceBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct p2de_handle {
+  p2de_config cfg{};
+  int N1D = 0, Nq = 0, Nfp = 0, Nc = 0, Nd = 0, Ns = 3;
+  long long K = 0;
+  int mode = 0;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  long long launches = 0;
+  bool have_state = false;
+
+  // tables (one of these is used, by N1D)
+  Tables2D<2> t2{};
+  Tables2D<3> t3{};
+  Tables2D<4> t4{};
+  Tables2D<5> t5{};
+  MeshTopo topo{};
+  double Jq = 0, Jcons = 0;
+  std::vector<double> wq;
+
+  // device memory
+  double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
+  int cur = 0;
+  double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
+  double *Lz = nullptr;       // [K, Ns]
+  double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
+  double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
+  unsigned long long *dt_bits = nullptr;
+  double *partial = nullptr;  // reduction scratch
+  int *mapP32 = nullptr, *bcflag = nullptr;
+  double *Ival = nullptr;
+  unsigned char *bc_type[4] = {nullptr, nullptr, nullptr, nullptr};
+  double *bc_val[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<void *> owned;
+  double last_dt = 0;
+};
+
+namespace {
+
+int fail(p2de_handle *h, int code, const char *fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(h, call)                                                                              \
+  do {                                                                                           \
+    cudaError_t e_ = (call);                                                                     \
+    if (e_ != cudaSuccess) return fail(h, P2DE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+template <class T>
+int dev_alloc(p2de_handle *h, T **p, size_t n) {
+  void *q = nullptr;
+  CU(h, cudaMalloc(&q, n * sizeof(T)));
+  h->owned.push_back(q);
+  *p = static_cast<T *>(q);
+  return 0;
+}
+
+template <int N1D>
+Tables2D<N1D> &tables(p2de_handle *h);
+template <> Tables2D<2> &tables<2>(p2de_handle *h) { return h->t2; }
+template <> Tables2D<3> &tables<3>(p2de_handle *h) { return h->t3; }
+template <> Tables2D<4> &tables<4>(p2de_handle *h) { return h->t4; }
+template <> Tables2D<5> &tables<5>(p2de_handle *h) { return h->t5; }
+
+template <int N1D> struct Launch { static constexpr int EPB = (N1D <= 4) ? 32 : 16; };
+
+// Extract the per-line tables from the caller's operators and verify the structure this
+// kernel family relies on (tensor-product LGL collocation on a Cartesian mesh).
+template <int N1D>
+int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
+  constexpr int Nq = N1D * N1D, Nfp = 4 * N1D, Nh = Nq + Nfp;
+  Tables2D<N1D> &T = tables<N1D>(h);
+  const double tol = 0.0;
+  auto node = [](int d, int line, int a) { return d == 0 ? a + line * N1D : line + a * N1D; };
+  // fq2q must be the LGL boundary-node map in face order left, right, bottom, top
+  for (int f = 0; f < Nfp; ++f) {
+    int F = f / N1D, a = f % N1D;
+    int expect = F == 0 ? a * N1D : F == 1 ? (N1D - 1) + a * N1D : F == 2 ? a : a + (N1D - 1) * N1D;
+    if ((int)o->fq2q[f] - 1 != expect) return fail(h, P2DE_ERR_UNSUPPORTED, "fq2q[%d]=%lld is not the LGL tensor-product face map", f, (long long)o->fq2q[f]);
+    T.fq2q[f] = expect;
+  }
+  // Vf must be the 0/1 gather (collocated face nodes)
+  for (int f = 0; f < Nfp; ++f)
+    for (int j = 0; j < Nq; ++j) {
+      double v = o->Vf[f + (size_t)j * Nfp], e = (j == T.fq2q[f]) ? 1.0 : 0.0;
+      if (std::fabs(v - e) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "Vf is not a 0/1 gather: only Lobatto collocation has a GPU kernel in this build");
+    }
+  for (int d = 0; d < 2; ++d) {
+    const double *S = o->Srsh_db[d], *S0 = o->Srs0[d];
+    const double g = GJ[d == 0 ? 0 : 3];
+    if (GJ[1] != 0.0 || GJ[2] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "non-Cartesian geometric factors (sxJ, ryJ != 0)");
+    // every volume-volume nonzero of S_d must couple two nodes of one d-line
+    for (int i = 0; i < Nq; ++i)
+      for (int j = 0; j < Nq; ++j) {
+        bool same_line = d == 0 ? (i / N1D == j / N1D) : (i % N1D == j % N1D);
+        if (!same_line && (std::fabs(S[i + (size_t)j * Nh]) > tol || std::fabs(S0[i + (size_t)j * Nq]) > tol))
+          return fail(h, P2DE_ERR_UNSUPPORTED, "S_%d couples nodes of different grid lines", d);
+      }
+    for (int line = 0; line < N1D; ++line) {
+      for (int a = 0; a < N1D; ++a)
+        for (int b = 0; b < N1D; ++b)
+          T.SH[d][line][a][b] = g * S[node(d, line, a) + (size_t)node(d, line, b) * Nh];
+      for (int a = 0; a < N1D; ++a) {
+        T.S0[d][line][a] = (a + 1 < N1D) ? g * S0[node(d, line, a + 1) + (size_t)node(d, line, a) * Nq] : 0.0;
+        for (int b = 0; b < N1D; ++b)   // low-order operator must be nearest-neighbour
+          if (std::abs(a - b) > 1 && std::fabs(S0[node(d, line, a) + (size_t)node(d, line, b) * Nq]) > tol)
+            return fail(h, P2DE_ERR_UNSUPPORTED, "low-order S0 is not tridiagonal along lines");
+      }
+      for (int e = 0; e < 2; ++e) {
+        int f = (2 * d + e) * N1D + line;
+        T.Bf[d][line][e] = g * o->Brs[d][f];
+        if (o->Brs[1 - d][f] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "face %d has a tangential boundary weight", f);
+      }
+    }
+    // faces of the other direction must have zero weight in B_d
+    for (int f = 0; f < Nfp; ++f)
+      if ((f / (2 * N1D)) != d && o->Brs[d][f] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "B_%d nonzero on a face of the other direction", d);
+  }
+  for (int i = 0; i < Nq; ++i) {
+    T.wq[i] = o->wq[i];
+    T.minv[i] = o->MinvVhT[i + (size_t)i * Nq];
+    for (int j = 0; j < Nq; ++j)
+      if (j != i && o->MinvVhT[i + (size_t)j * Nq] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "mass matrix is not diagonal");
+  }
+  for (int f = 0; f < Nfp; ++f) T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
+  return 0;
+}
+
+void structured_partner(int N1D, int Kx, int Ky, bool px, bool py, long long k, int f, long long *kP, int *fP) {
+  int ix = (int)(k % Kx), iy = (int)(k / Kx), F = f / N1D, a = f % N1D;
+  int jx = ix + (F == 0 ? -1 : F == 1 ? 1 : 0), jy = iy + (F == 2 ? -1 : F == 3 ? 1 : 0);
+  bool out = jx < 0 || jx >= Kx || jy < 0 || jy >= Ky;
+  if (out) {
+    bool wrap = F < 2 ? px : py;
+    if (!wrap) { *kP = k; *fP = f; return; }
+    jx = (jx + Kx) % Kx; jy = (jy + Ky) % Ky;
+  }
+  *kP = jx + (long long)jy * Kx; *fP = (F ^ 1) * N1D + a;
+}
+
+int setup_topology(p2de_handle *h, const p2de_bcdata *bc) {
+  const int N1D = h->N1D, Nfp = h->Nfp, Kx = h->cfg.Kx, Ky = h->cfg.Ky;
+  const long long K = h->K;
+  MeshTopo &M = h->topo;
+  M.K = K; M.Kx = Kx; M.Ky = Ky;
+  bool structured = (long long)Kx * Ky == K;
+  int px = bc->periodic_x != 0, py = bc->periodic_y != 0;
+  if (bc->mapP && structured) {
+    bool found = false;
+    for (int c = 0; c < 4 && !found; ++c) {
+      bool tx = c & 1, ty = c & 2, ok = true;
+      for (long long k = 0; k < K && ok; ++k)
+        for (int f = 0; f < Nfp; ++f) {
+          long long kP; int fP;
+          structured_partner(N1D, Kx, Ky, tx, ty, k, f, &kP, &fP);
+          if (bc->mapP[k * Nfp + f] - 1 != kP * Nfp + fP) { ok = false; break; }
+        }
+      if (ok) { found = true; px = tx; py = ty; }
+    }
+    structured = found;
+  } else if (!bc->mapP && !structured) {
+    return fail(h, P2DE_ERR_ARG, "mapP == NULL needs K == Kx*Ky");
+  }
+  // boundary data must sit on domain-boundary faces for the structured tables
+  auto on_boundary = [&](long long idx) {
+    long long k = idx / Nfp; int f = (int)(idx % Nfp), F = f / N1D;
+    int ix = (int)(k % Kx), iy = (int)(k / Kx);
+    return F == 0 ? ix == 0 : F == 1 ? ix == Kx - 1 : F == 2 ? iy == 0 : iy == Ky - 1;
+  };
+  for (long long i = 0; i < bc->nI; ++i) {
+    long long idx = bc->mapI[i] - 1;
+    if (idx < 0 || idx >= K * Nfp) return fail(h, P2DE_ERR_ARG, "mapI[%lld] out of range", i);
+    if (structured && !on_boundary(idx)) structured = false;
+  }
+  for (long long i = 0; i < bc->nO; ++i) {
+    long long idx = bc->mapO[i] - 1;
+    if (idx < 0 || idx >= K * Nfp) return fail(h, P2DE_ERR_ARG, "mapO[%lld] out of range", i);
+    if (structured && !on_boundary(idx)) structured = false;
+  }
+  if (structured) {
+    M.periodic_x = px; M.periodic_y = py;
+    M.mapP32 = nullptr; M.bcflag = nullptr; M.Ival = nullptr;
+    if (bc->nI + bc->nO > 0) {
+      std::vector<unsigned char> type[4];
+      std::vector<double> val[4];
+      for (int F = 0; F < 4; ++F) {
+        size_t len = (size_t)(F < 2 ? Ky : Kx) * N1D;
+        type[F].assign(len, 0); val[F].assign(len * 4, 0.0);
+      }
+      auto put = [&](long long idx, int t, const double *v) {
+        long long k = idx / Nfp; int f = (int)(idx % Nfp), F = f / N1D, a = f % N1D;
+        int pos = F < 2 ? (int)(k / Kx) : (int)(k % Kx);
+        type[F][(size_t)pos * N1D + a] = (unsigned char)t;
+        if (v) std::memcpy(&val[F][((size_t)pos * N1D + a) * 4], v, 4 * sizeof(double));
+      };
+      for (long long i = 0; i < bc->nI; ++i) put(bc->mapI[i] - 1, 1, bc->Ival + 4 * i);
+      for (long long i = 0; i < bc->nO; ++i) put(bc->mapO[i] - 1, 2, nullptr);
+      for (int F = 0; F < 4; ++F) {
+        bool any = false;
+        for (unsigned char t : type[F]) any |= t != 0;
+        if (!any) continue;
+        if (int rc = dev_alloc(h, &h->bc_type[F], type[F].size())) return rc;
+        if (int rc = dev_alloc(h, &h->bc_val[F], val[F].size())) return rc;
+        CU(h, cudaMemcpy(h->bc_type[F], type[F].data(), type[F].size(), cudaMemcpyHostToDevice));
+        CU(h, cudaMemcpy(h->bc_val[F], val[F].data(), val[F].size() * sizeof(double), cudaMemcpyHostToDevice));
+        M.bc_type[F] = h->bc_type[F]; M.bc_val[F] = h->bc_val[F];
+      }
+    }
+    return 0;
+  }
+  // generic gather tables
+  if (!bc->mapP) return fail(h, P2DE_ERR_ARG, "boundary data off the domain boundary needs an explicit mapP");
+  if (K * Nfp >= (1ll << 31)) return fail(h, P2DE_ERR_UNSUPPORTED, "generic mapP limited to 2^31 face nodes");
+  std::vector<int> m32((size_t)K * Nfp), fl((size_t)K * Nfp, 0);
+  for (size_t i = 0; i < m32.size(); ++i) {
+    long long v = bc->mapP[i] - 1;
+    if (v < 0 || v >= K * Nfp) return fail(h, P2DE_ERR_ARG, "mapP[%zu] out of range", i);
+    m32[i] = (int)v;
+  }
+  for (long long i = 0; i < bc->nI; ++i) fl[bc->mapI[i] - 1] = (int)(i + 1);
+  for (long long i = 0; i < bc->nO; ++i) fl[bc->mapO[i] - 1] = -1;
+  if (int rc = dev_alloc(h, &h->mapP32, m32.size())) return rc;
+  if (int rc = dev_alloc(h, &h->bcflag, fl.size())) return rc;
+  CU(h, cudaMemcpy(h->mapP32, m32.data(), m32.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->bcflag, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (bc->nI > 0) {
+    if (int rc = dev_alloc(h, &h->Ival, (size_t)bc->nI * 4)) return rc;
+    CU(h, cudaMemcpy(h->Ival, bc->Ival, (size_t)bc->nI * 4 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  M.mapP32 = h->mapP32; M.bcflag = h->bcflag; M.Ival = h->Ival;
+  return 0;
+}
+
+__global__ void set_dt_kernel(unsigned long long *dt_bits, double v) { *dt_bits = (unsigned long long)__double_as_longlong(v); }
+
+__global__ void reduce_kernel(const double *U, const double *wq, int Nq, long long n_nodes, double J, int what, double *partial) {
+  __shared__ double sh[256];
+  double acc = what == P2DE_REDUCE_CONSERVATION ? 0.0 : INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_nodes; i += (long long)gridDim.x * blockDim.x) {
+    Cons2 u = load_cons(U + i * 4);
+    if (what == P2DE_REDUCE_CONSERVATION) acc += J * wq[i % Nq] * (((u.rho + u.m1) + u.m2) + u.E);
+    else if (what == P2DE_REDUCE_MIN_RHO) acc = fmin(acc, u.rho);
+    else acc = fmin(acc, rhoe2(u));
+  }
+  sh[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) sh[threadIdx.x] = what == P2DE_REDUCE_CONSERVATION ? sh[threadIdx.x] + sh[threadIdx.x + s] : fmin(sh[threadIdx.x], sh[threadIdx.x + s]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+template <int N1D, int MODE>
+int launch_stage_t(p2de_handle *h, const StageArgs &A) {
+  constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
+  constexpr int TBL = (sizeof(Tables2D<N1D>) + 7) / 8;
+  size_t smem = sizeof(double) * (TBL + (size_t)EPB * stage_smem_doubles_per_elem<N1D, MODE>());
+  auto kern = stage_kernel<N1D, MODE, EPB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  kern<<<grid, EPB * TPE, smem, h->stream>>>(A, h->topo, tables<N1D>(h));
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+template <int N1D>
+int launch_stage_n(p2de_handle *h, const StageArgs &A) {
+  switch (h->mode) {
+    case MODE_SUBCELL: return launch_stage_t<N1D, MODE_SUBCELL>(h, A);
+    case MODE_ZHANGSHU: return launch_stage_t<N1D, MODE_ZHANGSHU>(h, A);
+    case MODE_LOW: return launch_stage_t<N1D, MODE_LOW>(h, A);
+    default: return launch_stage_t<N1D, MODE_HIGH>(h, A);
+  }
+}
+int launch_stage(p2de_handle *h, const StageArgs &A) {
+  switch (h->N1D) {
+    case 2: return launch_stage_n<2>(h, A);
+    case 3: return launch_stage_n<3>(h, A);
+    case 4: return launch_stage_n<4>(h, A);
+    case 5: return launch_stage_n<5>(h, A);
+  }
+  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+
+template <int N1D, int MODE>
+int launch_update_t(p2de_handle *h, const UpdateArgs &A) {
+  constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
+  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  update_kernel<N1D, MODE, EPB><<<grid, EPB * TPE, 0, h->stream>>>(A, h->topo, tables<N1D>(h));
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+template <int N1D>
+int launch_update_n(p2de_handle *h, const UpdateArgs &A) {
+  if (h->mode == MODE_SUBCELL) return launch_update_t<N1D, MODE_SUBCELL>(h, A);
+  return launch_update_t<N1D, MODE_LOW>(h, A);
+}
+int launch_update(p2de_handle *h, const UpdateArgs &A) {
+  switch (h->N1D) {
+    case 2: return launch_update_n<2>(h, A);
+    case 3: return launch_update_n<3>(h, A);
+    case 4: return launch_update_n<4>(h, A);
+    case 5: return launch_update_n<5>(h, A);
+  }
+  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+
+StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_host, bool use_dt_dev) {
+  StageArgs A{};
+  A.Uq = Uq;
+  A.rhsL = h->rhsL; A.dF = h->dF; A.lpre = h->lpre; A.rhsU = h->rhsU;
+  A.Lout = h->Lz ? h->Lz + h->K * (nstage - 1) : nullptr;
+  A.rhsH_diag = h->rhsH_diag; A.rhsL_diag = h->rhsL_diag;
+  A.dt_bits = h->dt_bits;
+  A.dt_dev = reinterpret_cast<const double *>(h->dt_bits);
+  A.dt_host = dt_host; A.use_dt_dev = use_dt_dev; A.nstage = nstage;
+  A.gamma = h->cfg.gamma; A.ZEROTOL = h->cfg.ZEROTOL; A.POSTOL = h->cfg.POSTOL; A.zeta = h->cfg.zeta;
+  A.CFL = h->cfg.CFL; A.Jq = h->Jq; A.blend = 1.0;
+  A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
+  return A;
+}
+
+int ensure_rhsU(p2de_handle *h) {
+  if (!h->rhsU) return dev_alloc(h, &h->rhsU, (size_t)h->K * h->Nq * 4);
+  return 0;
+}
+int ensure_Llocal(p2de_handle *h) {
+  if (!h->Llocal) {
+    size_t n = (size_t)(h->Nq + h->N1D) * 2 * h->K * h->Ns;
+    if (int rc = dev_alloc(h, &h->Llocal, n)) return rc;
+    CU(h, cudaMemsetAsync(h->Llocal, 0, n * sizeof(double), h->stream));
+  }
+  return 0;
+}
+
+// one stage: stage_kernel + update_kernel.  `Uin` is the stage input; if `Uout` != nullptr the
+// SSP combine Uout = a*resW + b*(Uin + dt*rhsU) is fused into the update kernel.
+int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt_host, bool limiter_dt_dev,
+              bool update_dt_dev, double *Uout, const double *resW, double a, double b, bool want_outputs) {
+  if (nstage == 1) {
+    double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // low_order_graph_viscosity.jl:230
+    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->dt_bits, cap);
+    CU(h, cudaGetLastError());
+    h->launches++;
+  }
+  if (h->rhsH_diag && h->mode == MODE_SUBCELL)
+    CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * 4 * sizeof(double), h->stream));
+  StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
+  if (int rc = launch_stage(h, A)) return rc;
+  UpdateArgs B{};
+  B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
+  B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)(h->Nq + h->N1D) * 2 * h->K * (nstage - 1) : nullptr;
+  B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
+  B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
+  B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
+  B.Jq = h->Jq;
+  if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *p2de_last_error(const p2de_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2de_geometry *geom,
+                    const p2de_bcdata *bc, p2de_handle **out) {
+  if (!cfg || !ops || !geom || !bc || !out) return fail(nullptr, P2DE_ERR_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->abi_version != P2DE_ABI_VERSION) return fail(nullptr, P2DE_ERR_ARG, "abi_version %d != %d", cfg->abi_version, P2DE_ABI_VERSION);
+  if (cfg->dim != 2) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "dim=%d: only the 2D path has a GPU kernel in this build", cfg->dim);
+  if (cfg->N < 1 || cfg->N > 4) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "N=%d outside 1..4", cfg->N);
+  const int N1D = cfg->N + 1;
+  if (cfg->Nq != N1D * N1D || cfg->Nfp != 4 * N1D || cfg->Nh != cfg->Nq + cfg->Nfp || cfg->Np != cfg->Nq)
+    return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d quad", cfg->N);
+  if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
+  if (cfg->basis != P2DE_BASIS_LOBATTO) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "GaussCollocation has no GPU kernel in this build (SURVEY.md 8f-1)");
+  if (cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation has no GPU kernel in this build (SURVEY.md 8f-1)");
+  if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture has no GPU kernel in this build (SURVEY.md 8f-2)");
+  int mode;
+  if (cfg->rhs_type == P2DE_RHS_LOW_ORDER_POSITIVITY) mode = MODE_LOW;
+  else if (cfg->rhs_type == P2DE_RHS_FLUX_DIFF) mode = MODE_HIGH;
+  else if (cfg->rhs_type == P2DE_RHS_LIMITED_DG) {
+    if (cfg->limiter == P2DE_LIMITER_ZHANGSHU) mode = MODE_ZHANGSHU;
+    else if (cfg->limiter == P2DE_LIMITER_SUBCELL) {
+      if (cfg->bound != P2DE_BOUND_POSITIVITY) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "only PositivityBound has a GPU kernel in this build (SURVEY.md 8f-2)");
+      mode = MODE_SUBCELL;
+    } else return fail(nullptr, P2DE_ERR_UNSUPPORTED, "LimitedDG needs ZhangShuLimiter or SubcellLimiter");
+  } else return fail(nullptr, P2DE_ERR_ARG, "rhs_type %d", cfg->rhs_type);
+  if (cfg->surf_flux_low != P2DE_SURFFLUX_LF_NODAL && cfg->surf_flux_low != P2DE_SURFFLUX_LF_PROJECTED)
+    return fail(nullptr, P2DE_ERR_ARG, "surf_flux_low %d", cfg->surf_flux_low);
+  if (cfg->surf_flux_high != P2DE_SURFFLUX_LF_PROJECTED && cfg->surf_flux_high != P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED)
+    return fail(nullptr, P2DE_ERR_ARG, "surf_flux_high %d", cfg->surf_flux_high);
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, P2DE_ERR_CUDA, "no CUDA device (%s): libp2de_b200 has no CPU fallback", cudaGetErrorString(e));
+  p2de_handle *h = new p2de_handle();
+  h->cfg = *cfg;
+  h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = 4; h->Nd = 2; h->K = cfg->K; h->mode = mode;
+  auto bail = [&](int rc) { g_create_error = h->err; p2de_destroy(h); return rc; };
+  if (cfg->device >= 0) { if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device)); }
+  cudaGetDevice(&h->device);
+
+  // geometry: uniform meshes only (the reference builds nothing else, init.jl:137)
+  double GJ[4];
+  if (geom->uniform) {
+    h->Jq = geom->J_const; h->Jcons = geom->J_const;
+    for (int a = 0; a < 4; ++a) GJ[a] = geom->GJ_const[a];
+  } else {
+    if (!geom->Jq || !geom->GJh[0] || !geom->GJh[1] || !geom->GJh[2] || !geom->GJh[3]) return bail(fail(h, P2DE_ERR_ARG, "geometry arrays missing"));
+    h->Jq = geom->Jq[0]; h->Jcons = geom->J ? geom->J[0] : geom->Jq[0];
+    for (int a = 0; a < 4; ++a) GJ[a] = geom->GJh[a][0];
+    for (size_t i = 0; i < (size_t)cfg->Nq * cfg->K; ++i)
+      if (geom->Jq[i] != h->Jq || (geom->J && geom->J[i] != h->Jcons)) return bail(fail(h, P2DE_ERR_UNSUPPORTED, "non-uniform Jq: only uniform meshes are supported"));
+    for (int a = 0; a < 4; ++a)
+      for (size_t i = 0; i < (size_t)cfg->Nh * cfg->K; ++i)
+        if (geom->GJh[a][i] != GJ[a]) return bail(fail(h, P2DE_ERR_UNSUPPORTED, "non-uniform geometric factors"));
+  }
+  int rc = 0;
+  switch (N1D) {
+    case 2: rc = build_tables<2>(h, ops, GJ); break;
+    case 3: rc = build_tables<3>(h, ops, GJ); break;
+    case 4: rc = build_tables<4>(h, ops, GJ); break;
+    case 5: rc = build_tables<5>(h, ops, GJ); break;
+  }
+  if (rc) return bail(rc);
+  h->wq.assign(ops->wq, ops->wq + cfg->Nq);
+  if ((rc = setup_topology(h, bc))) return bail(rc);
+
+  const size_t nU = (size_t)h->K * h->Nq * 4;
+  if ((rc = dev_alloc(h, &h->U[0], nU)) || (rc = dev_alloc(h, &h->U[1], nU))) return bail(rc);
+  if (mode == MODE_SUBCELL) {
+    if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)) ||
+        (rc = dev_alloc(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1))))
+      return bail(rc);
+  } else {
+    if ((rc = ensure_rhsU(h))) return bail(rc);
+  }
+  if ((rc = dev_alloc(h, &h->Lz, (size_t)h->K * h->Ns))) return bail(rc);
+  if (cudaMemset(h->Lz, 0, (size_t)h->K * h->Ns * sizeof(double)) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memset"));
+  if (cfg->keep_diagnostics) {
+    if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return bail(rc);
+    cudaMemset(h->rhsH_diag, 0, nU * sizeof(double)); cudaMemset(h->rhsL_diag, 0, nU * sizeof(double));
+  }
+  if ((rc = dev_alloc(h, &h->dt_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
+  if (cudaMemcpy(h->partial + 1024, h->wq.data(), h->Nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy wq"));
+  *out = h;
+  return P2DE_OK;
+}
+
+int32_t p2de_destroy(p2de_handle *h) {
+  if (!h) return P2DE_OK;
+  cudaSetDevice(h->device);
+  for (void *p : h->owned) cudaFree(p);
+  delete h;
+  return P2DE_OK;
+}
+
+int32_t p2de_set_stream(p2de_handle *h, void *cuda_stream) {
+  if (!h) return P2DE_ERR_ARG;
+  h->stream = static_cast<cudaStream_t>(cuda_stream);
+  return P2DE_OK;
+}
+
+int32_t p2de_synchronize(p2de_handle *h) {
+  if (!h) return P2DE_ERR_ARG;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return P2DE_OK;
+}
+
+int32_t p2de_set_state_async(p2de_handle *h, const double *Uq_host) {
+  if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
+  CU(h, cudaMemcpyAsync(h->U[h->cur], Uq_host, (size_t)h->K * h->Nq * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->have_state = true;
+  return P2DE_OK;
+}
+int32_t p2de_set_state(p2de_handle *h, const double *Uq_host) {
+  if (int rc = p2de_set_state_async(h, Uq_host)) return rc;
+  return p2de_synchronize(h);
+}
+int32_t p2de_get_state_async(p2de_handle *h, double *Uq_host) {
+  if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
+  if (!h->have_state) return fail(h, P2DE_ERR_STATE, "get_state before set_state");
+  CU(h, cudaMemcpyAsync(Uq_host, h->U[h->cur], (size_t)h->K * h->Nq * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  return P2DE_OK;
+}
+int32_t p2de_get_state(p2de_handle *h, double *Uq_host) {
+  if (int rc = p2de_get_state_async(h, Uq_host)) return rc;
+  return p2de_synchronize(h);
+}
+
+int32_t p2de_rhs(p2de_handle *h, double t, double dt, int32_t nstage, double *dt_out) {
+  if (!h) return P2DE_ERR_ARG;
+  if (!h->have_state) return fail(h, P2DE_ERR_STATE, "rhs before set_state");
+  if (nstage < 1 || nstage > h->Ns) return fail(h, P2DE_ERR_ARG, "nstage %d outside 1..%d", nstage, h->Ns);
+  if (int rc = ensure_rhsU(h)) return rc;
+  if (h->mode == MODE_SUBCELL) if (int rc = ensure_Llocal(h)) return rc;
+  if (int rc = run_stage(h, h->U[h->cur], nstage, t, dt, false, false, nullptr, nullptr, 0, 0, true)) return rc;
+  double dtr = dt;
+  if (nstage == 1 && h->mode != MODE_HIGH) {
+    CU(h, cudaMemcpyAsync(&dtr, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  }
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (dt_out) *dt_out = dtr;
+  return P2DE_OK;
+}
+
+int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
+  if (!h) return P2DE_ERR_ARG;
+  if (!h->have_state) return fail(h, P2DE_ERR_STATE, "ssp33_step before set_state");
+  const bool outs = h->Llocal != nullptr;   // keep L_local current only if someone asked for it before
+  double *Ua = h->U[h->cur], *Ub = h->U[1 - h->cur];
+  double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // SSPRK33.jl:30
+  const bool has_cfl = h->mode != MODE_HIGH;                          // FluxDiffRHS never changes dt (rhs.jl:38)
+  // stage 1: limiter sees the cap (rhs.jl:46,52), the combine sees the CFL-limited dt
+  if (int rc = run_stage(h, Ua, 1, t, cap, false, has_cfl, Ub, Ua, 0.0, 1.0, outs)) return rc;
+  if (int rc = run_stage(h, Ub, 2, t, cap, has_cfl, has_cfl, Ub, Ua, 3.0 / 4.0, 1.0 / 4.0, outs)) return rc;
+  if (int rc = run_stage(h, Ub, 3, t, cap, has_cfl, has_cfl, Ub, Ua, 1.0 / 3.0, 2.0 / 3.0, outs)) return rc;
+  h->cur = 1 - h->cur;
+  return P2DE_OK;
+}
+
+int32_t p2de_last_dt(p2de_handle *h, double *dt_out) {
+  if (!h || !dt_out) return P2DE_ERR_ARG;
+  CU(h, cudaMemcpyAsync(dt_out, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return P2DE_OK;
+}
+
+int32_t p2de_ssp33_step(p2de_handle *h, double t, double *dt_out) {
+  if (int rc = p2de_ssp33_step_async(h, t)) return rc;
+  double dt = 0;
+  if (h->mode == MODE_HIGH) {
+    CU(h, cudaStreamSynchronize(h->stream));
+    dt = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);
+  } else if (int rc = p2de_last_dt(h, &dt)) return rc;
+  h->last_dt = dt;
+  if (dt_out) *dt_out = dt;
+  return P2DE_OK;
+}
+
+int32_t p2de_ssp33_run(p2de_handle *h, double *t_inout, int64_t max_steps, int64_t *steps_out, double *dthist) {
+  if (!h || !t_inout) return P2DE_ERR_ARG;
+  double t = *t_inout;
+  int64_t n = 0;
+  while (t < h->cfg.T && n < max_steps) {   // SSPRK33.jl:28
+    double dt;
+    if (int rc = p2de_ssp33_step(h, t, &dt)) return rc;
+    t += dt;
+    if (dthist) dthist[n] = dt;
+    ++n;
+  }
+  *t_inout = t;
+  if (steps_out) *steps_out = n;
+  return P2DE_OK;
+}
+
+int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
+  if (!h || !dst) return fail(h, P2DE_ERR_ARG, "null argument");
+  const int64_t nU = h->K * h->Nq * 4;
+  const double *src = nullptr;
+  int64_t cnt = 0;
+  switch (field) {
+    case P2DE_FIELD_UQ: src = h->U[h->cur]; cnt = nU; break;
+    case P2DE_FIELD_RESW: src = h->U[1 - h->cur]; cnt = nU; break;
+    case P2DE_FIELD_RHSU: src = h->rhsU; cnt = nU; break;
+    case P2DE_FIELD_RHSH: src = h->rhsH_diag; cnt = nU; break;
+    case P2DE_FIELD_RHSL: src = h->rhsL_diag; cnt = nU; break;
+    case P2DE_FIELD_L: src = h->Lz; cnt = h->K * h->Ns; break;
+    case P2DE_FIELD_L_LOCAL: src = h->Llocal; cnt = (int64_t)(h->Nq + h->N1D) * 2 * h->K * h->Ns; break;
+    case P2DE_FIELD_THETA: cnt = h->K * h->Ns; break;          // NoEntropyProjectionLimiter: never written (zeros)
+    case P2DE_FIELD_THETA_LOCAL: cnt = (int64_t)h->Nfp * h->K * h->Ns; break;
+    default: return fail(h, P2DE_ERR_ARG, "unknown field %d", field);
+  }
+  if (n < cnt) return fail(h, P2DE_ERR_ARG, "destination too small: %lld < %lld", (long long)n, (long long)cnt);
+  if (field == P2DE_FIELD_THETA || field == P2DE_FIELD_THETA_LOCAL) { std::memset(dst, 0, cnt * sizeof(double)); return P2DE_OK; }
+  if (!src) return fail(h, P2DE_ERR_STATE, "field %d is not kept (keep_diagnostics / call p2de_rhs first)", field);
+  CU(h, cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return P2DE_OK;
+}
+
+int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out) {
+  if (!h || !out) return P2DE_ERR_ARG;
+  if (what < 0 || what > 2) return fail(h, P2DE_ERR_ARG, "unknown reduction %d", what);
+  const int blocks = 1024;
+  reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->partial + 1024, h->Nq, h->K * h->Nq, h->Jcons, what, h->partial);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  std::vector<double> part(blocks);
+  CU(h, cudaMemcpyAsync(part.data(), h->partial, blocks * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  double r = what == P2DE_REDUCE_CONSERVATION ? 0.0 : std::numeric_limits<double>::infinity();
+  for (double v : part) r = what == P2DE_REDUCE_CONSERVATION ? r + v : std::fmin(r, v);
+  *out = r;
+  return P2DE_OK;
+}
+
+int64_t p2de_kernel_launch_count(const p2de_handle *h) { return h ? h->launches : 0; }
+void *p2de_device_state_ptr(p2de_handle *h) { return h ? h->U[h->cur] : nullptr; }
+
+int32_t p2de_comm_unique_id(uint8_t id_out[128]) { (void)id_out; g_create_error = "multi-GPU not built yet"; return P2DE_ERR_UNSUPPORTED; }
+int32_t p2de_comm_init(p2de_handle *h, int32_t, int32_t, const uint8_t *) { return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU not built yet"); }
+
+}  // extern "C"

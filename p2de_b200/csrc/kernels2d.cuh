@@ -1,0 +1,623 @@
+// kernels2d.cuh — the per-stage hot path on 2D uniform quad meshes with LGL collocation.
+//
+// Two kernels per SSP-RK stage:
+//
+//   stage_kernel   = entropy projection + low-order graph-viscosity RHS + CFL dt +
+//                    entropy-stable flux-differencing RHS + element-local part of the limiter
+//                    (reference: rhs.jl:41-55, low_order_graph_viscosity.jl:4-243,
+//                    flux_differencing.jl:4-361, limiter/subcell.jl:163-349, limiter/zhangshu.jl:4-45)
+//   update_kernel  = interface symmetrisation of the subcell coefficients, limited reassembly
+//                    and the SSP stage combine (subcell.jl:418-456,841-924, SSPRK33.jl:31-39)
+//
+// Thread mapping ("line threads"): an element with N1D x N1D nodes is handled by 2*N1D threads;
+// thread (d, line) owns one grid line of nodes along axis d (d=0: x-line `line` = fixed j,
+// d=1: y-line = fixed i).  On a Cartesian mesh every operator of the scheme couples nodes of one
+// line only (tensor-product SBP; S_x acts along x-lines, S_y along y-lines), the two end nodes of
+// a line are exactly its two face nodes, and the subcell limiter's running sums / coefficients
+// are per line as well.  So a line thread keeps its N1D nodal states in registers and does the
+// volume pairs, the two surface fluxes, the f_bar prefix sums and the limiting coefficients of
+// its line without talking to anyone; x- and y-lines meet through shared memory only for
+// rhsL = rhs_x + rhs_y (needed for u^L), the CFL sum and the final rhsU.
+// Direction is data, not control flow: both kinds of lines run the same instruction stream.
+#pragma once
+#include "physics.cuh"
+
+namespace p2de {
+
+enum { MODE_SUBCELL = 0, MODE_ZHANGSHU = 1, MODE_LOW = 2, MODE_HIGH = 3 };
+
+template <int N1D>
+struct Tables2D {
+  double SH[2][N1D][N1D][N1D];  // physical hybridized S: [d][line][a][b] = GJ_dd * Srsh_db[d][node(a), node(b)]
+  double S0[2][N1D][N1D];       // physical low-order S0 of pair (a+1, a): [d][line][a]
+  double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
+  double wq[N1D * N1D];
+  double minv[N1D * N1D];       // MinvVhT[i, i]
+  double minvf[4 * N1D];        // MinvVfT[fq2q[f], f]
+  int fq2q[4 * N1D];            // 0-based
+};
+
+struct MeshTopo {
+  long long K;
+  int Kx, Ky, periodic_x, periodic_y;
+  const int *mapP32;                 // generic mode: [K][Nfp] 0-based linear index; nullptr = structured
+  const int *bcflag;                 // generic mode: 0 none, >0 inflow (index+1 into Ival), -1 outflow
+  const double *Ival;                // generic mode: [nI][4]
+  const unsigned char *bc_type[4];   // structured mode, per side L,R,B,T: [len][N1D] 0 none,1 inflow,2 outflow
+  const double *bc_val[4];           // structured mode: [len][N1D][4]
+};
+
+struct StageArgs {
+  const double *Uq;
+  double *rhsL, *dF, *lpre;          // MODE_SUBCELL scratch
+  double *rhsU;                      // other modes
+  double *Lout;                      // MODE_ZHANGSHU: L[:, nstage]
+  double *rhsH_diag, *rhsL_diag;     // optional full fields (keep_diagnostics)
+  unsigned long long *dt_bits;       // stage 1: atomicMin target, pre-set to the cap
+  const double *dt_dev;              // limiter dt read from the device when use_dt_dev
+  double dt_host;
+  int use_dt_dev, nstage;
+  double gamma, ZEROTOL, POSTOL, zeta, CFL, Jq, blend;
+  int vol_flux, surf_low, surf_high; // P2DE_VOLFLUX_*, P2DE_SURFFLUX_*
+};
+
+struct UpdateArgs {
+  const double *rhsL, *dF, *lpre;    // MODE_SUBCELL inputs
+  const double *rhsU_in;             // other modes
+  double *Llocal_out;                // symmetrised L_local[:, :, :, nstage] or nullptr
+  double *rhsU_out;                  // or nullptr
+  const double *Uq_in, *resW;        // stage combine: Uq_out = a*resW + b*(Uq_in + dt*rhsU); Uq_out nullptr = skip
+  double *Uq_out;
+  double a, b;
+  const double *dt_dev;
+  double dt_host;
+  int use_dt_dev;
+  double Jq;
+};
+
+struct Nbr { long long kP; int fP; int bc; const double *ival; };
+
+template <int N1D>
+P2DE_DEV Nbr neighbor(const MeshTopo &M, long long k, int f) {
+  constexpr int Nfp = 4 * N1D;
+  Nbr nb;
+  nb.bc = 0; nb.ival = nullptr;
+  if (M.mapP32) {
+    int m = M.mapP32[k * Nfp + f];
+    nb.kP = m / Nfp; nb.fP = m % Nfp;
+    int fl = M.bcflag ? M.bcflag[k * Nfp + f] : 0;
+    if (fl > 0) { nb.bc = 1; nb.ival = M.Ival + 4ll * (fl - 1); }
+    else if (fl < 0) nb.bc = 2;
+    return nb;
+  }
+  int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
+  int F = f / N1D, a = f % N1D;
+  int jx = ix + (F == 0 ? -1 : F == 1 ? 1 : 0), jy = iy + (F == 2 ? -1 : F == 3 ? 1 : 0);
+  bool out = jx < 0 || jx >= M.Kx || jy < 0 || jy >= M.Ky;
+  if (out) {
+    bool wrap = F < 2 ? M.periodic_x : M.periodic_y;
+    if (wrap) { jx = (jx + M.Kx) % M.Kx; jy = (jy + M.Ky) % M.Ky; nb.kP = jx + (long long)jy * M.Kx; nb.fP = (F ^ 1) * N1D + a; }
+    else { nb.kP = k; nb.fP = f; }
+    if (M.bc_type[F]) {
+      int pos = F < 2 ? iy : ix;
+      int t = M.bc_type[F][pos * N1D + a];
+      if (t) { nb.bc = t; nb.ival = M.bc_val[F] + 4ll * (pos * N1D + a); }
+    }
+  } else { nb.kP = jx + (long long)jy * M.Kx; nb.fP = (F ^ 1) * N1D + a; }
+  return nb;
+}
+
+P2DE_DEV Cons2 load_cons(const double *p) {
+  const double2 *q = reinterpret_cast<const double2 *>(p);
+  double2 a = q[0], b = q[1];
+  Cons2 U; U.rho = a.x; U.m1 = a.y; U.m2 = b.x; U.E = b.y;
+  return U;
+}
+P2DE_DEV void store4(double *p, const double v[4]) {
+  double2 *q = reinterpret_cast<double2 *>(p);
+  q[0] = make_double2(v[0], v[1]); q[1] = make_double2(v[2], v[3]);
+}
+P2DE_DEV void cons_arr(const Cons2 &U, double v[4]) { v[0] = U.rho; v[1] = U.m1; v[2] = U.m2; v[3] = U.E; }
+
+// find_alpha, low_order_graph_viscosity.jl:299-327
+P2DE_DEV double find_alpha(double POSTOL, const Cons2 &ui, const Cons2 &ut) {
+  double alphaL = 0.0, alphaR = 1.0;
+  Cons2 s;
+  auto sub = [&](double al) { s.rho = al * ui.rho - ut.rho; s.m1 = al * ui.m1 - ut.m1; s.m2 = al * ui.m2 - ut.m2; s.E = al * ui.E - ut.E; };
+  sub(alphaR);
+  while (!(s.rho > POSTOL && rhoe2(s) > POSTOL) && alphaR < 1e300) { alphaR = 2 * alphaR; sub(alphaR); }
+  for (int it = 0; it < 50; ++it) {
+    double alphaM = (alphaL + alphaR) / 2;
+    sub(alphaM);
+    if (s.rho > POSTOL && rhoe2(s) > POSTOL) alphaR = alphaM; else alphaL = alphaM;
+  }
+  return alphaR;
+}
+
+template <int N1D, int MODE>
+constexpr int stage_smem_doubles_per_elem() {
+  constexpr int Nq = N1D * N1D;
+  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D;
+}
+
+template <int N1D, int MODE, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D)
+stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+             const __grid_constant__ Tables2D<N1D> Tc) {
+  constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1, NFLD = 12;
+  constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
+  constexpr int TBL = (sizeof(Tables2D<N1D>) + 7) / 8;
+  extern __shared__ double sm[];
+  Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
+  double *nodes = sm + TBL;                       // [NFLD][EPB*Nq]
+  double *partsL = nodes + NFLD * EPB * Nq;       // [EPB*Nq][2][4]
+  double *partsH = partsL + 8 * EPB * Nq;         // [EPB*Nq][2][4]   (not MODE_SUBCELL)
+  double *lamp = partsH + ((MODE == MODE_SUBCELL) ? 0 : 8 * EPB * Nq);  // [EPB*Nq][6]
+  double *lmin = lamp + 6 * EPB * Nq;             // [EPB][N1D]
+
+  const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
+  const long long k = (long long)blockIdx.x * EPB + el;
+  const bool active = k < M.K;
+  const int nbase = el * Nq;
+  const double gamma = A.gamma, gm1 = A.gamma - 1.0;
+
+  {
+    const double *src = reinterpret_cast<const double *>(&Tc);
+    for (int i = tid; i < TBL; i += EPB * TPE) sm[i] = src[i];
+  }
+  // ---- node phase: primitives, logs, axis wavespeeds of every volume node (once per node)
+  //      calculate_primitive_variables! flux_differencing.jl:39-52; wavespeed_estimate :48-62
+  if (active) {
+    for (int node = ln; node < Nq; node += TPE) {
+      Cons2 U = load_cons(A.Uq + (k * Nq + node) * 4);
+      double p = pfun2(gm1, U);
+      double *o = nodes + nbase + node;
+      constexpr int S = EPB * Nq;
+      o[0 * S] = U.rho; o[1 * S] = U.m1; o[2 * S] = U.m2; o[3 * S] = U.E;
+      o[4 * S] = U.m1 / U.rho; o[5 * S] = U.m2 / U.rho; o[6 * S] = p;
+      double beta = U.rho / (2 * p);
+      o[7 * S] = beta;
+      if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
+      if (DO_LOW) { o[10 * S] = wavespeed_dir(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir(gamma, gm1, U, 1); }
+    }
+  }
+  __syncthreads();
+
+  // ---- line phase
+  Cons2 U[N1D];
+  double rhsxL[N1D][4], rhsxH[N1D][4], BFL[2][4], BFH[2][4];
+  double lamPair[N1D], lamFace[2];
+  double wJ[N1D];
+  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
+  if (active) {
+    double uu[N1D], vv[N1D], pp[N1D];
+    constexpr int S = EPB * Nq;
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      int node = d == 0 ? a + line * N1D : line + a * N1D;
+      const double *o = nodes + nbase + node;
+      U[a].rho = o[0 * S]; U[a].m1 = o[1 * S]; U[a].m2 = o[2 * S]; U[a].E = o[3 * S];
+      uu[a] = o[4 * S]; vv[a] = o[5 * S]; pp[a] = o[6 * S];
+      wJ[a] = A.Jq * T.wq[node];
+    }
+    // neighbour data of the two end face nodes
+    Nbr nb[2];
+    Cons2 Unb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      int f = (2 * d + e) * N1D + line;
+      nb[e] = neighbor<N1D>(M, k, f);
+      Unb[e] = load_cons(A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4);
+    }
+    Cons2 Ut[2], Utnb[2];   // entropy-projected face states (rhs.jl:84-94), mine and the neighbour's
+    if (DO_HIGH || A.surf_low == P2DE_SURFFLUX_LF_PROJECTED) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        Ut[e] = entropy_roundtrip(gamma, gm1, U[e ? N1D - 1 : 0]);
+        Utnb[e] = entropy_roundtrip(gamma, gm1, Unb[e]);
+      }
+    }
+
+    if (DO_LOW) {
+      // ---- low-order graph-viscosity RHS along this line, low_order_graph_viscosity.jl:139-204
+      double ws[N1D], fl[N1D][4], Q0[N1D][4];
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        int node = d == 0 ? a + line * N1D : line + a * N1D;
+        ws[a] = nodes[(10 + d) * S + nbase + node];
+        flux_dir(U[a], uu[a], vv[a], pp[a], d, fl[a]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Q0[a][c] = 0.0;
+      }
+#pragma unroll
+      for (int a = 0; a < N1D - 1; ++a) {
+        const int i = a + 1, j = a;
+        double Sv = T.S0[d][line][a], nn = fabs(Sv);
+        double lam = nn * jl_max(ws[i], ws[j]);
+        lamPair[a] = lam;
+        double ui[4], uj[4];
+        cons_arr(U[i], ui); cons_arr(U[j], uj);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double F = 0.5 * (fl[i][c] + fl[j][c]);
+          double SF = 2.0 * Sv * F - lam * (uj[c] - ui[c]);
+          Q0[i][c] += SF; Q0[j][c] += -SF;
+        }
+      }
+      lamPair[N1D - 1] = 0.0;
+#pragma unroll
+      for (int a = 0; a < N1D; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rhsxL[a][c] = 0.0 - Q0[a][c];
+      // surface, :175-204
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ae = e ? N1D - 1 : 0;
+        double B = T.Bf[d][line][e], nn = fabs(B);
+        bool proj = A.surf_low == P2DE_SURFFLUX_LF_PROJECTED;
+        Cons2 Uf = proj ? Ut[e] : U[ae];
+        Cons2 UfP = proj ? Utnb[e] : Unb[e];
+        double wsM = proj ? wavespeed_dir(gamma, gm1, Uf, d) : ws[ae];
+        double wsP = wavespeed_dir(gamma, gm1, UfP, d);
+        double lamB = 0.5 * nn * jl_max(wsM, wsP);
+        Cons2 uP = UfP;
+        if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
+        else if (nb[e].bc == 2) uP = U[ae];
+        double fM[4], fP[4], uf[4], up[4];
+        if (proj) flux_dir(gm1, Uf, d, fM);
+        else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) fM[c] = fl[ae][c];
+        }
+        flux_dir(gm1, uP, d, fP);
+        cons_arr(Uf, uf); cons_arr(uP, up);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double fs = 0.5 * (fM[c] + fP[c]);
+          double bf = B * fs - lamB * (up[c] - uf[c]);
+          BFL[e][c] = bf;
+          rhsxL[ae][c] -= bf;
+        }
+        lamFace[e] = lamB;
+        if (proj && A.nstage == 1) {   // lambda_B_CFL(::LaxFriedrichsOnProjectedVal), :287-291
+          double alpha = find_alpha(A.POSTOL, U[ae], Uf);
+          lamFace[e] = alpha * lamB + 0.5 * nn * wsM;
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < N1D; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) rhsxL[a][c] = rhsxL[a][c] / wJ[a];   // scale_low_order_rhs_by_mass! :206-220
+    }
+
+    if (DO_HIGH) {
+      // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer)
+      double QF[N1D][4];
+#pragma unroll
+      for (int a = 0; a < N1D; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) QF[a][c] = 0.0;
+      if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
+        Prim2 q[N1D];
+#pragma unroll
+        for (int a = 0; a < N1D; ++a) {
+          int node = d == 0 ? a + line * N1D : line + a * N1D;
+          const double *o = nodes + nbase + node;
+          q[a].rho = U[a].rho; q[a].u = uu[a]; q[a].v = vv[a];
+          q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
+        }
+#pragma unroll
+        for (int j = 0; j < N1D; ++j)
+#pragma unroll
+          for (int i = j + 1; i < N1D; ++i) {
+            double F[4];
+            fS_dir(gm1, q[i], q[j], d, F);
+            double Sv = T.SH[d][line][i][j];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; QF[i][c] += Sf; QF[j][c] += -Sf; }
+          }
+      } else {   // CentralFlux, flux_differencing.jl:217-221
+        double fl[N1D][4];
+#pragma unroll
+        for (int a = 0; a < N1D; ++a) flux_dir(U[a], uu[a], vv[a], pp[a], d, fl[a]);
+#pragma unroll
+        for (int j = 0; j < N1D; ++j)
+#pragma unroll
+          for (int i = j + 1; i < N1D; ++i) {
+            double Sv = T.SH[d][line][i][j];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { double Sf = Sv * (0.5 * (fl[i][c] + fl[j][c])); QF[i][c] += Sf; QF[j][c] += -Sf; }
+          }
+      }
+      // surface, flux_differencing.jl:90-151,223-272
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ae = e ? N1D - 1 : 0;
+        double B = T.Bf[d][line][e], nn = fabs(B);
+        double LFc = 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
+        Cons2 uP = Utnb[e];
+        if (nb[e].bc == 1) { uP = load_cons(nb[e].ival); LFc = 0.0; }
+        else if (nb[e].bc == 2) { uP = U[ae]; LFc = 0.0; }
+        double fs[4];
+        if (A.surf_high == P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED) {
+          fS_dir(gm1, prim_of(gm1, Ut[e]), prim_of(gm1, uP), d, fs);
+        } else {
+          double fM[4], fP[4];
+          flux_dir(gm1, Ut[e], d, fM); flux_dir(gm1, uP, d, fP);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) fs[c] = 0.5 * (fM[c] + fP[c]);
+        }
+        double uf[4], up[4];
+        cons_arr(Ut[e], uf); cons_arr(uP, up);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
+      }
+      // assemble_rhs!, flux_differencing.jl:331-361 (LGL: M^-1 Vh^T is a scaled 0/1 gather; the
+      // hybridized face-volume pairs cancel identically and are not formed)
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        int node = d == 0 ? a + line * N1D : line + a * N1D;
+        double mi = T.minv[node];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double acc = mi * QF[a][c];
+          double b = 0.0;
+          if (a == 0) b = T.minvf[(2 * d) * N1D + line] * BFH[0][c];
+          if (a == N1D - 1) b += T.minvf[(2 * d + 1) * N1D + line] * BFH[1][c];
+          rhsxH[a][c] = -(acc + b) / A.Jq;
+        }
+      }
+    }
+
+    // ---- publish this line's share of rhsL / rhsH / lambda for the node-wise combination
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      int node = d == 0 ? a + line * N1D : line + a * N1D;
+      if (DO_LOW) store4(partsL + (nbase + node) * 8 + d * 4, rhsxL[a]);
+      if (MODE != MODE_SUBCELL && DO_HIGH) store4(partsH + (nbase + node) * 8 + d * 4, rhsxH[a]);
+      if (DO_LOW && A.nstage == 1) {
+        double *lp = lamp + (nbase + node) * 6 + d * 3;
+        lp[0] = a > 0 ? lamPair[a - 1] : 0.0;
+        lp[1] = lamPair[a];
+        lp[2] = a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0);
+        if (N1D == 1) lp[2] = lamFace[0] + lamFace[1];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- CFL: dt = min_i CFL * 0.5 * wJ_i / lambda_i, low_order_graph_viscosity.jl:222-281
+  if (DO_LOW && A.nstage == 1) {
+    double dtloc = INFINITY;
+    if (active && d == 0) {
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        int node = a + line * N1D;
+        const double *lp = lamp + (nbase + node) * 6;
+        double li = 0.0;
+        li += lp[3]; li += lp[0]; li += lp[1]; li += lp[4];   // partners ascending: y-, x-, x+, y+
+        li += lp[2]; li += lp[5];                             // q2fq: vertical face first, then horizontal
+        dtloc = jl_min(dtloc, A.CFL * 0.5 * wJ[a] / li);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dtloc = jl_min(dtloc, __shfl_xor_sync(0xffffffffu, dtloc, off));
+    if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
+  }
+
+  if (!active && MODE != MODE_ZHANGSHU) return;
+
+  if (MODE == MODE_SUBCELL) {
+    // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
+    //      limiting coefficients of this line's N1D+1 subcell faces (subcell.jl:248-349)
+    double dFv[NF][4];
+    {
+      double fH[4], fL[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { fH[c] = BFH[0][c]; fL[c] = BFL[0][c]; dFv[0][c] = fH[c] - fL[c]; }
+#pragma unroll
+      for (int s = 1; s < NF; ++s)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          fH[c] = fH[c] + wJ[s - 1] * rhsxH[s - 1][c];
+          fL[c] = fL[c] + wJ[s - 1] * rhsxL[s - 1][c];
+          dFv[s][c] = fH[c] - fL[c];
+        }
+    }
+    Cons2 uL[N1D];
+    double Lrho[N1D], Lrhoe[N1D];
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      int node = d == 0 ? a + line * N1D : line + a * N1D;
+      const double *pl = partsL + (nbase + node) * 8;
+      double r[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) r[c] = pl[c] + pl[4 + c];
+      uL[a].rho = U[a].rho + dtl * r[0]; uL[a].m1 = U[a].m1 + dtl * r[1];
+      uL[a].m2 = U[a].m2 + dtl * r[2]; uL[a].E = U[a].E + dtl * r[3];
+      Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
+      if (d == 0) {
+        store4(A.rhsL + (k * Nq + node) * 4, r);
+        if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+      }
+      if (d == 0 && A.rhsH_diag) {   // needs the y share of rhsH: recompute it is not possible here, see below
+      }
+    }
+    double lv[NF];
+#pragma unroll
+    for (int s = 0; s < NF; ++s) {
+      double l = 1.0;
+      if (s < N1D) {
+        double Pv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = -4 * dtl * dFv[s][c] / wJ[s];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], Pv, Lrho[s], Lrhoe[s]));
+      }
+      if (s >= 1) {
+        double Pv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = 4 * dtl * dFv[s][c] / wJ[s - 1];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
+      }
+      lv[s] = jl_min(l, A.blend);
+    }
+    double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
+#pragma unroll
+    for (int s = 0; s < NF; ++s) store4(dst + s * 4, dFv[s]);
+    double *ldst = A.lpre + (k * 2 + d) * (N1D * NF);
+#pragma unroll
+    for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
+    if (A.rhsH_diag) {   // diagnostics: each line adds its share of rhsH (rhsH_diag is zeroed by the host)
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        int node = d == 0 ? a + line * N1D : line + a * N1D;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) atomicAdd(A.rhsH_diag + (k * Nq + node) * 4 + c, rhsxH[a][c]);
+      }
+    }
+    return;
+  }
+
+  // ---- element-local limiters / no limiter: produce rhsU here
+  double rL[N1D][4], rH[N1D][4];
+  double lline = 1.0;
+  if (active && d == 0) {
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      int node = a + line * N1D;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        rL[a][c] = DO_LOW ? partsL[(nbase + node) * 8 + c] + partsL[(nbase + node) * 8 + 4 + c] : 0.0;
+        rH[a][c] = DO_HIGH ? partsH[(nbase + node) * 8 + c] + partsH[(nbase + node) * 8 + 4 + c] : 0.0;
+      }
+      if (MODE == MODE_ZHANGSHU) {   // zhangshu.jl:4-45
+        Cons2 uL;
+        uL.rho = U[a].rho + dtl * rL[a][0]; uL.m1 = U[a].m1 + dtl * rL[a][1];
+        uL.m2 = U[a].m2 + dtl * rL[a][2]; uL.E = U[a].E + dtl * rL[a][3];
+        double Pv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = dtl * (rH[a][c] - rL[a][c]);
+        lline = jl_min(lline, limiting_param_pos(A.ZEROTOL, uL, Pv, A.zeta * uL.rho, A.zeta * rhoe2(uL)));
+      }
+    }
+    if (MODE == MODE_ZHANGSHU) lmin[el * N1D + line] = lline;
+  }
+  double l = 1.0;
+  if (MODE == MODE_ZHANGSHU) {
+    __syncthreads();
+    if (!active) return;
+#pragma unroll
+    for (int j = 0; j < N1D; ++j) l = jl_min(l, lmin[el * N1D + j]);
+    if (ln == 0) A.Lout[k] = l;
+    l = jl_min(l, A.blend);
+  }
+  if (d == 0) {
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      int node = a + line * N1D;
+      double r[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        r[c] = MODE == MODE_ZHANGSHU ? (1 - l) * rL[a][c] + l * rH[a][c] : (MODE == MODE_LOW ? rL[a][c] : rH[a][c]);
+      store4(A.rhsU + (k * Nq + node) * 4, r);
+      if (A.rhsL_diag && DO_LOW) store4(A.rhsL_diag + (k * Nq + node) * 4, rL[a]);
+      if (A.rhsH_diag && DO_HIGH) store4(A.rhsH_diag + (k * Nq + node) * 4, rH[a]);
+    }
+  }
+}
+
+// subcell index of the neighbour's interface coefficient (limiter_utils.jl:123-181)
+template <int N1D>
+P2DE_DEV int lidx_of_face(int fP) {
+  constexpr int NF = N1D + 1;
+  int F = fP / N1D, a = fP % N1D;
+  if (F < 2) return (F == 0 ? 0 : N1D) + a * NF;   // x block: si + sj*(N1D+1)
+  return a + (F == 2 ? 0 : N1D) * N1D;             // y block: si + sj*N1D
+}
+
+template <int N1D, int MODE, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D)
+update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ MeshTopo M,
+              const __grid_constant__ Tables2D<N1D> Tc) {
+  constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1;
+  __shared__ double cy[EPB * Nq * 4];
+  const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
+  const long long k = (long long)blockIdx.x * EPB + el;
+  const bool active = k < M.K;
+  const int nbase = el * Nq;
+  double cx[N1D][4];
+  if (MODE == MODE_SUBCELL) {
+    if (active) {
+      // symmetrize_limiting_parameters!, subcell.jl:418-456, as a pure gather (min is idempotent)
+      double lv[NF];
+      const double *lsrc = A.lpre + (k * 2 + d) * (N1D * NF);
+#pragma unroll
+      for (int s = 0; s < NF; ++s) lv[s] = lsrc[d == 0 ? s + line * NF : line + s * N1D];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        Nbr nb = neighbor<N1D>(M, k, (2 * d + e) * N1D + line);
+        double lP = A.lpre[(nb.kP * 2 + d) * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
+        lv[e ? N1D : 0] = jl_min(lv[e ? N1D : 0], lP);
+      }
+      if (A.Llocal_out) {
+        double *ldst = A.Llocal_out + (k * 2 + d) * (N1D * NF);
+#pragma unroll
+        for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
+      }
+      // accumulate_f_bar_limited! + apply_subcell_limiter!, subcell.jl:841-924, in the form
+      // rhsU = rhsL + sum_d (l_{s+1} dF_{s+1} - l_s dF_s) / wJ   (f_lim = f_L + l (f_H - f_L))
+      const double *dsrc = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
+      double g[NF][4];
+#pragma unroll
+      for (int s = 0; s < NF; ++s) {
+        Cons2 t = load_cons(dsrc + s * 4);
+        g[s][0] = lv[s] * t.rho; g[s][1] = lv[s] * t.m1; g[s][2] = lv[s] * t.m2; g[s][3] = lv[s] * t.E;
+      }
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        int node = d == 0 ? a + line * N1D : line + a * N1D;
+        double wJ = A.Jq * Tc.wq[node];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) cx[a][c] = (g[a + 1][c] - g[a][c]) / wJ;
+        if (d == 1) store4(cy + (nbase + node) * 4, cx[a]);
+      }
+    }
+    __syncthreads();
+  }
+  if (!active || d != 0) return;
+  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+#pragma unroll
+  for (int a = 0; a < N1D; ++a) {
+    int node = a + line * N1D;
+    long long off = (k * Nq + node) * 4;
+    double r[4];
+    if (MODE == MODE_SUBCELL) {
+      Cons2 rl = load_cons(A.rhsL + off);
+      const double *y = cy + (nbase + node) * 4;
+      r[0] = rl.rho + (cx[a][0] + y[0]); r[1] = rl.m1 + (cx[a][1] + y[1]);
+      r[2] = rl.m2 + (cx[a][2] + y[2]); r[3] = rl.E + (cx[a][3] + y[3]);
+    } else {
+      Cons2 ru = load_cons(A.rhsU_in + off);
+      cons_arr(ru, r);
+    }
+    if (A.rhsU_out) store4(A.rhsU_out + off, r);
+    if (A.Uq_out) {   // SSPRK33.jl:31-39
+      Cons2 u = load_cons(A.Uq_in + off);
+      double un[4], uo[4];
+      cons_arr(u, uo);
+      if (A.b == 1.0 && A.a == 0.0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) un[c] = uo[c] + dt * r[c];
+      } else {
+        Cons2 w = load_cons(A.resW + off);
+        double wv[4];
+        cons_arr(w, wv);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) un[c] = A.a * wv[c] + A.b * (uo[c] + dt * r[c]);
+      }
+      store4(A.Uq_out + off, un);
+    }
+  }
+}
+
+}  // namespace p2de

@@ -1,0 +1,123 @@
+"""Problem setups shared by the tests, bench.py and smoke(): the reference's own scenarios
+(test/test_smoke.jl, examples/2D/*.jl) plus the synthetic double-Mach-reflection data of
+SURVEY.md §8d.  Pure host-side code (numpy); no oracle, no GPU."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from p2de_b200 import (BCData, CompressibleEulerIdealGas, ESLimitedLowOrderPos, GlobalConstant,
+                       LaxFriedrichsOnNodalVal, LaxFriedrichsOnProjectedVal, LimitingParameter,
+                       LobattoCollocation, NoEntropyProjectionLimiter, Param, PositivityBound,
+                       PostprocessingParameter, SubcellLimiter, TimesteppingParameter, ZhangShuLimiter,
+                       initialize_data, make_periodic, primitive_to_conservative, sample_initial_condition)
+
+
+def make_param(N, K, xL, xR, *, limiter=None, rhs=None, T=1.0, CFL=0.5, dt0=1e-2, t0=0.0, gamma=1.4,
+               zeta=0.1, eta=0.5, basis=None, dim=2):
+    return Param(N=N, K=K, xL=xL, xR=xR,
+                 global_constants=GlobalConstant(POSTOL=1e-14, ZEROTOL=5e-16),
+                 timestepping_param=TimesteppingParameter(T=T, CFL=CFL, dt0=dt0, t0=t0),
+                 limiting_param=LimitingParameter(zeta=zeta, eta=eta),
+                 postprocessing_param=PostprocessingParameter(output_interval=10000),
+                 equation=CompressibleEulerIdealGas(dim, gamma),
+                 rhs=rhs if rhs is not None else ESLimitedLowOrderPos(LaxFriedrichsOnNodalVal(), LaxFriedrichsOnProjectedVal()),
+                 approximation_basis=basis if basis is not None else LobattoCollocation(),
+                 entropyproj_limiter=NoEntropyProjectionLimiter(),
+                 rhs_limiter=limiter if limiter is not None else SubcellLimiter(bound=PositivityBound()))
+
+
+# ---- isentropic vortex: test/test_smoke.jl:6-20 -------------------------------------------
+def vortex_exact(eqn, x, y, t):
+    gamma = eqn.gamma
+    x0, y0, beta = 4.5, 5.0, 8.5
+    r2 = (x - x0 - t) ** 2 + (y - y0) ** 2
+    u = 1 - beta * np.exp(1 - r2) * (y - y0) / (2 * np.pi)
+    v = beta * np.exp(1 - r2) * (x - x0 - t) / (2 * np.pi)
+    rho = 1 - (1 / (8 * gamma * np.pi ** 2)) * (gamma - 1) / 2 * (beta * np.exp(1 - r2)) ** 2
+    rho = rho ** (1 / (gamma - 1))
+    p = rho ** gamma
+    return (rho, u, v, p)
+
+
+def vortex_ic(param, x, y):
+    return primitive_to_conservative(param.equation, vortex_exact(param.equation, x, y, param.timestepping_param.t0))
+
+
+def periodic_bc(param, md):
+    return BCData(make_periodic(md).mapP, [], [], [])
+
+
+def vortex(N=3, K=(5, 5), **kw):
+    """test/test_smoke.jl:53-67 (T=2e-2, CFL=1, dt0=1e-2 by default there)."""
+    kw.setdefault("T", 2e-2); kw.setdefault("CFL", 1.0); kw.setdefault("dt0", 1e-2)
+    return make_param(N, K, (0.0, 0.0), (10.0, 10.0), **kw), vortex_ic, periodic_bc
+
+
+# ---- Kelvin-Helmholtz: examples/2D/kelvin-helmholtz.jl:9-18 ------------------------------
+def kh_ic(param, x, y):
+    B = np.tanh(15 * y + 7.5) - np.tanh(15 * y - 7.5)
+    return primitive_to_conservative(param.equation, (0.5 + 0.75 * B, 0.5 * (B - 1), 0.1 * np.sin(2 * np.pi * x), 1.0 + 0 * x))
+
+
+def kelvin_helmholtz(N=3, K=(16, 16), **kw):
+    kw.setdefault("T", 10.0); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3)
+    return make_param(N, K, (-1.0, -1.0), (1.0, 1.0), **kw), kh_ic, periodic_bc
+
+
+# ---- Sedov-type blast: examples/2D/sedov.jl:9-20 ------------------------------------------
+def sedov(N=3, K=(16, 16), **kw):
+    kw.setdefault("T", 1.0); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3)
+    K1D = K[0]
+
+    def ic(param, x, y):
+        g = param.equation.gamma
+        r_ini = 4 * 3 / K1D
+        r = np.sqrt(x ** 2 + y ** 2)
+        p = np.where(r < r_ini, (g - 1) / math.pi / r_ini / r_ini, 1e-5)
+        return primitive_to_conservative(param.equation, (1.0 + 0 * x, 0 * x, 0 * x, p))
+    return make_param(N, K, (-1.5, -1.5), (1.5, 1.5), **kw), ic, periodic_bc
+
+
+# ---- synthetic double Mach reflection data (SURVEY.md §8d "S-DMR") -------------------------
+DMR_POST = (8.0, 8.25 * math.cos(math.pi / 6), -8.25 * math.sin(math.pi / 6), 116.5)
+DMR_PRE = (1.4, 0.0, 0.0, 1.0)
+
+
+def dmr_ic(param, x, y):
+    post = x < 1.0 / 6.0 + y / math.sqrt(3.0)
+    prim = tuple(np.where(post, a, b) for a, b in zip(DMR_POST, DMR_PRE))
+    return primitive_to_conservative(param.equation, prim)
+
+
+def dmr_bc(param, md):
+    """Left: Dirichlet inflow at the post-shock state (mapI/Ival); right, bottom, top: copy-out
+    (mapO), through the reference's BC surface (src/common/types/StateParam.jl:1-7)."""
+    eq = param.equation
+    Nfp = md.mapP.shape[1]
+    n = Nfp // 4
+    Kx, Ky = md.Kxy
+    k = np.arange(md.K)
+    ix, iy = k % Kx, k // Kx
+    idx = md.mapM                                    # 1-based linear indices [K, Nfp]
+    left = idx[ix == 0, 0:n].reshape(-1)
+    right = idx[ix == Kx - 1, n:2 * n].reshape(-1)
+    bottom = idx[iy == 0, 2 * n:3 * n].reshape(-1)
+    top = idx[iy == Ky - 1, 3 * n:4 * n].reshape(-1)
+    Ival = np.tile(np.array(primitive_to_conservative(eq, DMR_POST)), (len(left), 1))
+    return BCData(md.mapP, left, np.concatenate([right, bottom, top]), Ival)
+
+
+def dmr(N=3, K=(64, 16), **kw):
+    kw.setdefault("T", 0.2); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3)
+    return make_param(N, K, (0.0, 0.0), (4.0, 1.0), **kw), dmr_ic, dmr_bc
+
+
+def setup(problem):
+    """(param, ic, bc_callback) -> (param, rd, md, discrete_data, bcdata, U0)."""
+    param, ic, bcf = problem
+    rd, md, dd = initialize_data(param)
+    bc = bcf(param, md)
+    U0 = sample_initial_condition(param, md, ic)
+    return param, rd, md, dd, bc, U0

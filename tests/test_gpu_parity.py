@@ -1,0 +1,155 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Tolerances: one rhs! evaluation <= 1e-12 relative (max-norm scaled by the field
+max); limiting coefficients <= 1e-12 absolute and identical {l == 1} sets; sign(rho), sign(rho e)
+identical; after T steps a stated, problem-dependent tolerance.
+"""
+import numpy as np
+import pytest
+
+import problems as P
+from p2de_b200 import (EntropyStable, ESLimitedLowOrderPos, LaxFriedrichsOnNodalVal, LaxFriedrichsOnProjectedVal,
+                       ChandrashekarOnProjectedVal, LowOrderPositivity, PositivityBound, StandardDG,
+                       StdDGLimitedLowOrderPos, SubcellLimiter, TimeParam, ZhangShuLimiter, NoRHSLimiter)
+from p2de_b200 import types as T
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+def make_pair(problem, keep_diagnostics=True):
+    from oracle.oracle import Oracle
+    from p2de_b200.api import State
+    from p2de_b200.types import Solver
+    param, rd, md, dd, bc, U0 = P.setup(problem)
+    solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc, keep_diagnostics=keep_diagnostics)
+    st.set_state(U0)
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    return param, solver, st, orc, U0
+
+
+def check_rhs(problem, nstage=1, dt=None):
+    from p2de_b200.api import rhs
+    param, solver, st, orc, U0 = make_pair(problem)
+    tp = param.timestepping_param
+    dt = tp.CFL * tp.dt0 if dt is None else dt
+    dt_o = orc.rhs(tp.t0, dt, nstage)
+    dt_g = rhs(st, solver, None, TimeParam(t=tp.t0, dt=dt, nstage=nstage))
+    assert abs(dt_g - dt_o) <= 1e-13 * abs(dt_o), (dt_g, dt_o)
+    pre = st.preallocation
+    assert rel(pre.rhsU, orc.field("rhsU")) < RTOL
+    code = param.rhs.code
+    if code != T.RHS_FLUX_DIFF:
+        assert rel(pre.rhsL, orc.field("rhsL")) < RTOL
+    if code != T.RHS_LOW_ORDER_POSITIVITY:
+        assert rel(pre.rhsH, orc.field("rhsH")) < RTOL
+    if code == T.RHS_LIMITED_DG:
+        if param.rhs_limiter.code == T.LIMITER_SUBCELL:
+            Lg, Lo = pre.L_local[nstage - 1], orc.field("L_local")[nstage - 1]
+            assert np.abs(Lg - Lo).max() < 1e-12
+            assert np.array_equal(Lg == 1.0, Lo == 1.0)
+            return Lo
+        Lg, Lo = pre.L[nstage - 1], orc.field("L")[nstage - 1]
+        assert np.abs(Lg - Lo).max() < 1e-12
+        assert np.array_equal(Lg == 1.0, Lo == 1.0)
+        return Lo
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 4])
+@pytest.mark.parametrize("limiter", [SubcellLimiter(bound=PositivityBound()), ZhangShuLimiter()], ids=["subcell", "zhangshu"])
+def test_smoke_vortex_rhs(N, limiter):
+    """test/test_smoke.jl:44-67 scenario, one rhs! evaluation per stage index."""
+    for nstage in (1, 2, 3):
+        check_rhs(P.vortex(N=N, K=(5, 5), limiter=limiter), nstage=nstage)
+
+
+@pytest.mark.parametrize("N", [2, 3])
+def test_limiter_active_rhs(N):
+    """Large dt on a blast wave: the limiter must actually bite and still match."""
+    L = check_rhs(P.sedov(N=N, K=(8, 8)), dt=2e-2)
+    assert (L < 1.0).any() and (L < 0.5).any()
+    L = check_rhs(P.sedov(N=N, K=(8, 8), limiter=ZhangShuLimiter()), dt=2e-2)
+    assert (L < 1.0).any()
+
+
+@pytest.mark.parametrize("rhs_type", [
+    LowOrderPositivity(LaxFriedrichsOnNodalVal()),
+    LowOrderPositivity(LaxFriedrichsOnProjectedVal()),
+    EntropyStable(LaxFriedrichsOnProjectedVal()),
+    EntropyStable(ChandrashekarOnProjectedVal()),
+    StandardDG(),
+    ESLimitedLowOrderPos(LaxFriedrichsOnProjectedVal(), LaxFriedrichsOnProjectedVal()),
+    ESLimitedLowOrderPos(LaxFriedrichsOnNodalVal(), ChandrashekarOnProjectedVal()),
+    StdDGLimitedLowOrderPos(),
+], ids=["low-nodal", "low-proj", "es-lf", "es-chand", "stddg", "lim-lowproj", "lim-chand", "lim-central"])
+def test_rhs_types(rhs_type):
+    lim = NoRHSLimiter() if rhs_type.code != T.RHS_LIMITED_DG else SubcellLimiter()
+    check_rhs(P.kelvin_helmholtz(N=3, K=(6, 6), rhs=rhs_type, limiter=lim))
+
+
+def test_dmr_boundary_conditions_rhs():
+    """Inflow (mapI/Ival) + outflow (mapO) faces through the reference's BC surface."""
+    L = check_rhs(P.dmr(N=3, K=(16, 4)), dt=5e-4)
+    check_rhs(P.dmr(N=2, K=(12, 4), limiter=ZhangShuLimiter()), dt=5e-4)
+    assert (L < 1.0).any()
+
+
+def run_both(problem, nsteps):
+    param, solver, st, orc, U0 = make_pair(problem, keep_diagnostics=False)
+    t_o = t_g = param.timestepping_param.t0
+    for _ in range(nsteps):
+        dto = orc.ssp33_step(t_o); t_o += dto
+        dtg = st.ssp33_step(t_g); t_g += dtg
+        assert abs(dtg - dto) <= 1e-10 * dto
+    return param, st.preallocation.Uq, orc.get_state(), st, orc
+
+
+@pytest.mark.parametrize("limiter", [SubcellLimiter(), ZhangShuLimiter()], ids=["subcell", "zhangshu"])
+def test_ssp33_vortex_steps(limiter):
+    """10 SSP33! steps on the smooth vortex: <= 1e-9 relative."""
+    param, Ug, Uo, st, orc = run_both(P.vortex(N=3, K=(8, 8), limiter=limiter, CFL=0.5, T=10.0), 10)
+    assert rel(Ug, Uo) < 1e-9
+    assert abs(st.reduce(T.REDUCE_CONSERVATION) - orc.reduce(0)) < 1e-10 * abs(orc.reduce(0))
+
+
+def test_ssp33_dmr_steps_positivity():
+    """20 steps of the DMR-type data: positivity signs identical, states within 1e-7 relative
+    (the limiter's thresholds amplify last-bit differences across a Mach-10 shock)."""
+    param, Ug, Uo, st, orc = run_both(P.dmr(N=3, K=(32, 8)), 20)
+    assert rel(Ug, Uo) < 1e-7
+    rhoe = lambda U: U[..., 3] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) / U[..., 0]
+    assert np.array_equal(np.sign(Ug[..., 0]), np.sign(Uo[..., 0])) and (Ug[..., 0] > 0).all()
+    assert np.array_equal(np.sign(rhoe(Ug)), np.sign(rhoe(Uo))) and (rhoe(Ug) > 0).all()
+    assert st.reduce(T.REDUCE_MIN_RHO) > 0 and st.reduce(T.REDUCE_MIN_RHOE) > 0
+
+
+def test_generic_mapP_path_matches_structured():
+    """A mapP that is not the structured pattern (elements renumbered) goes through the generic
+    gather tables and must give the same answer as the oracle."""
+    from oracle.oracle import Oracle
+    from p2de_b200.api import State, rhs
+    from p2de_b200.types import Solver, BCData
+    param, rd, md, dd, bc, U0 = P.setup(P.vortex(N=2, K=(4, 4)))
+    K, Nfp = bc.mapP.shape
+    rng = np.random.default_rng(0)
+    perm = rng.permutation(K)                 # new element index -> old element index
+    inv = np.argsort(perm)
+    old = bc.mapP[perm] - 1                   # [new k, f] -> old linear index
+    mapP_new = inv[old // Nfp] * Nfp + old % Nfp + 1
+    bc2 = BCData(mapP_new, [], [], [])
+    solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc2, keep_diagnostics=True)
+    st.set_state(U0[perm])
+    orc = Oracle(param, dd, bc2); orc.set_state(U0[perm])
+    dt = 5e-3
+    dto = orc.rhs(0.0, dt, 1)
+    dtg = rhs(st, solver, None, TimeParam(t=0.0, dt=dt, nstage=1))
+    assert abs(dtg - dto) <= 1e-13 * dto
+    assert rel(st.preallocation.rhsU, orc.field("rhsU")) < RTOL

@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""bench.py — DOF-updates/s (FP64, per RK stage) of the per-stage DG RHS + limiter hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one iteration of the SSP33! time loop (3 stages: rhs! + limiter + SSP combine) over
+the whole synthetic mesh.  `value` = 3 * K_elements * Nq * n_steps / time, state resident in HBM.
+`e2e` = the same through the C ABI with HOST buffers: every step copies the state host->device
+(pinned memory), runs the 3 stages and copies the state back.
+`--impl reference` times the CPU oracle (a C++/OpenMP restatement of the reference's Julia
+algorithm, SURVEY.md §8c: Julia is not installed on this image) on a bounded sample.
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "DOF-updates/sec (FP64, per RK stage)"
+UNIT = "DOF-updates/s"
+
+# name -> (problem factory name in tests/problems.py, N, (Kx, Ky) per GPU, limiter)
+WORKLOADS = {
+    "S-DMR": dict(problem="dmr", N=3, K=(4096, 1024), note="2D double-Mach-reflection data, N=3 LGL, 4096x1024 quads (4.19M elements, 67.1M nodes), subcell positivity limiter; inflow/outflow BCs through the reference's BCData"),
+    "S-DMR-small": dict(problem="dmr", N=3, K=(512, 128), note="S-DMR at 512x128"),
+    "S-KH": dict(problem="kelvin_helmholtz", N=4, K=(4096, 512), note="Kelvin-Helmholtz, N=4 LGL, 4096x512 per GPU, periodic"),
+}
+CPU_SAMPLE_K = (512, 128)    # bounded sample of the same workload for the CPU arm (39 kB of state per element)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes_per_dof(N, limiter_code):
+    """SURVEY.md §8d / DESIGN.md §5: Uq read 32 + resW 32 + Uq write 32 + L_local write."""
+    n = N + 1
+    if limiter_code == 2:
+        return 96.0 + 8.0 * 2 * n * (n + 1) / (n * n)
+    return 96.0 + 8.0 / (n * n)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def build_problem(workload, K):
+    import problems as P
+    from p2de_b200 import initialize_data
+    w = WORKLOADS[workload]
+    problem = getattr(P, w["problem"])(N=w["N"], K=K)
+    param, ic, bcf = problem
+    return param, ic, bcf
+
+
+def boundary_data_light(param, workload):
+    """BCData for the structured (mapP == NULL) path without building per-element arrays."""
+    import problems as P
+    from p2de_b200 import BCData, primitive_to_conservative
+    w = WORKLOADS[workload]
+    if w["problem"] != "dmr":
+        return BCData(np.zeros((0, 0), dtype=np.int64), [], [], []), (True, True)
+    n = param.N + 1
+    Nfp = 4 * n
+    Kx, Ky = param.K
+    a = np.arange(n)
+
+    def idx(k, face):
+        return (k[:, None] * Nfp + face * n + a[None, :] + 1).reshape(-1)
+    rows, cols = np.arange(Ky), np.arange(Kx)
+    left, right = idx(rows * Kx, 0), idx(rows * Kx + Kx - 1, 1)
+    bottom, top = idx(cols, 2), idx((Ky - 1) * Kx + cols, 3)
+    Ival = np.tile(np.array(primitive_to_conservative(param.equation, P.DMR_POST)), (len(left), 1))
+    return BCData(np.zeros((0, 0), dtype=np.int64), left, np.concatenate([right, bottom, top]), Ival), (False, False)
+
+
+def initial_state(param, rd, ic, out):
+    """Fill out[K, Nq, Nc] chunk by chunk (the full coordinate arrays are never materialised)."""
+    from p2de_b200 import element_nodes
+    K = out.shape[0]
+    chunk = 1 << 18
+    for s in range(0, K, chunk):
+        k = np.arange(s, min(K, s + chunk))
+        xq, yq = element_nodes(param, rd, k)
+        out[s:s + len(k)] = np.stack([np.broadcast_to(c, xq.shape) for c in ic(param, xq, yq)], axis=-1)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from p2de_b200 import initialize_data
+    from p2de_b200.api import State
+    from p2de_b200.types import Solver
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = WORKLOADS[args.workload]
+    K = w["K"]
+    param, ic, _ = build_problem(args.workload, K)
+    rd, md, dd = initialize_data(param, light=True)
+    bc, periodic = boundary_data_light(param, args.workload)
+    solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc, device=local, structured_bc=periodic)
+    stream = torch.cuda.current_stream()
+    st.set_stream(stream.cuda_stream)
+    sz = dd.sizes
+    host = torch.empty((sz.K, sz.Nq, sz.Nc), dtype=torch.float64, pin_memory=True)
+    initial_state(param, rd, ic, host.numpy())
+    st.set_state_async_ptr(host.data_ptr())
+    st.synchronize()
+    t0 = param.timestepping_param.t0
+    nbytes = host.numel() * 8
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`)
+    t = t0
+    for _ in range(args.warmup):
+        t += st.ssp33_step(t)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    st.profile(True)
+    launches0 = st.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    tt = t
+    for _ in range(args.steps):
+        st.ssp33_step_async(tt)
+        tt += 0.0          # t only enters through the (T - t) cap; T is far away for the bench configs
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = st.kernel_launch_count() - launches0
+    stage_ms, n_stage = st.profile_get(0)
+    upd_ms, n_upd = st.profile_get(1)
+    st.profile(False)
+    clocks = sampler.stop()
+    if world > 1:
+        tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ms = float(tm.item())
+    dof_per_stage = sz.K * sz.Nq * world
+    value = 3.0 * dof_per_stage * args.steps / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers
+    st.set_state_async_ptr(host.data_ptr()); st.synchronize()
+    for _ in range(max(1, min(args.warmup, 2))):
+        st.set_state_async_ptr(host.data_ptr()); st.ssp33_step_async(t0); st.get_state_async_ptr(host.data_ptr())
+    initial_state(param, rd, ic, host.numpy())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(1, min(args.steps, 5))
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        st.set_state_async_ptr(host.data_ptr())
+        st.ssp33_step_async(t0)
+        st.get_state_async_ptr(host.data_ptr())
+    e1.record(stream)
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tm = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tm.item())
+    e2e_value = 3.0 * dof_per_stage * e2e_steps / (e2e_ms * 1e-3)
+
+    peak, peak_src = peaks()
+    A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
+    stage_total_ms = (stage_ms + upd_ms) / max(n_stage, 1)          # both kernels of one stage, device time
+    achieved = A * sz.K * sz.Nq / (stage_total_ms * 1e-3) / 1e9 if n_stage else None
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["note"], "N": param.N, "elements_per_gpu": list(K),
+                   "dof_updates_per_stage": dof_per_stage, "stages_per_step": 3,
+                   "l2": "state arrays (2.1 GB each at S-DMR) are far larger than the 126 MB L2; no explicit flush",
+                   "parallelism": f"dp{world} (y-stripes)" if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "kernel": "stage_kernel + update_kernel (one RK stage)", "algorithmic_bytes_per_dof_update": A,
+                     "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
+                     "stage_kernel_share": stage_ms / max(stage_ms + upd_ms, 1e-30)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.workload, steps=2, warmup=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, steps, warmup):
+    """The oracle (C++/OpenMP restatement of the reference's CPU algorithm) on all host cores,
+    on a bounded sample of the same workload."""
+    import problems as P
+    from oracle.oracle import Oracle, lib as oracle_lib
+    K = CPU_SAMPLE_K
+    param, ic, bcf = build_problem(workload, K)
+    param_, rd, md, dd, bc, U0 = P.setup((param, ic, bcf))
+    cores = os.cpu_count() or 1
+    orc = Oracle(param, dd, bc, threads=cores)
+    orc.set_state(U0)
+    t = param.timestepping_param.t0
+    for _ in range(warmup):
+        t += orc.ssp33_step(t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        t += orc.ssp33_step(t)
+    el = time.perf_counter() - t0
+    sz = dd.sizes
+    v = 3.0 * sz.K * sz.Nq * steps / el
+    return {"value": v, "unit": UNIT, "cores": int(oracle_lib().oracle_max_threads()), "kind": "port",
+            "sample": f"{workload} data on a {K[0]}x{K[1]} mesh (N={param.N}, {sz.K * sz.Nq} nodes), {steps} SSP-RK3 steps after {warmup} warm-up; "
+                      "C++/OpenMP restatement of the reference's CPU algorithm (Julia is not installed on this image)",
+            "ms_per_step": el / steps * 1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cb = cpu_baseline(args.workload, steps=args.steps, warmup=args.warmup)
+    w = WORKLOADS[args.workload]
+    out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": args.workload, "description": w["note"], "N": w["N"], "elements_per_gpu": list(w["K"]),
+                      "sample_elements": list(CPU_SAMPLE_K)},
+           "cpu_baseline": cb,
+           "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="S-DMR", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

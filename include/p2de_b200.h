@@ -210,6 +210,12 @@ int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out);
 int32_t p2de_comm_unique_id(uint8_t id_out[128]);
 int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8_t unique_id[128]);
 
+/* Per-kernel device timing for bench.py's roofline: while enabled, every launch of the two
+ * hot kernels is bracketed by a CUDA event pair on the handle's stream.  kernel_id 0 =
+ * stage_kernel, 1 = update_kernel.  p2de_profile(h, x) also clears the records.              */
+int32_t p2de_profile(p2de_handle *h, int32_t enable);
+int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, int64_t *launches);
+
 /* Number of kernels this handle has launched so far (bench.py reports it).            */
 int64_t p2de_kernel_launch_count(const p2de_handle *h);
 /* Device pointer of Uq (for zero-copy wrapping by the host, e.g. torch.from_dlpack).  */

@@ -147,6 +147,20 @@ class State:
         _lib.check(self.L, self.h, self.L.p2de_reduce(self.h, what, C.byref(out)))
         return out.value
 
+    def profile(self, enable: bool):
+        _lib.check(self.L, self.h, self.L.p2de_profile(self.h, int(enable)))
+
+    def profile_get(self, kernel_id: int):
+        ms, n = C.c_double(), C.c_int64()
+        _lib.check(self.L, self.h, self.L.p2de_profile_get(self.h, kernel_id, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def set_state_async_ptr(self, host_ptr: int):
+        _lib.check(self.L, self.h, self.L.p2de_set_state_async(self.h, C.c_void_p(host_ptr)))
+
+    def get_state_async_ptr(self, host_ptr: int):
+        _lib.check(self.L, self.h, self.L.p2de_get_state_async(self.h, C.c_void_p(host_ptr)))
+
     def kernel_launch_count(self) -> int:
         return int(self.L.p2de_kernel_launch_count(self.h))
 

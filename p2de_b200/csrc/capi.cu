@@ -64,6 +64,10 @@ struct p2de_handle {
   double *bc_val[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void *> owned;
   double last_dt = 0;
+  // optional per-kernel timing (p2de_profile): one event pair per launch, on h->stream
+  bool profiling = false;
+  struct ProfRec { cudaEvent_t a, b; int kid; };
+  std::vector<ProfRec> prof;
 };
 
 namespace {
@@ -91,6 +95,22 @@ int dev_alloc(p2de_handle *h, T **p, size_t n) {
   h->owned.push_back(q);
   *p = static_cast<T *>(q);
   return 0;
+}
+
+void prof_begin(p2de_handle *h, int kid) {
+  if (!h->profiling) return;
+  p2de_handle::ProfRec r{};
+  r.kid = kid;
+  cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, h->stream);
+  h->prof.push_back(r);
+}
+void prof_end(p2de_handle *h) {
+  if (h->profiling && !h->prof.empty()) cudaEventRecord(h->prof.back().b, h->stream);
+}
+void prof_clear(p2de_handle *h) {
+  for (auto &r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  h->prof.clear();
 }
 
 template <int N1D>
@@ -301,7 +321,9 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
     attr_set = true;
   }
   unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  prof_begin(h, 0);
   kern<<<grid, EPB * TPE, smem, h->stream>>>(A, h->topo, tables<N1D>(h));
+  prof_end(h);
   CU(h, cudaGetLastError());
   h->launches++;
   return 0;
@@ -329,7 +351,9 @@ template <int N1D, int MODE>
 int launch_update_t(p2de_handle *h, const UpdateArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
   unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  prof_begin(h, 1);
   update_kernel<N1D, MODE, EPB><<<grid, EPB * TPE, 0, h->stream>>>(A, h->topo, tables<N1D>(h));
+  prof_end(h);
   CU(h, cudaGetLastError());
   h->launches++;
   return 0;
@@ -498,6 +522,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
 int32_t p2de_destroy(p2de_handle *h) {
   if (!h) return P2DE_OK;
   cudaSetDevice(h->device);
+  prof_clear(h);
   for (void *p : h->owned) cudaFree(p);
   delete h;
   return P2DE_OK;
@@ -640,6 +665,27 @@ int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out) {
   double r = what == P2DE_REDUCE_CONSERVATION ? 0.0 : std::numeric_limits<double>::infinity();
   for (double v : part) r = what == P2DE_REDUCE_CONSERVATION ? r + v : std::fmin(r, v);
   *out = r;
+  return P2DE_OK;
+}
+
+int32_t p2de_profile(p2de_handle *h, int32_t enable) {
+  if (!h) return P2DE_ERR_ARG;
+  CU(h, cudaStreamSynchronize(h->stream));
+  prof_clear(h);
+  h->profiling = enable != 0;
+  return P2DE_OK;
+}
+int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, int64_t *launches) {
+  if (!h || !total_ms || !launches) return P2DE_ERR_ARG;
+  CU(h, cudaStreamSynchronize(h->stream));
+  double tot = 0; int64_t n = 0;
+  for (auto &r : h->prof) {
+    if (r.kid != kernel_id) continue;
+    float ms = 0;
+    CU(h, cudaEventElapsedTime(&ms, r.a, r.b));
+    tot += ms; ++n;
+  }
+  *total_ms = tot; *launches = n;
   return P2DE_OK;
 }
 

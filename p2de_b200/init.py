@@ -313,9 +313,9 @@ def build_operators(param: Param, rd: RefElemData, md: MeshData) -> Discretizati
     q2fq = [[f + 1 for f in range(Nfp) if Vf_low[f, i] == 1.0] for i in range(Nq)]
 
     K = num_elements(param)
-    Jq = md.J @ Vq.T if False else md.J.copy()               # Vq = I
+    Jq = md.J                                                # Jq = Vq * J with Vq = I (init.jl:259,270)
     GJ = (md.rxJ,) if dim == 1 else (md.rxJ, md.sxJ, md.ryJ, md.syJ)
-    GJh = tuple(np.full((K, Nh), g) for g in GJ) if K * Nh <= (1 << 24) else tuple(
+    GJh = tuple(np.full((K, Nh), g) for g in GJ) if K * Nh <= (1 << 22) else tuple(
         np.broadcast_to(np.float64(g), (K, Nh)) for g in GJ)
     sizes = SizeData(K=K, N1D=n, Nd=dim, Nc=dim + 2, Np=rd.VDM.shape[1], Nq=Nq, Nfp=Nfp, Nh=Nh, Ns=3)
     geom = GeomData(J=md.J, Jq=Jq, GJh=GJh)
@@ -326,10 +326,39 @@ def build_operators(param: Param, rd: RefElemData, md: MeshData) -> Discretizati
     return Discretization(sizes=sizes, geom=geom, ops=ops)
 
 
-def initialize_data(param: Param):
+def light_mesh(param: Param, rd: RefElemData) -> MeshData:
+    """Uniform-mesh metadata WITHOUT per-element arrays (J is a zero-memory broadcast view and the
+    coordinate / map arrays are None): for meshes of millions of elements that are handed to the
+    library in structured form (`p2de_bcdata.mapP == NULL`, `p2de_geometry.uniform`)."""
+    dim, n = rd.dim, param.N + 1
+    if dim == 1:
+        Kx, Ky = int(param.K), 1
+        hx = (float(param.xR) - float(param.xL)) / Kx
+        J, GJ = hx / 2.0, (1.0, 0.0, 0.0, 0.0)
+    else:
+        Kx, Ky = int(param.K[0]), int(param.K[1])
+        hx, hy = (param.xR[0] - param.xL[0]) / Kx, (param.xR[1] - param.xL[1]) / Ky
+        J, GJ = hx * hy / 4.0, (hy / 2.0, 0.0, 0.0, hx / 2.0)
+    K = Kx * Ky
+    return MeshData(K=K, xq=None, yq=None, xf=None, yf=None, mapM=None, mapP=None, mapB=None,
+                    J=np.broadcast_to(np.float64(J), (K, n ** dim)), rxJ=GJ[0], sxJ=GJ[1], ryJ=GJ[2], syJ=GJ[3],
+                    Kxy=(Kx, Ky), is_periodic=(False, False))
+
+
+def element_nodes(param: Param, rd: RefElemData, k: np.ndarray):
+    """(xq, yq) [len(k), Nq] of the elements `k` of the uniform mesh (same arithmetic as uniform_mesh)."""
+    Kx, Ky = int(param.K[0]), int(param.K[1])
+    hx, hy = (param.xR[0] - param.xL[0]) / Kx, (param.xR[1] - param.xL[1]) / Ky
+    ix, iy = k % Kx, k // Kx
+    xq = param.xL[0] + hx * (ix[:, None] + 0.5 * (rd.rq[None, :] + 1.0))
+    yq = param.xL[1] + hy * (iy[:, None] + 0.5 * (rd.sq[None, :] + 1.0))
+    return xq, yq
+
+
+def initialize_data(param: Param, light: bool = False):
     """initialize_data / initialize_reference_data (init.jl:62-103)."""
     rd = RefElemData(param.equation.dim, param.N, param.approximation_basis.code)
-    md = uniform_mesh(param, rd)
+    md = light_mesh(param, rd) if light else uniform_mesh(param, rd)
     return rd, md, build_operators(param, rd, md)
 
 

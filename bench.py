@@ -36,6 +36,7 @@ UNIT = "DOF-updates/s"
 WORKLOADS = {
     "S-DMR": dict(problem="dmr", N=3, K=(4096, 1024), note="2D double-Mach-reflection data, N=3 LGL, 4096x1024 quads (4.19M elements, 67.1M nodes), subcell positivity limiter; inflow/outflow BCs through the reference's BCData"),
     "S-DMR-small": dict(problem="dmr", N=3, K=(512, 128), note="S-DMR at 512x128"),
+    "S-DMR-mid": dict(problem="dmr", N=3, K=(1024, 512), note="S-DMR at 1024x512 (profiling size)"),
     "S-KH": dict(problem="kelvin_helmholtz", N=4, K=(4096, 512), note="Kelvin-Helmholtz, N=4 LGL, 4096x512 per GPU, periodic"),
 }
 CPU_SAMPLE_K = (512, 128)    # bounded sample of the same workload for the CPU arm (39 kB of state per element)

@@ -109,6 +109,12 @@ typedef struct p2de_config {
   int32_t shockcapture;     /* P2DE_SHOCKCAPTURE_*                                       */
   int32_t keep_diagnostics; /* !=0: also keep rhsH/rhsL (costs 64 B per node per stage)  */
   int32_t device;           /* CUDA device ordinal; -1 = current device                  */
+  int32_t lgl_projection_roundtrip; /* Lobatto face states u_tilde_f = u(v(U_node)) (rhs.jl:84-94).
+                               0 (default): use U_node itself - Vf is a 0/1 gather so the entropy
+                               projection is the identity up to rounding (~1e-16; the reference's
+                               own TODO at rhs.jl:107).  1: evaluate the log/pow/exp round trip
+                               like the reference does.                                     */
+  int32_t _reserved;
   double hennemann_a, hennemann_c; /* HennemannShockCapture(a, c)  Solver.jl:68-74       */
   double bound_beta;        /* PositivityAndRelaxedCellEntropyBound(beta)                */
   double gamma;             /* CompressibleIdealGas.gamma                                */

@@ -27,7 +27,7 @@ class Config(C.Structure):
         ("rhs_type", C.c_int32), ("vol_flux", C.c_int32), ("surf_flux_low", C.c_int32),
         ("surf_flux_high", C.c_int32), ("proj_limiter", C.c_int32), ("limiter", C.c_int32),
         ("bound", C.c_int32), ("shockcapture", C.c_int32), ("keep_diagnostics", C.c_int32),
-        ("device", C.c_int32),
+        ("device", C.c_int32), ("lgl_projection_roundtrip", C.c_int32), ("_reserved", C.c_int32),
         ("hennemann_a", C.c_double), ("hennemann_c", C.c_double), ("bound_beta", C.c_double),
         ("gamma", C.c_double), ("POSTOL", C.c_double), ("ZEROTOL", C.c_double),
         ("zeta", C.c_double), ("eta", C.c_double),
@@ -76,7 +76,8 @@ class PackedProblem:
     """Owns every buffer the four ABI structs point into (keeps them alive)."""
 
     def __init__(self, param: Param, dd: Discretization, bc: Optional[BCData], *, Kx_Ky=None,
-                 structured_bc=None, uniform_geometry=True, keep_diagnostics=False, device=-1):
+                 structured_bc=None, uniform_geometry=True, keep_diagnostics=False, device=-1,
+                 lgl_projection_roundtrip=False):
         sz, ops, geom = dd.sizes, dd.ops, dd.geom
         eq = param.equation
         self.keep: Dict[str, Any] = {}
@@ -109,6 +110,7 @@ class PackedProblem:
         cfg.hennemann_a, cfg.hennemann_c = float(getattr(sc, "a", 0.5)), float(getattr(sc, "c", 1.8))
         cfg.keep_diagnostics = int(keep_diagnostics)
         cfg.device = device
+        cfg.lgl_projection_roundtrip = int(lgl_projection_roundtrip)
         cfg.gamma = eq.gamma
         cfg.POSTOL, cfg.ZEROTOL = param.global_constants.POSTOL, param.global_constants.ZEROTOL
         cfg.zeta, cfg.eta = param.limiting_param.zeta, param.limiting_param.eta

@@ -93,11 +93,12 @@ class State:
     """`State(preallocation, cache)` of the reference; the caches live on the device."""
 
     def __init__(self, solver: Solver, bcdata: BCData, *, keep_diagnostics=False, device=-1,
-                 structured_bc=None, Kx_Ky=None):
+                 structured_bc=None, Kx_Ky=None, lgl_projection_roundtrip=False):
         self.L = _lib.load()
         self.sizes = solver.discrete_data.sizes
         self.packed = PackedProblem(solver.param, solver.discrete_data, bcdata, keep_diagnostics=keep_diagnostics,
-                                    device=device, structured_bc=structured_bc, Kx_Ky=Kx_Ky)
+                                    device=device, structured_bc=structured_bc, Kx_Ky=Kx_Ky,
+                                    lgl_projection_roundtrip=lgl_projection_roundtrip)
         h = C.c_void_p()
         rc = self.L.p2de_create(C.byref(self.packed.cfg), C.byref(self.packed.ops), C.byref(self.packed.geom),
                                 C.byref(self.packed.bc), C.byref(h))

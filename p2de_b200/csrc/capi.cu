@@ -384,6 +384,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.dt_host = dt_host; A.use_dt_dev = use_dt_dev; A.nstage = nstage;
   A.gamma = h->cfg.gamma; A.ZEROTOL = h->cfg.ZEROTOL; A.POSTOL = h->cfg.POSTOL; A.zeta = h->cfg.zeta;
   A.CFL = h->cfg.CFL; A.Jq = h->Jq; A.blend = 1.0;
+  A.roundtrip = h->cfg.lgl_projection_roundtrip;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   return A;
 }

@@ -59,6 +59,7 @@ struct StageArgs {
   int use_dt_dev, nstage;
   double gamma, ZEROTOL, POSTOL, zeta, CFL, Jq, blend;
   int vol_flux, surf_low, surf_high; // P2DE_VOLFLUX_*, P2DE_SURFFLUX_*
+  int roundtrip;                     // evaluate u(v(U)) at LGL face nodes instead of using U
 };
 
 struct UpdateArgs {
@@ -213,8 +214,12 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     if (DO_HIGH || A.surf_low == P2DE_SURFFLUX_LF_PROJECTED) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        Ut[e] = entropy_roundtrip(gamma, gm1, U[e ? N1D - 1 : 0]);
-        Utnb[e] = entropy_roundtrip(gamma, gm1, Unb[e]);
+        Ut[e] = U[e ? N1D - 1 : 0];
+        Utnb[e] = Unb[e];
+        if (A.roundtrip) {
+          Ut[e] = entropy_roundtrip(gamma, gm1, Ut[e]);
+          Utnb[e] = entropy_roundtrip(gamma, gm1, Utnb[e]);
+        }
       }
     }
 

@@ -22,22 +22,26 @@ def rel(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
 
 
-def make_pair(problem, keep_diagnostics=True):
+ROUNDTRIP = False   # default build option: LGL face states are the nodal states
+
+
+def make_pair(problem, keep_diagnostics=True, roundtrip=None):
     from oracle.oracle import Oracle
     from p2de_b200.api import State
     from p2de_b200.types import Solver
     param, rd, md, dd, bc, U0 = P.setup(problem)
     solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
-    st = State(solver, bc, keep_diagnostics=keep_diagnostics)
+    st = State(solver, bc, keep_diagnostics=keep_diagnostics,
+               lgl_projection_roundtrip=ROUNDTRIP if roundtrip is None else roundtrip)
     st.set_state(U0)
     orc = Oracle(param, dd, bc)
     orc.set_state(U0)
     return param, solver, st, orc, U0
 
 
-def check_rhs(problem, nstage=1, dt=None):
+def check_rhs(problem, nstage=1, dt=None, roundtrip=None):
     from p2de_b200.api import rhs
-    param, solver, st, orc, U0 = make_pair(problem)
+    param, solver, st, orc, U0 = make_pair(problem, roundtrip=roundtrip)
     tp = param.timestepping_param
     dt = tp.CFL * tp.dt0 if dt is None else dt
     dt_o = orc.rhs(tp.t0, dt, nstage)
@@ -92,6 +96,14 @@ def test_limiter_active_rhs(N):
 def test_rhs_types(rhs_type):
     lim = NoRHSLimiter() if rhs_type.code != T.RHS_LIMITED_DG else SubcellLimiter()
     check_rhs(P.kelvin_helmholtz(N=3, K=(6, 6), rhs=rhs_type, limiter=lim))
+
+
+@pytest.mark.parametrize("N", [1, 3])
+def test_faithful_projection_roundtrip_option(N):
+    """cfg.lgl_projection_roundtrip=1 evaluates u(v(U)) at the face nodes exactly like rhs.jl:84-94."""
+    check_rhs(P.vortex(N=N, K=(5, 5)), roundtrip=True)
+    check_rhs(P.sedov(N=N, K=(6, 6), limiter=ZhangShuLimiter()), dt=2e-2, roundtrip=True)
+    check_rhs(P.dmr(N=N, K=(8, 4)), dt=5e-4, roundtrip=True)
 
 
 def test_dmr_boundary_conditions_rhs():

@@ -34,6 +34,7 @@ struct p2de_handle {
   int N1D = 0, Nq = 0, Nfp = 0, Nc = 0, Nd = 0, Ns = 3;
   long long K = 0;
   int mode = 0;
+  bool fast = false;   // default flux configuration -> FAST kernel variant (kernels2d.cuh)
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -176,11 +177,16 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
   }
   for (int i = 0; i < Nq; ++i) {
     T.wq[i] = o->wq[i];
+    T.rwJ[i] = 1.0 / (h->Jq * o->wq[i]);
     T.minv[i] = o->MinvVhT[i + (size_t)i * Nq];
+    if (std::fabs(T.minv[i] * o->wq[i] - 1.0) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "MinvVhT diagonal is not 1/wq");
     for (int j = 0; j < Nq; ++j)
       if (j != i && o->MinvVhT[i + (size_t)j * Nq] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "mass matrix is not diagonal");
   }
-  for (int f = 0; f < Nfp; ++f) T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
+  for (int f = 0; f < Nfp; ++f) {
+    T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
+    if (std::fabs(T.minvf[f] * o->wq[T.fq2q[f]] - 1.0) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "MinvVfT is not the 1/wq-scaled face gather");
+  }
   return 0;
 }
 
@@ -309,12 +315,12 @@ __global__ void reduce_kernel(const double *U, const double *wq, int Nq, long lo
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
-template <int N1D, int MODE>
+template <int N1D, int MODE, bool FAST>
 int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
-  constexpr int TBL = (sizeof(Tables2D<N1D>) + 7) / 8;
+  constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
   size_t smem = sizeof(double) * (TBL + (size_t)EPB * stage_smem_doubles_per_elem<N1D, MODE>());
-  auto kern = stage_kernel<N1D, MODE, EPB>;
+  auto kern = stage_kernel<N1D, MODE, EPB, FAST>;
   static bool attr_set = false;
   if (!attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -330,11 +336,19 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
 }
 template <int N1D>
 int launch_stage_n(p2de_handle *h, const StageArgs &A) {
+  if (h->fast) {
+    switch (h->mode) {
+      case MODE_SUBCELL: return launch_stage_t<N1D, MODE_SUBCELL, true>(h, A);
+      case MODE_ZHANGSHU: return launch_stage_t<N1D, MODE_ZHANGSHU, true>(h, A);
+      case MODE_LOW: return launch_stage_t<N1D, MODE_LOW, true>(h, A);
+      default: return launch_stage_t<N1D, MODE_HIGH, true>(h, A);
+    }
+  }
   switch (h->mode) {
-    case MODE_SUBCELL: return launch_stage_t<N1D, MODE_SUBCELL>(h, A);
-    case MODE_ZHANGSHU: return launch_stage_t<N1D, MODE_ZHANGSHU>(h, A);
-    case MODE_LOW: return launch_stage_t<N1D, MODE_LOW>(h, A);
-    default: return launch_stage_t<N1D, MODE_HIGH>(h, A);
+    case MODE_SUBCELL: return launch_stage_t<N1D, MODE_SUBCELL, false>(h, A);
+    case MODE_ZHANGSHU: return launch_stage_t<N1D, MODE_ZHANGSHU, false>(h, A);
+    case MODE_LOW: return launch_stage_t<N1D, MODE_LOW, false>(h, A);
+    default: return launch_stage_t<N1D, MODE_HIGH, false>(h, A);
   }
 }
 int launch_stage(p2de_handle *h, const StageArgs &A) {
@@ -385,6 +399,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.gamma = h->cfg.gamma; A.ZEROTOL = h->cfg.ZEROTOL; A.POSTOL = h->cfg.POSTOL; A.zeta = h->cfg.zeta;
   A.CFL = h->cfg.CFL; A.Jq = h->Jq; A.blend = 1.0;
   A.roundtrip = h->cfg.lgl_projection_roundtrip;
+  A.half_inv_gm1 = 1.0 / (2.0 * (h->cfg.gamma - 1.0));
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   return A;
 }
@@ -468,6 +483,12 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     return fail(nullptr, P2DE_ERR_CUDA, "no CUDA device (%s): libp2de_b200 has no CPU fallback", cudaGetErrorString(e));
   p2de_handle *h = new p2de_handle();
   h->cfg = *cfg;
+  {
+    bool low_ok = cfg->surf_flux_low == P2DE_SURFFLUX_LF_NODAL;
+    bool high_ok = cfg->surf_flux_high == P2DE_SURFFLUX_LF_PROJECTED && cfg->vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR &&
+                   !cfg->lgl_projection_roundtrip;
+    h->fast = mode == MODE_LOW ? low_ok : mode == MODE_HIGH ? high_ok : (low_ok && high_ok);
+  }
   h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = 4; h->Nd = 2; h->K = cfg->K; h->mode = mode;
   auto bail = [&](int rc) { g_create_error = h->err; p2de_destroy(h); return rc; };
   if (cfg->device >= 0) { if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device)); }

@@ -32,6 +32,7 @@ struct Tables2D {
   double S0[2][N1D][N1D];       // physical low-order S0 of pair (a+1, a): [d][line][a]
   double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
   double wq[N1D * N1D];
+  double rwJ[N1D * N1D];        // 1 / (Jq * wq)
   double minv[N1D * N1D];       // MinvVhT[i, i]
   double minvf[4 * N1D];        // MinvVfT[fq2q[f], f]
   int fq2q[4 * N1D];            // 0-based
@@ -60,6 +61,7 @@ struct StageArgs {
   double gamma, ZEROTOL, POSTOL, zeta, CFL, Jq, blend;
   int vol_flux, surf_low, surf_high; // P2DE_VOLFLUX_*, P2DE_SURFFLUX_*
   int roundtrip;                     // evaluate u(v(U)) at LGL face nodes instead of using U
+  double half_inv_gm1;               // 1 / (2 (gamma - 1))
 };
 
 struct UpdateArgs {
@@ -79,7 +81,7 @@ struct UpdateArgs {
 struct Nbr { long long kP; int fP; int bc; const double *ival; };
 
 template <int N1D>
-P2DE_DEV Nbr neighbor(const MeshTopo &M, long long k, int f) {
+P2DE_DEV Nbr neighbor(const MeshTopo &M, long long k, int ix, int iy, int f) {
   constexpr int Nfp = 4 * N1D;
   Nbr nb;
   nb.bc = 0; nb.ival = nullptr;
@@ -91,7 +93,6 @@ P2DE_DEV Nbr neighbor(const MeshTopo &M, long long k, int f) {
     else if (fl < 0) nb.bc = 2;
     return nb;
   }
-  int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
   int F = f / N1D, a = f % N1D;
   int jx = ix + (F == 0 ? -1 : F == 1 ? 1 : 0), jy = iy + (F == 2 ? -1 : F == 3 ? 1 : 0);
   bool out = jx < 0 || jx >= M.Kx || jy < 0 || jy >= M.Ky;
@@ -141,13 +142,18 @@ constexpr int stage_smem_doubles_per_elem() {
   return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D;
 }
 
-template <int N1D, int MODE, int EPB>
+// FAST = default flux configuration (Chandrashekar volume flux, Lax-Friedrichs surface fluxes on
+// nodal/projected values, identity LGL projection): hoisted reciprocals, merged low/high surface
+// flux, three-division two-point flux.  !FAST = every other option, reference operation order.
+template <int N1D, int MODE, int EPB, bool FAST>
 __global__ void __launch_bounds__(EPB * 2 * N1D)
 stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
              const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1, NFLD = 12;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
-  constexpr int TBL = (sizeof(Tables2D<N1D>) + 7) / 8;
+  constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;          // doubles to copy
+  constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;   // keeps what follows 16-byte aligned
+  constexpr int S = EPB * Nq;
   extern __shared__ double sm[];
   Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
   double *nodes = sm + TBL;                       // [NFLD][EPB*Nq]
@@ -164,54 +170,99 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 
   {
     const double *src = reinterpret_cast<const double *>(&Tc);
-    for (int i = tid; i < TBL; i += EPB * TPE) sm[i] = src[i];
+    for (int i = tid; i < TBLC; i += EPB * TPE) sm[i] = src[i];
   }
   // ---- node phase: primitives, logs, axis wavespeeds of every volume node (once per node)
   //      calculate_primitive_variables! flux_differencing.jl:39-52; wavespeed_estimate :48-62
   if (active) {
     for (int node = ln; node < Nq; node += TPE) {
       Cons2 U = load_cons(A.Uq + (k * Nq + node) * 4);
-      double p = pfun2(gm1, U);
       double *o = nodes + nbase + node;
-      constexpr int S = EPB * Nq;
       o[0 * S] = U.rho; o[1 * S] = U.m1; o[2 * S] = U.m2; o[3 * S] = U.E;
-      o[4 * S] = U.m1 / U.rho; o[5 * S] = U.m2 / U.rho; o[6 * S] = p;
-      double beta = U.rho / (2 * p);
-      o[7 * S] = beta;
+      double p, beta;
+      if (FAST) {
+        double rinv = 1.0 / U.rho;
+        p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+        o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv;
+        if (DO_LOW) { o[10 * S] = wavespeed_fast(gamma, gm1, rinv, U.m1, U.E); o[11 * S] = wavespeed_fast(gamma, gm1, rinv, U.m2, U.E); }
+      } else {
+        p = pfun2(gm1, U);
+        o[4 * S] = U.m1 / U.rho; o[5 * S] = U.m2 / U.rho;
+        if (DO_LOW) { o[10 * S] = wavespeed_dir(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir(gamma, gm1, U, 1); }
+      }
+      beta = U.rho / (2 * p);
+      o[6 * S] = p; o[7 * S] = beta;
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
-      if (DO_LOW) { o[10 * S] = wavespeed_dir(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir(gamma, gm1, U, 1); }
     }
   }
   __syncthreads();
 
   // ---- line phase
   Cons2 U[N1D];
-  double rhsxL[N1D][4], rhsxH[N1D][4], BFL[2][4], BFH[2][4];
+  double GL[N1D][4], GH[N1D][4];          // wJ * rhsxy_d of this line's nodes (low / high order)
+  double BFL[2][4], BFH[2][4];
   double lamPair[N1D], lamFace[2];
-  double wJ[N1D];
+  double wJ[N1D], rwJ[N1D];
   const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   if (active) {
     double uu[N1D], vv[N1D], pp[N1D];
-    constexpr int S = EPB * Nq;
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       int node = d == 0 ? a + line * N1D : line + a * N1D;
       const double *o = nodes + nbase + node;
       U[a].rho = o[0 * S]; U[a].m1 = o[1 * S]; U[a].m2 = o[2 * S]; U[a].E = o[3 * S];
       uu[a] = o[4 * S]; vv[a] = o[5 * S]; pp[a] = o[6 * S];
-      wJ[a] = A.Jq * T.wq[node];
+      wJ[a] = A.Jq * T.wq[node]; rwJ[a] = T.rwJ[node];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { GL[a][c] = 0.0; GH[a][c] = 0.0; }
     }
-    // neighbour data of the two end face nodes
+    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
     Nbr nb[2];
     Cons2 Unb[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      int f = (2 * d + e) * N1D + line;
-      nb[e] = neighbor<N1D>(M, k, f);
+      nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
       Unb[e] = load_cons(A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4);
     }
+    double fl[N1D][4];                      // nodal flux along d
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) flux_dir(U[a], uu[a], vv[a], pp[a], d, fl[a]);
+
+    if (FAST) {
+      // ---- both surface fluxes at the two line ends.  With the identity LGL projection the
+      //      low-order LF flux on nodal values (low_order_graph_viscosity.jl:175-204) and the
+      //      high-order LF flux on projected values (flux_differencing.jl:90-151,223-272) are
+      //      the same numbers; on inflow/outflow faces the high-order one drops the dissipation.
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ae = e ? N1D - 1 : 0;
+        const int node = d == 0 ? ae + line * N1D : line + ae * N1D;
+        double B = T.Bf[d][line][e], nn = fabs(B);
+        double rinvP = 1.0 / Unb[e].rho;
+        double wsP = wavespeed_fast(gamma, gm1, rinvP, d == 0 ? Unb[e].m1 : Unb[e].m2, Unb[e].E);
+        double wsM = DO_LOW ? nodes[(10 + d) * S + nbase + node] : wavespeed_fast(gamma, gm1, 1.0 / U[ae].rho, d == 0 ? U[ae].m1 : U[ae].m2, U[ae].E);
+        double lamB = 0.5 * nn * jl_max(wsM, wsP);
+        Cons2 uP = Unb[e];
+        if (nb[e].bc) {
+          uP = nb[e].bc == 1 ? load_cons(nb[e].ival) : U[ae];
+          rinvP = 1.0 / uP.rho;
+        }
+        double fP[4], up[4], uf[4];
+        flux_dir(uP, uP.m1 * rinvP, uP.m2 * rinvP, gm1 * (uP.E - 0.5 * (uP.m1 * uP.m1 + uP.m2 * uP.m2) * rinvP), d, fP);
+        cons_arr(uP, up); cons_arr(U[ae], uf);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
+          double lf = lamB * (up[c] - uf[c]);
+          BFL[e][c] = bfs - lf;
+          BFH[e][c] = nb[e].bc ? bfs : bfs - lf;
+        }
+        lamFace[e] = lamB;
+      }
+    }
+
     Cons2 Ut[2], Utnb[2];   // entropy-projected face states (rhs.jl:84-94), mine and the neighbour's
-    if (DO_HIGH || A.surf_low == P2DE_SURFFLUX_LF_PROJECTED) {
+    if (!FAST) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         Ut[e] = U[e ? N1D - 1 : 0];
@@ -224,16 +275,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     }
 
     if (DO_LOW) {
-      // ---- low-order graph-viscosity RHS along this line, low_order_graph_viscosity.jl:139-204
-      double ws[N1D], fl[N1D][4], Q0[N1D][4];
+      // ---- low-order graph-viscosity volume terms along this line, low_order_graph_viscosity.jl:139-173
+      double ws[N1D];
 #pragma unroll
-      for (int a = 0; a < N1D; ++a) {
-        int node = d == 0 ? a + line * N1D : line + a * N1D;
-        ws[a] = nodes[(10 + d) * S + nbase + node];
-        flux_dir(U[a], uu[a], vv[a], pp[a], d, fl[a]);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Q0[a][c] = 0.0;
-      }
+      for (int a = 0; a < N1D; ++a) ws[a] = nodes[(10 + d) * S + nbase + (d == 0 ? a + line * N1D : line + a * N1D)];
 #pragma unroll
       for (int a = 0; a < N1D - 1; ++a) {
         const int i = a + 1, j = a;
@@ -246,68 +291,55 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         for (int c = 0; c < 4; ++c) {
           double F = 0.5 * (fl[i][c] + fl[j][c]);
           double SF = 2.0 * Sv * F - lam * (uj[c] - ui[c]);
-          Q0[i][c] += SF; Q0[j][c] += -SF;
+          GL[i][c] -= SF; GL[j][c] += SF;          // GL = -Q0F1
         }
       }
       lamPair[N1D - 1] = 0.0;
+      if (!FAST) {
+        // surface, :175-204 (reference operation order; LaxFriedrichsOnProjectedVal supported)
 #pragma unroll
-      for (int a = 0; a < N1D; ++a)
+        for (int e = 0; e < 2; ++e) {
+          const int ae = e ? N1D - 1 : 0;
+          double B = T.Bf[d][line][e], nn = fabs(B);
+          bool proj = A.surf_low == P2DE_SURFFLUX_LF_PROJECTED;
+          Cons2 Uf = proj ? Ut[e] : U[ae];
+          Cons2 UfP = proj ? Utnb[e] : Unb[e];
+          double wsM = proj ? wavespeed_dir(gamma, gm1, Uf, d) : ws[ae];
+          double wsP = wavespeed_dir(gamma, gm1, UfP, d);
+          double lamB = 0.5 * nn * jl_max(wsM, wsP);
+          Cons2 uP = UfP;
+          if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
+          else if (nb[e].bc == 2) uP = U[ae];
+          double fM[4], fP[4], uf[4], up[4];
+          if (proj) flux_dir(gm1, Uf, d, fM);
+          else {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) rhsxL[a][c] = 0.0 - Q0[a][c];
-      // surface, :175-204
+            for (int c = 0; c < 4; ++c) fM[c] = fl[ae][c];
+          }
+          flux_dir(gm1, uP, d, fP);
+          cons_arr(Uf, uf); cons_arr(uP, up);
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int ae = e ? N1D - 1 : 0;
-        double B = T.Bf[d][line][e], nn = fabs(B);
-        bool proj = A.surf_low == P2DE_SURFFLUX_LF_PROJECTED;
-        Cons2 Uf = proj ? Ut[e] : U[ae];
-        Cons2 UfP = proj ? Utnb[e] : Unb[e];
-        double wsM = proj ? wavespeed_dir(gamma, gm1, Uf, d) : ws[ae];
-        double wsP = wavespeed_dir(gamma, gm1, UfP, d);
-        double lamB = 0.5 * nn * jl_max(wsM, wsP);
-        Cons2 uP = UfP;
-        if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
-        else if (nb[e].bc == 2) uP = U[ae];
-        double fM[4], fP[4], uf[4], up[4];
-        if (proj) flux_dir(gm1, Uf, d, fM);
-        else {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) fM[c] = fl[ae][c];
-        }
-        flux_dir(gm1, uP, d, fP);
-        cons_arr(Uf, uf); cons_arr(uP, up);
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double fs = 0.5 * (fM[c] + fP[c]);
-          double bf = B * fs - lamB * (up[c] - uf[c]);
-          BFL[e][c] = bf;
-          rhsxL[ae][c] -= bf;
-        }
-        lamFace[e] = lamB;
-        if (proj && A.nstage == 1) {   // lambda_B_CFL(::LaxFriedrichsOnProjectedVal), :287-291
-          double alpha = find_alpha(A.POSTOL, U[ae], Uf);
-          lamFace[e] = alpha * lamB + 0.5 * nn * wsM;
+          for (int c = 0; c < 4; ++c) BFL[e][c] = B * (0.5 * (fM[c] + fP[c])) - lamB * (up[c] - uf[c]);
+          lamFace[e] = lamB;
+          if (proj && A.nstage == 1) {   // lambda_B_CFL(::LaxFriedrichsOnProjectedVal), :287-291
+            double alpha = find_alpha(A.POSTOL, U[ae], Uf);
+            lamFace[e] = alpha * lamB + 0.5 * nn * wsM;
+          }
         }
       }
 #pragma unroll
-      for (int a = 0; a < N1D; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) rhsxL[a][c] = rhsxL[a][c] / wJ[a];   // scale_low_order_rhs_by_mass! :206-220
+      for (int c = 0; c < 4; ++c) { GL[0][c] -= BFL[0][c]; GL[N1D - 1][c] -= BFL[1][c]; }
     }
 
     if (DO_HIGH) {
-      // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer)
-      double QF[N1D][4];
-#pragma unroll
-      for (int a = 0; a < N1D; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) QF[a][c] = 0.0;
-      if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
+      // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer).
+      //      GH = -(QF1 + B F*) (LGL: M^-1 Vh^T is a scaled 0/1 gather; the hybridized face-volume
+      //      pairs cancel identically and are not formed)
+      if (FAST || A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
         Prim2 q[N1D];
 #pragma unroll
         for (int a = 0; a < N1D; ++a) {
-          int node = d == 0 ? a + line * N1D : line + a * N1D;
-          const double *o = nodes + nbase + node;
+          const double *o = nodes + nbase + (d == 0 ? a + line * N1D : line + a * N1D);
           q[a].rho = U[a].rho; q[a].u = uu[a]; q[a].v = vv[a];
           q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
         }
@@ -316,76 +348,72 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
           for (int i = j + 1; i < N1D; ++i) {
             double F[4];
-            fS_dir(gm1, q[i], q[j], d, F);
+            if (FAST) fS_fast(A.half_inv_gm1, q[i], q[j], d, F); else fS_dir(gm1, q[i], q[j], d, F);
             double Sv = T.SH[d][line][i][j];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; QF[i][c] += Sf; QF[j][c] += -Sf; }
+            for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; GH[i][c] -= Sf; GH[j][c] += Sf; }
           }
       } else {   // CentralFlux, flux_differencing.jl:217-221
-        double fl[N1D][4];
-#pragma unroll
-        for (int a = 0; a < N1D; ++a) flux_dir(U[a], uu[a], vv[a], pp[a], d, fl[a]);
 #pragma unroll
         for (int j = 0; j < N1D; ++j)
 #pragma unroll
           for (int i = j + 1; i < N1D; ++i) {
             double Sv = T.SH[d][line][i][j];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) { double Sf = Sv * (0.5 * (fl[i][c] + fl[j][c])); QF[i][c] += Sf; QF[j][c] += -Sf; }
+            for (int c = 0; c < 4; ++c) { double Sf = Sv * (0.5 * (fl[i][c] + fl[j][c])); GH[i][c] -= Sf; GH[j][c] += Sf; }
           }
       }
-      // surface, flux_differencing.jl:90-151,223-272
+      if (!FAST) {
+        // surface, flux_differencing.jl:90-151,223-272
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int ae = e ? N1D - 1 : 0;
-        double B = T.Bf[d][line][e], nn = fabs(B);
-        double LFc = 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
-        Cons2 uP = Utnb[e];
-        if (nb[e].bc == 1) { uP = load_cons(nb[e].ival); LFc = 0.0; }
-        else if (nb[e].bc == 2) { uP = U[ae]; LFc = 0.0; }
-        double fs[4];
-        if (A.surf_high == P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED) {
-          fS_dir(gm1, prim_of(gm1, Ut[e]), prim_of(gm1, uP), d, fs);
-        } else {
-          double fM[4], fP[4];
-          flux_dir(gm1, Ut[e], d, fM); flux_dir(gm1, uP, d, fP);
+        for (int e = 0; e < 2; ++e) {
+          const int ae = e ? N1D - 1 : 0;
+          double B = T.Bf[d][line][e], nn = fabs(B);
+          double LFc = 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
+          Cons2 uP = Utnb[e];
+          if (nb[e].bc == 1) { uP = load_cons(nb[e].ival); LFc = 0.0; }
+          else if (nb[e].bc == 2) { uP = U[ae]; LFc = 0.0; }
+          double fs[4];
+          if (A.surf_high == P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED) {
+            fS_dir(gm1, prim_of(gm1, Ut[e]), prim_of(gm1, uP), d, fs);
+          } else {
+            double fM[4], fP[4];
+            flux_dir(gm1, Ut[e], d, fM); flux_dir(gm1, uP, d, fP);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) fs[c] = 0.5 * (fM[c] + fP[c]);
-        }
-        double uf[4], up[4];
-        cons_arr(Ut[e], uf); cons_arr(uP, up);
+            for (int c = 0; c < 4; ++c) fs[c] = 0.5 * (fM[c] + fP[c]);
+          }
+          double uf[4], up[4];
+          cons_arr(Ut[e], uf); cons_arr(uP, up);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
-      }
-      // assemble_rhs!, flux_differencing.jl:331-361 (LGL: M^-1 Vh^T is a scaled 0/1 gather; the
-      // hybridized face-volume pairs cancel identically and are not formed)
-#pragma unroll
-      for (int a = 0; a < N1D; ++a) {
-        int node = d == 0 ? a + line * N1D : line + a * N1D;
-        double mi = T.minv[node];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double acc = mi * QF[a][c];
-          double b = 0.0;
-          if (a == 0) b = T.minvf[(2 * d) * N1D + line] * BFH[0][c];
-          if (a == N1D - 1) b += T.minvf[(2 * d + 1) * N1D + line] * BFH[1][c];
-          rhsxH[a][c] = -(acc + b) / A.Jq;
+          for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
         }
       }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { GH[0][c] -= BFH[0][c]; GH[N1D - 1][c] -= BFH[1][c]; }
     }
 
     // ---- publish this line's share of rhsL / rhsH / lambda for the node-wise combination
+    //      (scale_low_order_rhs_by_mass! :206-220, assemble_rhs! flux_differencing.jl:331-361)
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       int node = d == 0 ? a + line * N1D : line + a * N1D;
-      if (DO_LOW) store4(partsL + (nbase + node) * 8 + d * 4, rhsxL[a]);
-      if (MODE != MODE_SUBCELL && DO_HIGH) store4(partsH + (nbase + node) * 8 + d * 4, rhsxH[a]);
+      if (DO_LOW) {
+        double r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[c] = GL[a][c] * rwJ[a];
+        store4(partsL + (nbase + node) * 8 + d * 4, r);
+      }
+      if (MODE != MODE_SUBCELL && DO_HIGH) {
+        double r[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) r[c] = GH[a][c] * rwJ[a];
+        store4(partsH + (nbase + node) * 8 + d * 4, r);
+      }
       if (DO_LOW && A.nstage == 1) {
         double *lp = lamp + (nbase + node) * 6 + d * 3;
         lp[0] = a > 0 ? lamPair[a - 1] : 0.0;
         lp[1] = lamPair[a];
         lp[2] = a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0);
-        if (N1D == 1) lp[2] = lamFace[0] + lamFace[1];
       }
     }
   }
@@ -416,21 +444,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
     //      limiting coefficients of this line's N1D+1 subcell faces (subcell.jl:248-349)
     double dFv[NF][4];
-    {
-      double fH[4], fL[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { fH[c] = BFH[0][c]; fL[c] = BFL[0][c]; dFv[0][c] = fH[c] - fL[c]; }
+    for (int c = 0; c < 4; ++c) dFv[0][c] = BFH[0][c] - BFL[0][c];
 #pragma unroll
-      for (int s = 1; s < NF; ++s)
+    for (int s = 1; s < NF; ++s)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          fH[c] = fH[c] + wJ[s - 1] * rhsxH[s - 1][c];
-          fL[c] = fL[c] + wJ[s - 1] * rhsxL[s - 1][c];
-          dFv[s][c] = fH[c] - fL[c];
-        }
-    }
+      for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + (GH[s - 1][c] - GL[s - 1][c]);
     Cons2 uL[N1D];
-    double Lrho[N1D], Lrhoe[N1D];
+    double Lrho[N1D], Lrhoe[N1D], c0[N1D];
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       int node = d == 0 ? a + line * N1D : line + a * N1D;
@@ -441,28 +462,27 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       uL[a].rho = U[a].rho + dtl * r[0]; uL[a].m1 = U[a].m1 + dtl * r[1];
       uL[a].m2 = U[a].m2 + dtl * r[2]; uL[a].E = U[a].E + dtl * r[3];
       Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
+      c0[a] = quad_coeff_c(uL[a], Lrhoe[a]);
       if (d == 0) {
         store4(A.rhsL + (k * Nq + node) * 4, r);
         if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
-      }
-      if (d == 0 && A.rhsH_diag) {   // needs the y share of rhsH: recompute it is not possible here, see below
       }
     }
     double lv[NF];
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
       double l = 1.0;
-      if (s < N1D) {
-        double Pv[4];
+      if (s < N1D) {   // node to the right/top of the face: P = -4 dt (fH - fL) / wJ (subcell.jl:300,328)
+        double Pv[4], kk = -4 * dtl * rwJ[s];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Pv[c] = -4 * dtl * dFv[s][c] / wJ[s];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], Pv, Lrho[s], Lrhoe[s]));
+        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]));
       }
-      if (s >= 1) {
-        double Pv[4];
+      if (s >= 1) {    // node to the left/bottom: P = +4 dt (fH - fL) / wJ (subcell.jl:312,340)
+        double Pv[4], kk = 4 * dtl * rwJ[s - 1];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Pv[c] = 4 * dtl * dFv[s][c] / wJ[s - 1];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
+        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
       }
       lv[s] = jl_min(l, A.blend);
     }
@@ -477,7 +497,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       for (int a = 0; a < N1D; ++a) {
         int node = d == 0 ? a + line * N1D : line + a * N1D;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) atomicAdd(A.rhsH_diag + (k * Nq + node) * 4 + c, rhsxH[a][c]);
+        for (int c = 0; c < 4; ++c) atomicAdd(A.rhsH_diag + (k * Nq + node) * 4 + c, GH[a][c] * rwJ[a]);
       }
     }
     return;
@@ -502,7 +522,8 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         double Pv[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = dtl * (rH[a][c] - rL[a][c]);
-        lline = jl_min(lline, limiting_param_pos(A.ZEROTOL, uL, Pv, A.zeta * uL.rho, A.zeta * rhoe2(uL)));
+        double Lrhoe = A.zeta * rhoe2(uL);
+        lline = jl_min(lline, limiting_param_pos(A.ZEROTOL, uL, quad_coeff_c(uL, Lrhoe), Pv, A.zeta * uL.rho, Lrhoe));
       }
     }
     if (MODE == MODE_ZHANGSHU) lmin[el * N1D + line] = lline;
@@ -546,21 +567,25 @@ update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ Mesh
               const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1;
   __shared__ double cy[EPB * Nq * 4];
+  __shared__ double s_rwJ[Nq];
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
   const bool active = k < M.K;
   const int nbase = el * Nq;
   double cx[N1D][4];
   if (MODE == MODE_SUBCELL) {
+    if (tid < Nq) s_rwJ[tid] = Tc.rwJ[tid];
+    __syncthreads();
     if (active) {
       // symmetrize_limiting_parameters!, subcell.jl:418-456, as a pure gather (min is idempotent)
       double lv[NF];
       const double *lsrc = A.lpre + (k * 2 + d) * (N1D * NF);
 #pragma unroll
       for (int s = 0; s < NF; ++s) lv[s] = lsrc[d == 0 ? s + line * NF : line + s * N1D];
+      const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        Nbr nb = neighbor<N1D>(M, k, (2 * d + e) * N1D + line);
+        Nbr nb = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
         double lP = A.lpre[(nb.kP * 2 + d) * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
         lv[e ? N1D : 0] = jl_min(lv[e ? N1D : 0], lP);
       }
@@ -581,9 +606,9 @@ update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ Mesh
 #pragma unroll
       for (int a = 0; a < N1D; ++a) {
         int node = d == 0 ? a + line * N1D : line + a * N1D;
-        double wJ = A.Jq * Tc.wq[node];
+        double rw = s_rwJ[node];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) cx[a][c] = (g[a + 1][c] - g[a][c]) / wJ;
+        for (int c = 0; c < 4; ++c) cx[a][c] = (g[a + 1][c] - g[a][c]) * rw;
         if (d == 1) store4(cy + (nbase + node) * 4, cx[a]);
       }
     }

@@ -1,9 +1,16 @@
 // physics.cuh — pointwise compressible-Euler device functions (FP64, CUDA cores).
 //
-// Same formulas, same operation order as the reference's src/math/compressible_Navier_Stokes.jl
-// (line numbers cited per function) so that the only differences from the CPU oracle are FMA
-// contraction and libm last-bit differences (log/exp/pow); IEEE division and sqrt are kept
-// (no -use_fast_math, no reciprocal tricks that would change Inf/NaN outcomes in the limiter).
+// Two families:
+//   * "reference-order" functions (pfun2, wavespeed_dir, flux_dir, fS_dir, entropy_roundtrip,
+//     limiting_param_pos): same formulas in the same operation order as the reference's
+//     src/math/compressible_Navier_Stokes.jl and src/dg/limiter/limiter_utils.jl.  Used by the
+//     generic kernel variant (non-default flux options).
+//   * "_fast" functions: algebraically identical, but with the divisions hoisted into per-node
+//     reciprocals, the two divisions of each logmean merged into one, and the limiter's
+//     quadratic solved only when a root in (0, 1] is possible.  Differences from the
+//     reference-order results are a few ulp (tests hold both to 1e-12 against the CPU oracle).
+// IEEE division and sqrt everywhere (no -use_fast_math); Inf/NaN behaviour of the limiter's
+// root selection is the reference's.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -33,6 +40,11 @@ P2DE_DEV double wavespeed_n(double gamma, double gm1, double rho, double mn, dou
 P2DE_DEV double wavespeed_dir(double gamma, double gm1, const Cons2 &U, int d) {
   return wavespeed_n(gamma, gm1, U.rho, d == 0 ? U.m1 : U.m2, U.E);
 }
+// same with rinv = 1/rho supplied
+P2DE_DEV double wavespeed_fast(double gamma, double gm1, double rinv, double mn, double E) {
+  double p = gm1 * (E - 0.5 * (mn * mn) * rinv);
+  return fabs(mn * rinv) + sqrt(gamma * p * rinv);
+}
 
 // flux component along axis d, fluxes(::Dim2) :175-194, given u = m1/rho, v = m2/rho, p
 P2DE_DEV void flux_dir(const Cons2 &U, double u, double v, double p, int d, double f[4]) {
@@ -47,7 +59,7 @@ P2DE_DEV void flux_dir(double gm1, const Cons2 &U, int d, double f[4]) {
 
 // v_ufun(::Dim2) :134-144 followed by u_vfun(::Dim2) :155-163 (entropy-projection round trip of a
 // collocated LGL face node, rhs.jl:84-94 with Vf a 0/1 row).
-P2DE_DEV Cons2 entropy_roundtrip(double gamma, double gm1, const Cons2 &U) {
+__device__ __noinline__ Cons2 entropy_roundtrip(double gamma, double gm1, Cons2 U) {
   double p = pfun2(gm1, U);
   double s = log(p / pow(U.rho, gamma));                 // sfun :64-68
   double v1 = (gamma + 1 - s) - gm1 * U.E / p;
@@ -85,6 +97,32 @@ P2DE_DEV void fS_dir(double gm1, const Prim2 &L, const Prim2 &R, int d, double F
   else { double FyS1 = rholog * vavg; F[0] = FyS1; F[1] = FxS3; F[2] = FyS1 * vavg + pa; F[3] = f4aux * vavg; }
 }
 
+// Same flux with three divisions instead of six:
+//   logmean(rho)      = |f| < 1e-4 ? aavg * P((da/aavg)^2) : da / (logR - logL)      (one quotient)
+//   1 / logmean(beta) = |f| < 1e-4 ? (1/bavg) * (1 + 0.2 v + 0.0912 v^2)  : (logR - logL) / db
+//                       (1/P(v) to O(v^3) ~ 1e-24 since v < 1e-8)
+//   pa                = rhoavg / (betaL + betaR)
+// `half_inv_gm1` = 1 / (2 (gamma - 1)).
+P2DE_DEV void fS_fast(double half_inv_gm1, const Prim2 &L, const Prim2 &R, int d, double F[4]) {
+  double da = R.rho - L.rho, aavg = 0.5 * (R.rho + L.rho);
+  bool ser = fabs(da) < 1e-4 * fabs(aavg);
+  double q = da / (ser ? aavg : (R.rholog - L.rholog));
+  double v = q * q;
+  double rholog = ser ? aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857))) : q;
+  double db = R.beta - L.beta, bavg = 0.5 * (R.beta + L.beta);
+  bool serb = fabs(db) < 1e-4 * fabs(bavg);
+  double qb = (serb ? 1.0 : (R.betalog - L.betalog)) / (serb ? bavg : db);
+  double fb = db * qb, vb = fb * fb;
+  double inv_betalog = serb ? qb * (1 + vb * (0.2 + vb * 0.0912)) : qb;
+  double rhoavg = aavg, uavg = 0.5 * (L.u + R.u), vavg = 0.5 * (L.v + R.v);
+  double unorm = L.u * R.u + L.v * R.v;
+  double pa = rhoavg / (L.beta + R.beta);
+  double f4aux = rholog * inv_betalog * half_inv_gm1 + pa + 0.5 * rholog * unorm;
+  double FxS1 = rholog * uavg, FxS3 = FxS1 * vavg;
+  if (d == 0) { F[0] = FxS1; F[1] = FxS1 * uavg + pa; F[2] = FxS3; F[3] = f4aux * uavg; }
+  else { double FyS1 = rholog * vavg; F[0] = FyS1; F[1] = FxS3; F[2] = FyS1 * vavg + pa; F[3] = f4aux * vavg; }
+}
+
 P2DE_DEV Prim2 prim_of(double gm1, const Cons2 &U) {
   Prim2 q;
   double p = pfun2(gm1, U);
@@ -94,11 +132,16 @@ P2DE_DEV Prim2 prim_of(double gm1, const Cons2 &U) {
   return q;
 }
 
-// rhoe_quadratic_solve, src/dg/limiter/limiter_utils.jl:52-90 (Dim2 coefficients :85-90)
-P2DE_DEV double rhoe_quadratic_solve(double ZEROTOL, const Cons2 &U, const double Pv[4], double Lrhoe) {
-  double a = Pv[0] * Pv[3] - 1.0 / 2.0 * (Pv[1] * Pv[1] + Pv[2] * Pv[2]);
-  double b = U.E * Pv[0] + U.rho * Pv[3] - U.m1 * Pv[1] - U.m2 * Pv[2] - Pv[0] * Lrhoe;
-  double c = U.E * U.rho - 1.0 / 2.0 * (U.m1 * U.m1 + U.m2 * U.m2) - U.rho * Lrhoe;
+// rhoe_quadratic_coefficients(::Dim2), src/dg/limiter/limiter_utils.jl:85-90
+P2DE_DEV void quad_coeff_ab(const Cons2 &U, const double Pv[4], double Lrhoe, double &a, double &b) {
+  a = Pv[0] * Pv[3] - 1.0 / 2.0 * (Pv[1] * Pv[1] + Pv[2] * Pv[2]);
+  b = U.E * Pv[0] + U.rho * Pv[3] - U.m1 * Pv[1] - U.m2 * Pv[2] - Pv[0] * Lrhoe;
+}
+P2DE_DEV double quad_coeff_c(const Cons2 &U, double Lrhoe) {
+  return U.E * U.rho - 1.0 / 2.0 * (U.m1 * U.m1 + U.m2 * U.m2) - U.rho * Lrhoe;
+}
+// root selection of rhoe_quadratic_solve, limiter_utils.jl:52-76
+__device__ __noinline__ double rhoe_quadratic_roots(double ZEROTOL, double a, double b, double c) {
   double l = 1.0;
   double disc = b * b - 4 * a * c;
   if (disc >= 0) {
@@ -110,12 +153,19 @@ P2DE_DEV double rhoe_quadratic_solve(double ZEROTOL, const Cons2 &U, const doubl
   }
   return l;
 }
-// limiting_param_bound_rho_rhoe, limiter_utils.jl:26-40 with Urho = Urhoe = Inf (positivity bounds)
-P2DE_DEV double limiting_param_pos(double ZEROTOL, const Cons2 &U, const double Pv[4], double Lrho, double Lrhoe) {
+// limiting_param_bound_rho_rhoe, limiter_utils.jl:26-40 with Urho = Urhoe = Inf (positivity
+// bounds): min(l_rho, quad(Lrhoe), quad(Inf) == 1.0).  `c` = quad_coeff_c(U, Lrhoe).
+// The quadratic q(l) = a l^2 + b l + c has no root in (0, 1] when q(0) > 0, q(1) > 0 and its
+// vertex is not an interior minimum; the reference then returns either 1 or a root > 1, which
+// the trailing min(., 1.0) turns into 1, so the sqrt and the two divisions are skipped.
+P2DE_DEV double limiting_param_pos(double ZEROTOL, const Cons2 &U, double c, const double Pv[4], double Lrho, double Lrhoe) {
   double l = 1.0;
   if (U.rho + Pv[0] < Lrho) l = jl_max((Lrho - U.rho) / Pv[0], 0.0);
-  // min(l, quad(Lrhoe), quad(Urhoe = Inf) == 1.0)
-  return jl_min(jl_min(l, rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe)), 1.0);
+  double a, b;
+  quad_coeff_ab(U, Pv, Lrhoe, a, b);
+  bool no_root = (c > 0.0) && (a + b + c > 0.0) && !(a > 0.0 && b < 0.0 && -b < 2.0 * a);
+  if (!no_root) l = jl_min(l, rhoe_quadratic_roots(ZEROTOL, a, b, c));
+  return jl_min(l, 1.0);
 }
 
 }  // namespace p2de

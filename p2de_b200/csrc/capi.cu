@@ -15,6 +15,7 @@
 
 #include "../../include/p2de_b200.h"
 #include "kernels2d.cuh"
+#include "stage_fast.cuh"
 
 using namespace p2de;
 
@@ -319,8 +320,9 @@ template <int N1D, int MODE, bool FAST>
 int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
   constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
-  size_t smem = sizeof(double) * (TBL + (size_t)EPB * stage_smem_doubles_per_elem<N1D, MODE>());
-  auto kern = stage_kernel<N1D, MODE, EPB, FAST>;
+  size_t smem = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
+  void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
+  if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, false>;
   static bool attr_set = false;
   if (!attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -437,7 +439,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
   B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
-  B.Jq = h->Jq;
+  B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0;
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
   return 0;
 }

@@ -24,6 +24,10 @@
 
 namespace p2de {
 
+#ifndef P2DE_STAGE_MIN_BLOCKS
+#define P2DE_STAGE_MIN_BLOCKS 2
+#endif
+
 enum { MODE_SUBCELL = 0, MODE_ZHANGSHU = 1, MODE_LOW = 2, MODE_HIGH = 3 };
 
 template <int N1D>
@@ -75,6 +79,7 @@ struct UpdateArgs {
   const double *dt_dev;
   double dt_host;
   int use_dt_dev;
+  int rotated;                       // dF of y-lines is stored in the rotated frame (FAST stage kernel)
   double Jq;
 };
 
@@ -146,7 +151,7 @@ constexpr int stage_smem_doubles_per_elem() {
 // nodal/projected values, identity LGL projection): hoisted reciprocals, merged low/high surface
 // flux, three-division two-point flux.  !FAST = every other option, reference operation order.
 template <int N1D, int MODE, int EPB, bool FAST>
-__global__ void __launch_bounds__(EPB * 2 * N1D)
+__global__ void __launch_bounds__(EPB * 2 * N1D, P2DE_STAGE_MIN_BLOCKS)
 stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
              const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1, NFLD = 12;
@@ -624,8 +629,10 @@ update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ Mesh
     if (MODE == MODE_SUBCELL) {
       Cons2 rl = load_cons(A.rhsL + off);
       const double *y = cy + (nbase + node) * 4;
-      r[0] = rl.rho + (cx[a][0] + y[0]); r[1] = rl.m1 + (cx[a][1] + y[1]);
-      r[2] = rl.m2 + (cx[a][2] + y[2]); r[3] = rl.E + (cx[a][3] + y[3]);
+      // FAST stage kernel: the y-lines' dF (hence cy) is in their rotated frame (momenta swapped)
+      const int s1 = A.rotated ? 2 : 1, s2 = A.rotated ? 1 : 2;
+      r[0] = rl.rho + (cx[a][0] + y[0]); r[1] = rl.m1 + (cx[a][1] + y[s1]);
+      r[2] = rl.m2 + (cx[a][2] + y[s2]); r[3] = rl.E + (cx[a][3] + y[3]);
     } else {
       Cons2 ru = load_cons(A.rhsU_in + off);
       cons_arr(ru, r);

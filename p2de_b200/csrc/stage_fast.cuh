@@ -1,0 +1,419 @@
+// stage_fast.cuh — stage kernel for the default flux configuration (FAST variant, see
+// kernels2d.cuh for the scheme and the line-thread mapping).  Same results as the generic
+// stage_kernel within a few ulp; differences are purely organisational:
+//
+//   * warps are direction-homogeneous (first half of the CTA = x-lines, second half = y-lines) and
+//     every line works in a frame rotated to its own axis (normal momentum first), so the axis is
+//     an address offset instead of per-pair selects;
+//   * node fields live in shared memory in a swizzled order that is bank-conflict free for both
+//     x-line and y-line warps (N1D = 4);
+//   * 1/x and sqrt are MUFU seed + Newton steps without the IEEE special-case branches, which
+//     lets ptxas interleave the independent node-pair chains (operands are positive normals);
+//   * with the identity LGL projection the low- and high-order surface fluxes coincide, so an
+//     interior face contributes nothing to f_H - f_L; only inflow/outflow faces do;
+//   * phases are ordered so that at most one 4-node accumulator set is live at a time.
+#pragma once
+#include "kernels2d.cuh"
+
+namespace p2de {
+
+#ifndef P2DE_FAST_MIN_BLOCKS
+#define P2DE_FAST_MIN_BLOCKS 2
+#endif
+
+// reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (error ~ seed^4)
+P2DE_DEV double rcp_fast(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-a, x, 1.0);
+  x = fma(x, e, x);
+  return x;
+}
+// n / a with one residual correction (last-bit accurate for normal operands)
+P2DE_DEV double div_fast(double n, double a) {
+  double x = rcp_fast(a);
+  double q = n * x;
+  double r = fma(-a, q, n);
+  return fma(r, x, q);
+}
+// sqrt: MUFU.RSQ64H seed + two coupled Newton steps + residual correction
+P2DE_DEV double sqrt_fast(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  double dd = fma(-g, g, a);
+  return fma(dd, h, g);
+}
+
+// state in the frame of one axis: (rho, normal momentum, tangential momentum, E)
+struct ConsR { double rho, mn, mt, E; };
+struct PrimR { double rho, un, ut, beta, rholog, betalog; };
+
+P2DE_DEV double wavespeed_rot(double gamma, double gm1, double rinv, double mn, double E) {
+  double p = gm1 * (E - 0.5 * (mn * mn) * rinv);
+  return fabs(mn * rinv) + sqrt_fast(gamma * p * rinv);
+}
+// normal flux of fluxes(::Dim2) (:175-194) in the rotated frame
+P2DE_DEV void flux_rot(const ConsR &U, double un, double ut, double p, double f[4]) {
+  f[0] = U.mn; f[1] = U.mn * un + p; f[2] = U.rho * un * ut; f[3] = un * (U.E + p);
+}
+// fS (:220-249) along the line's own axis, three reciprocals (see fS_fast in physics.cuh)
+P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double F[4]) {
+  double da = R.rho - L.rho, aavg = 0.5 * (R.rho + L.rho);
+  bool ser = fabs(da) < 1e-4 * fabs(aavg);
+  double q = div_fast(da, ser ? aavg : (R.rholog - L.rholog));
+  double v = q * q;
+  double rholog = ser ? aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857))) : q;
+  double db = R.beta - L.beta, bavg = 0.5 * (R.beta + L.beta);
+  bool serb = fabs(db) < 1e-4 * fabs(bavg);
+  double qb = div_fast(serb ? 1.0 : (R.betalog - L.betalog), serb ? bavg : db);
+  double fb = db * qb, vb = fb * fb;
+  double inv_betalog = serb ? qb * (1 + vb * (0.2 + vb * 0.0912)) : qb;
+  double unavg = 0.5 * (L.un + R.un), utavg = 0.5 * (L.ut + R.ut);
+  double unorm = L.un * R.un + L.ut * R.ut;
+  double pa = div_fast(aavg, L.beta + R.beta);
+  double f4aux = rholog * inv_betalog * half_inv_gm1 + pa + 0.5 * rholog * unorm;
+  double F1 = rholog * unavg;
+  F[0] = F1; F[1] = F1 * unavg + pa; F[2] = F1 * utavg; F[3] = f4aux * unavg;
+}
+
+// shared-memory position of node (i, j) of CTA-local element el
+template <int N1D>
+P2DE_DEV int node_pos(int el, int i, int j) {
+  if (N1D == 4) return el * 16 + 4 * ((j + el) & 3) + ((i + j) & 3);
+  return el * (N1D * N1D) + i + j * N1D;
+}
+
+template <int N1D, int MODE>
+constexpr int fast_smem_doubles_per_elem() {
+  constexpr int Nq = N1D * N1D;
+  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D;
+}
+
+template <int N1D, int MODE, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, P2DE_FAST_MIN_BLOCKS)
+stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                  const __grid_constant__ Tables2D<N1D> Tc) {
+  constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
+  constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
+  constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;
+  constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
+  constexpr int S = EPB * Nq;
+  extern __shared__ double sm[];
+  Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
+  double *nodes = sm + TBL;                       // [NFLD][S]   swizzled node positions
+  double2 *partsL = reinterpret_cast<double2 *>(nodes + NFLD * S);   // [d][half][S]
+  double2 *partsH = partsL + 4 * S;                                   // [d][half][S] (not MODE_SUBCELL)
+  double *lamp = reinterpret_cast<double *>(partsH + ((MODE == MODE_SUBCELL) ? 0 : 4 * S));  // [6][S]
+  double *lmin = lamp + 6 * S;                    // [EPB][N1D]
+
+  const int tid = threadIdx.x;
+  const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
+  const long long k = (long long)blockIdx.x * EPB + el;
+  const bool active = k < M.K;
+  const double gamma = A.gamma, gm1 = A.gamma - 1.0;
+
+  {
+    const double *src = reinterpret_cast<const double *>(&Tc);
+    for (int i = tid; i < TBLC; i += NT) sm[i] = src[i];
+  }
+  // ---- node phase (every volume node once): primitives, logs, axis wavespeeds
+  for (int n = tid; n < S; n += NT) {
+    const int e2 = n / Nq, node = n % Nq;
+    const long long k2 = (long long)blockIdx.x * EPB + e2;
+    if (k2 < M.K) {
+      Cons2 U = load_cons(A.Uq + (k2 * Nq + node) * 4);
+      double *o = nodes + node_pos<N1D>(e2, node % N1D, node / N1D);
+      double rinv = rcp_fast(U.rho);
+      double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+      double beta = 0.5 * U.rho * rcp_fast(p);
+      o[0 * S] = U.rho; o[1 * S] = U.m1; o[2 * S] = U.m2; o[3 * S] = U.E;
+      o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv; o[6 * S] = p; o[7 * S] = beta;
+      if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
+      o[10 * S] = wavespeed_rot(gamma, gm1, rinv, U.m1, U.E);
+      o[11 * S] = wavespeed_rot(gamma, gm1, rinv, U.m2, U.E);
+    }
+  }
+  __syncthreads();
+
+  // ---- line phase.  G = wJ * (rhsxyH - rhsxyL) along this line (SUBCELL) or the two parts.
+  int pos[N1D];
+  double G[N1D][4], GHs[N1D][4];
+  double dF0[4];
+  double wJ[N1D], rwJ[N1D];
+  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
+#pragma unroll
+  for (int a = 0; a < N1D; ++a) {
+    const int i = d == 0 ? a : line, j = d == 0 ? line : a;
+    pos[a] = node_pos<N1D>(el, i, j);
+    const int node = i + j * N1D;
+    wJ[a] = A.Jq * T.wq[node]; rwJ[a] = T.rwJ[node];
+  }
+  if (active) {
+    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
+    Nbr nb[2];
+    ConsR Unb[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
+      const double *p = A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4;
+      Unb[e].rho = p[0]; Unb[e].mn = p[1 + d]; Unb[e].mt = p[2 - d]; Unb[e].E = p[3];
+    }
+    double lamPair[N1D], lamFace[2];
+    {
+      // ---- low-order graph-viscosity terms + both surface fluxes (low_order_graph_viscosity.jl:139-204,
+      //      flux_differencing.jl:90-151,223-272)
+      ConsR U[N1D];
+      double fl[N1D][4], ws[N1D], GL[N1D][4];
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        const double *o = nodes + pos[a];
+        U[a].rho = o[0 * S]; U[a].mn = o[(1 + d) * S]; U[a].mt = o[(2 - d) * S]; U[a].E = o[3 * S];
+        flux_rot(U[a], o[(4 + d) * S], o[(5 - d) * S], o[6 * S], fl[a]);
+        ws[a] = o[(10 + d) * S];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) GL[a][c] = 0.0;
+      }
+      if (DO_LOW) {
+#pragma unroll
+        for (int a = 0; a < N1D - 1; ++a) {
+          const int i = a + 1, j = a;
+          double Sv = T.S0[d][line][a];
+          double lam = fabs(Sv) * fmax(ws[i], ws[j]);
+          lamPair[a] = lam;
+          const double ui[4] = {U[i].rho, U[i].mn, U[i].mt, U[i].E}, uj[4] = {U[j].rho, U[j].mn, U[j].mt, U[j].E};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            double SF = 2.0 * Sv * (0.5 * (fl[i][c] + fl[j][c])) - lam * (uj[c] - ui[c]);
+            GL[i][c] -= SF; GL[j][c] += SF;          // GL = -Q0F1
+          }
+        }
+        lamPair[N1D - 1] = 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dF0[c] = 0.0;
+#pragma unroll
+      for (int a = 0; a < N1D; ++a)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) GHs[a][c] = 0.0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ae = e ? N1D - 1 : 0;
+        double B = T.Bf[d][line][e], nn = fabs(B);
+        double rinvP = rcp_fast(Unb[e].rho);
+        double wsP = wavespeed_rot(gamma, gm1, rinvP, Unb[e].mn, Unb[e].E);
+        double lamB = 0.5 * nn * fmax(ws[ae], wsP);
+        ConsR uP = Unb[e];
+        if (nb[e].bc) {
+          if (nb[e].bc == 1) { const double *p = nb[e].ival; uP.rho = p[0]; uP.mn = p[1 + d]; uP.mt = p[2 - d]; uP.E = p[3]; }
+          else uP = U[ae];
+          rinvP = rcp_fast(uP.rho);
+        }
+        double fP[4];
+        flux_rot(uP, uP.mn * rinvP, uP.mt * rinvP, gm1 * (uP.E - 0.5 * (uP.mn * uP.mn + uP.mt * uP.mt) * rinvP), fP);
+        const double up[4] = {uP.rho, uP.mn, uP.mt, uP.E}, uf[4] = {U[ae].rho, U[ae].mn, U[ae].mt, U[ae].E};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
+          double lf = lamB * (up[c] - uf[c]);
+          GL[ae][c] -= bfs - lf;                         // - BF_L
+          GHs[ae][c] -= nb[e].bc ? bfs : bfs - lf;       // - BF_H (LFc = 0 on inflow/outflow faces)
+          if (e == 0 && nb[e].bc) dF0[c] = lf;           // BF_H - BF_L on the seed face
+        }
+        lamFace[e] = lamB;
+      }
+      // publish rhsxyL_d = GL / wJ (scale_low_order_rhs_by_mass! :206-220) and the CFL lambdas
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        if (DO_LOW) {
+          partsL[(d * 2 + 0) * S + pos[a]] = make_double2(GL[a][0] * rwJ[a], GL[a][1] * rwJ[a]);
+          partsL[(d * 2 + 1) * S + pos[a]] = make_double2(GL[a][2] * rwJ[a], GL[a][3] * rwJ[a]);
+          if (A.nstage == 1) {
+            lamp[(d * 3 + 0) * S + pos[a]] = a > 0 ? lamPair[a - 1] : 0.0;
+            lamp[(d * 3 + 1) * S + pos[a]] = lamPair[a];
+            lamp[(d * 3 + 2) * S + pos[a]] = a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0);
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) G[a][c] = -GL[a][c];
+      }
+    }
+    if (DO_HIGH) {
+      // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer)
+      PrimR q[N1D];
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        const double *o = nodes + pos[a];
+        q[a].rho = o[0 * S]; q[a].un = o[(4 + d) * S]; q[a].ut = o[(5 - d) * S];
+        q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
+      }
+#pragma unroll
+      for (int j = 0; j < N1D; ++j)
+#pragma unroll
+        for (int i = j + 1; i < N1D; ++i) {
+          double F[4];
+          fS_rot(A.half_inv_gm1, q[i], q[j], F);
+          double Sv = T.SH[d][line][i][j];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; GHs[i][c] -= Sf; GHs[j][c] += Sf; }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      if (MODE != MODE_SUBCELL && DO_HIGH) {
+        partsH[(d * 2 + 0) * S + pos[a]] = make_double2(GHs[a][0] * rwJ[a], GHs[a][1] * rwJ[a]);
+        partsH[(d * 2 + 1) * S + pos[a]] = make_double2(GHs[a][2] * rwJ[a], GHs[a][3] * rwJ[a]);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) G[a][c] += GHs[a][c];   // wJ (rhsxyH - rhsxyL)
+    }
+  }
+  __syncthreads();
+
+  // ---- CFL: dt = min_i CFL * 0.5 * wJ_i / lambda_i, low_order_graph_viscosity.jl:222-281
+  if (DO_LOW && A.nstage == 1) {
+    double dtloc = INFINITY;
+    if (active && d == 0) {
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        double li = 0.0;
+        li += lamp[3 * S + pos[a]]; li += lamp[0 * S + pos[a]]; li += lamp[1 * S + pos[a]]; li += lamp[4 * S + pos[a]];
+        li += lamp[2 * S + pos[a]]; li += lamp[5 * S + pos[a]];
+        dtloc = jl_min(dtloc, A.CFL * 0.5 * wJ[a] / li);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) dtloc = jl_min(dtloc, __shfl_xor_sync(0xffffffffu, dtloc, off));
+    if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
+  }
+
+  if (!active && MODE != MODE_ZHANGSHU) return;
+
+  if (MODE == MODE_SUBCELL) {
+    // ---- f_bar_H - f_bar_L by prefix sum (subcell.jl:163-206) and the limiting coefficients of
+    //      this line's N1D+1 subcell faces (subcell.jl:248-349)
+    double dFv[NF][4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) dFv[0][c] = dF0[c];
+#pragma unroll
+    for (int s = 1; s < NF; ++s)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + G[s - 1][c];
+    Cons2 uL[N1D];
+    double Lrho[N1D], Lrhoe[N1D], c0[N1D];
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      const double *o = nodes + pos[a];
+      double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
+      double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
+      // the other direction's share is in ITS rotated frame: momentum components swap
+      double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
+      uL[a].rho = o[0 * S] + dtl * r0; uL[a].m1 = o[(1 + d) * S] + dtl * r1;
+      uL[a].m2 = o[(2 - d) * S] + dtl * r2; uL[a].E = o[3 * S] + dtl * r3;
+      Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
+      c0[a] = quad_coeff_c(uL[a], Lrhoe[a]);
+      if (d == 0) {
+        const int node = a + line * N1D;
+        double r[4] = {r0, r1, r2, r3};
+        store4(A.rhsL + (k * Nq + node) * 4, r);
+        if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+      }
+    }
+    double lv[NF];
+#pragma unroll
+    for (int s = 0; s < NF; ++s) {
+      double l = 1.0;
+      if (s < N1D) {   // node to the right/top of the face: P = -4 dt (fH - fL) / wJ (subcell.jl:300,328)
+        double Pv[4], kk = -4 * dtl * rwJ[s];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]));
+      }
+      if (s >= 1) {    // node to the left/bottom: P = +4 dt (fH - fL) / wJ (subcell.jl:312,340)
+        double Pv[4], kk = 4 * dtl * rwJ[s - 1];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
+        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
+      }
+      lv[s] = jl_min(l, A.blend);
+    }
+    // dF is stored in the line's rotated frame (update_kernel knows)
+    double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
+#pragma unroll
+    for (int s = 0; s < NF; ++s) store4(dst + s * 4, dFv[s]);
+    double *ldst = A.lpre + (k * 2 + d) * (N1D * NF);
+#pragma unroll
+    for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
+    if (A.rhsH_diag) {   // diagnostics: rhsH = rhsL + sum_d G_d / wJ; each line adds its share (buffer pre-zeroed)
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        const int node = d == 0 ? a + line * N1D : line + a * N1D;
+        double *hd = A.rhsH_diag + (k * Nq + node) * 4;
+        atomicAdd(hd + 0, GHs[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, GHs[a][1] * rwJ[a]);
+        atomicAdd(hd + 2 - d, GHs[a][2] * rwJ[a]); atomicAdd(hd + 3, GHs[a][3] * rwJ[a]);
+      }
+    }
+    return;
+  }
+
+  // ---- element-local limiters / no limiter: x-line threads produce rhsU
+  double rL[N1D][4], rH[N1D][4];
+  double lline = 1.0;
+  if (active && d == 0) {
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      const double *o = nodes + pos[a];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { rL[a][c] = 0.0; rH[a][c] = 0.0; }
+      if (DO_LOW) {
+        double2 m0 = partsL[0 * S + pos[a]], m1 = partsL[1 * S + pos[a]], o0 = partsL[2 * S + pos[a]], o1 = partsL[3 * S + pos[a]];
+        rL[a][0] = m0.x + o0.x; rL[a][1] = m0.y + o1.x; rL[a][2] = m1.x + o0.y; rL[a][3] = m1.y + o1.y;
+      }
+      if (DO_HIGH) {
+        double2 m0 = partsH[0 * S + pos[a]], m1 = partsH[1 * S + pos[a]], o0 = partsH[2 * S + pos[a]], o1 = partsH[3 * S + pos[a]];
+        rH[a][0] = m0.x + o0.x; rH[a][1] = m0.y + o1.x; rH[a][2] = m1.x + o0.y; rH[a][3] = m1.y + o1.y;
+      }
+      if (MODE == MODE_ZHANGSHU) {   // zhangshu.jl:4-45
+        Cons2 uL;
+        uL.rho = o[0 * S] + dtl * rL[a][0]; uL.m1 = o[1 * S] + dtl * rL[a][1];
+        uL.m2 = o[2 * S] + dtl * rL[a][2]; uL.E = o[3 * S] + dtl * rL[a][3];
+        double Pv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) Pv[c] = dtl * (rH[a][c] - rL[a][c]);
+        double Lrhoe = A.zeta * rhoe2(uL);
+        lline = jl_min(lline, limiting_param_pos(A.ZEROTOL, uL, quad_coeff_c(uL, Lrhoe), Pv, A.zeta * uL.rho, Lrhoe));
+      }
+    }
+    if (MODE == MODE_ZHANGSHU) lmin[el * N1D + line] = lline;
+  }
+  double l = 1.0;
+  if (MODE == MODE_ZHANGSHU) {
+    __syncthreads();
+    if (!active) return;
+#pragma unroll
+    for (int j = 0; j < N1D; ++j) l = jl_min(l, lmin[el * N1D + j]);
+    if (d == 0 && line == 0) A.Lout[k] = l;
+    l = jl_min(l, A.blend);
+  }
+  if (d == 0) {
+#pragma unroll
+    for (int a = 0; a < N1D; ++a) {
+      const int node = a + line * N1D;
+      double r[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        r[c] = MODE == MODE_ZHANGSHU ? (1 - l) * rL[a][c] + l * rH[a][c] : (MODE == MODE_LOW ? rL[a][c] : rH[a][c]);
+      store4(A.rhsU + (k * Nq + node) * 4, r);
+      if (A.rhsL_diag && DO_LOW) store4(A.rhsL_diag + (k * Nq + node) * 4, rL[a]);
+      if (A.rhsH_diag && DO_HIGH) store4(A.rhsH_diag + (k * Nq + node) * 4, rH[a]);
+    }
+  }
+}
+
+}  // namespace p2de

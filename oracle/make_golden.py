@@ -1,0 +1,58 @@
+"""Generates tests/golden/*.npz with the CPU oracle (oracle/p2de_oracle.cpp).
+
+The reference's own tests pin no numbers (test/test_smoke.jl only checks that nothing throws)
+and Julia is not installed here, so these vectors pin the ORACLE (and through it the CUDA path)
+against regressions; they are not outputs of the Julia code ("parity unpinned").
+
+    python oracle/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import problems as P  # noqa: E402
+from oracle.oracle import Oracle  # noqa: E402
+from p2de_b200 import SubcellLimiter, ZhangShuLimiter  # noqa: E402
+
+CASES = {
+    # test/test_smoke.jl:44-67: vortex, K=(5,5), T=2e-2, CFL=1, dt0=1e-2 -> 2 steps
+    **{f"smoke_vortex_N{N}_{name}": (lambda N=N, lim=lim: P.vortex(N=N, K=(5, 5), limiter=lim), 2)
+       for N in (1, 2, 3, 4) for name, lim in (("subcell", SubcellLimiter()), ("zhangshu", ZhangShuLimiter()))},
+    "dmr_N3_subcell": (lambda: P.dmr(N=3, K=(16, 4)), 5),
+    "sedov_N2_zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 5),
+}
+
+
+def run_case(factory, nsteps):
+    param, rd, md, dd, bc, U0 = P.setup(factory())
+    orc = Oracle(param, dd, bc, threads=1)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    dt1 = orc.rhs(tp.t0, tp.CFL * tp.dt0, 1)
+    out = {"U0": U0, "rhsU_stage1": orc.field("rhsU"), "dt_stage1": np.array(dt1)}
+    if param.rhs_limiter.code == 2:
+        out["L_local_stage1"] = orc.field("L_local")[0]
+    else:
+        out["L_stage1"] = orc.field("L")[0]
+    orc.set_state(U0)
+    t, dth = tp.t0, []
+    for _ in range(nsteps):
+        if t >= tp.T:
+            break
+        dt = orc.ssp33_step(t)
+        t += dt
+        dth.append(dt)
+    out["U_final"] = orc.get_state()
+    out["dthist"] = np.array(dth)
+    return out
+
+
+if __name__ == "__main__":
+    outdir = os.path.join(ROOT, "tests", "golden")
+    for name, (factory, nsteps) in CASES.items():
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **run_case(factory, nsteps))
+        print("wrote", name)

@@ -1,0 +1,56 @@
+"""Golden vectors (tests/golden/*.npz, made by oracle/make_golden.py): pin the oracle on CPU and
+the CUDA path on the GPU against regressions."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import problems as P
+from oracle.make_golden import CASES, run_case
+
+GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def rel(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_oracle_reproduces_golden(path):
+    name = os.path.basename(path)[:-4]
+    g = np.load(path)
+    out = run_case(*CASES[name])
+    for key in g.files:
+        assert rel(out[key], g[key]) < 1e-13, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_gpu_reproduces_golden(path):
+    from p2de_b200 import TimeParam
+    from p2de_b200.api import State, rhs
+    from p2de_b200.types import Solver
+    name = os.path.basename(path)[:-4]
+    g = np.load(path)
+    factory, nsteps = CASES[name]
+    param, rd, md, dd, bc, U0 = P.setup(factory())
+    assert np.array_equal(U0, g["U0"])
+    solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc)
+    st.set_state(U0)
+    tp = param.timestepping_param
+    dt1 = rhs(st, solver, None, TimeParam(t=tp.t0, dt=tp.CFL * tp.dt0, nstage=1))
+    assert abs(dt1 - float(g["dt_stage1"])) <= 1e-13 * dt1
+    assert rel(st.preallocation.rhsU, g["rhsU_stage1"]) < 1e-12
+    if "L_local_stage1" in g.files:
+        assert np.abs(st.preallocation.L_local[0] - g["L_local_stage1"]).max() < 1e-12
+    else:
+        assert np.abs(st.preallocation.L[0] - g["L_stage1"]).max() < 1e-12
+    st.set_state(U0)
+    t = tp.t0
+    for i in range(len(g["dthist"])):
+        dt = st.ssp33_step(t)
+        t += dt
+        assert abs(dt - g["dthist"][i]) <= 1e-10 * dt
+    assert rel(st.preallocation.Uq, g["U_final"]) < 1e-8

@@ -144,13 +144,27 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     w = WORKLOADS[args.workload]
     K = w["K"]
-    param, ic, _ = build_problem(args.workload, K)
+    # weak scaling: every rank owns a K[0] x K[1] stripe of element rows of a K[0] x (K[1]*world)
+    # mesh on a domain stretched in y accordingly (y-stripes)
+    import dataclasses
+    from p2de_b200.partition import local_bcdata, local_param
+    gparam, ic, _ = build_problem(args.workload, K)
+    Ly = gparam.xR[1] - gparam.xL[1]
+    gparam = dataclasses.replace(gparam, K=(K[0], K[1] * world), xR=(gparam.xR[0], gparam.xL[1] + Ly * world))
+    gbc, periodic = boundary_data_light(gparam, args.workload)
+    param = local_param(gparam, rank, world)
+    bc = local_bcdata(gparam, gbc, rank, world)
     rd, md, dd = initialize_data(param, light=True)
-    bc, periodic = boundary_data_light(param, args.workload)
     solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
     st = State(solver, bc, device=local, structured_bc=periodic)
     stream = torch.cuda.current_stream()
     st.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(State.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        st.comm_init(rank, world, bytes(uid.cpu().tolist()))
     sz = dd.sizes
     host = torch.empty((sz.K, sz.Nq, sz.Nc), dtype=torch.float64, pin_memory=True)
     initial_state(param, rd, ic, host.numpy())

@@ -162,6 +162,19 @@ class State:
     def get_state_async_ptr(self, host_ptr: int):
         _lib.check(self.L, self.h, self.L.p2de_get_state_async(self.h, C.c_void_p(host_ptr)))
 
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        """128-byte ncclUniqueId (call on one rank, broadcast to the others)."""
+        L = _lib.load()
+        buf = (C.c_uint8 * 128)()
+        _lib.check(L, None, L.p2de_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank: int, nranks: int, unique_id: bytes):
+        """Join the y-stripe communicator: this handle owns stripe `rank` of `nranks`."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _lib.check(self.L, self.h, self.L.p2de_comm_init(self.h, rank, nranks, buf))
+
     def kernel_launch_count(self) -> int:
         return int(self.L.p2de_kernel_launch_count(self.h))
 

@@ -10,7 +10,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libp2de_b200.so")
 SOURCES = ["capi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
 def _nvcc() -> str:

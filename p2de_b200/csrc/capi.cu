@@ -4,6 +4,8 @@
 // Julia reaches through `ccall` (julia/P2DEB200.jl) and what the Python mirror (p2de_b200/) and
 // the tests reach through ctypes.  No torch types, no exceptions across the boundary.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -23,10 +25,52 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DeviceBuf {
-  void *p = nullptr;
-  size_t bytes = 0;
+// NCCL is resolved at run time (dlopen) so that the library also loads on machines without it;
+// only p2de_comm_* need it.  Inside a torch process this finds the libnccl torch already loaded.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  const char *(*GetErrorString)(ncclResult_t);
 };
+
+const NcclApi *nccl_api(std::string *why) {
+  static NcclApi api;
+  static int state = 0;   // 0 untried, 1 ok, -1 failed
+  static std::string err;
+  if (state == 0) {
+    void *lib = nullptr;
+    const char *env = getenv("P2DE_NCCL_LIB");
+    const char *cands[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *c : cands) {
+      if (!c) continue;
+      lib = dlopen(c, RTLD_NOW | RTLD_GLOBAL);
+      if (lib) break;
+    }
+    if (!lib) { err = std::string("cannot load NCCL (set P2DE_NCCL_LIB): ") + dlerror(); state = -1; }
+    else {
+      bool ok = true;
+      auto sym = [&](const char *name) { void *f = dlsym(lib, name); if (!f) { ok = false; err = std::string("NCCL symbol missing: ") + name; } return f; };
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(sym("ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(sym("ncclCommInitRank"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(sym("ncclCommDestroy"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(sym("ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(sym("ncclGroupEnd"));
+      api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
+      state = ok ? 1 : -1;
+    }
+  }
+  if (state != 1) { if (why) *why = err; return nullptr; }
+  return &api;
+}
 
 }  // namespace
 
@@ -66,6 +110,10 @@ struct p2de_handle {
   double *bc_val[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void *> owned;
   double last_dt = 0;
+  // multi-GPU (y-stripes, one handle per GPU): NCCL communicator and stripe neighbours
+  int rank = 0, nranks = 1, rank_lo = 0, rank_hi = 0;
+  bool has_lo = false, has_hi = false;
+  ncclComm_t comm = nullptr;
   // optional per-kernel timing (p2de_profile): one event pair per launch, on h->stream
   bool profiling = false;
   struct ProfRec { cudaEvent_t a, b; int kid; };
@@ -113,6 +161,38 @@ void prof_end(p2de_handle *h) {
 void prof_clear(p2de_handle *h) {
   for (auto &r : h->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   h->prof.clear();
+}
+
+// array of `n` owned doubles plus one halo row of `row` doubles on each side; *p points at the
+// first OWNED entry, so element indices -Kx..-1 and K..K+Kx-1 address the halo rows.
+int dev_alloc_halo(p2de_handle *h, double **p, size_t n, size_t row) {
+  double *base = nullptr;
+  if (int rc = dev_alloc(h, &base, n + 2 * row)) return rc;
+  CU(h, cudaMemset(base, 0, (n + 2 * row) * sizeof(double)));
+  *p = base + row;
+  return 0;
+}
+
+#define NC(h, call)                                                                                  \
+  do {                                                                                               \
+    ncclResult_t r_ = (call);                                                                        \
+    if (r_ != ncclSuccess) return fail(h, P2DE_ERR_NCCL, "%s: %s", #call, nccl_api(nullptr)->GetErrorString(r_)); \
+  } while (0)
+
+// halo exchange of one boundary element row (`row` doubles) with the stripes below and above.
+// Issue order (sends up, down; receives from below, above) keeps the pairing right when both
+// neighbours are the same rank (2 ranks, periodic).
+int exchange_rows(p2de_handle *h, double *owned, size_t row) {
+  if (!h->comm) return 0;
+  const NcclApi *n = nccl_api(nullptr);
+  const size_t nown = (size_t)h->cfg.Ky * row;
+  NC(h, n->GroupStart());
+  if (h->has_hi) NC(h, n->Send(owned + nown - row, row, ncclDouble, h->rank_hi, h->comm, h->stream));
+  if (h->has_lo) NC(h, n->Send(owned, row, ncclDouble, h->rank_lo, h->comm, h->stream));
+  if (h->has_lo) NC(h, n->Recv(owned - row, row, ncclDouble, h->rank_lo, h->comm, h->stream));
+  if (h->has_hi) NC(h, n->Recv(owned + nown, row, ncclDouble, h->rank_hi, h->comm, h->stream));
+  NC(h, n->GroupEnd());
+  return 0;
 }
 
 template <int N1D>
@@ -431,8 +511,17 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   }
   if (h->rhsH_diag && h->mode == MODE_SUBCELL)
     CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * 4 * sizeof(double), h->stream));
+  // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
+  if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
   if (int rc = launch_stage(h, A)) return rc;
+  if (h->comm) {
+    if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
+      NC(h, nccl_api(nullptr)->AllReduce(h->dt_bits, h->dt_bits, 1, ncclDouble, ncclMin, h->comm, h->stream));
+    // E2: un-symmetrised interface coefficients of the neighbouring stripes' boundary rows
+    if (h->mode == MODE_SUBCELL)
+      if (int rc = exchange_rows(h, h->lpre, (size_t)h->cfg.Kx * 2 * h->N1D * (h->N1D + 1))) return rc;
+  }
   UpdateArgs B{};
   B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
   B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)(h->Nq + h->N1D) * 2 * h->K * (nstage - 1) : nullptr;
@@ -523,10 +612,11 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if ((rc = setup_topology(h, bc))) return bail(rc);
 
   const size_t nU = (size_t)h->K * h->Nq * 4;
-  if ((rc = dev_alloc(h, &h->U[0], nU)) || (rc = dev_alloc(h, &h->U[1], nU))) return bail(rc);
+  const size_t rowU = (size_t)cfg->Kx * h->Nq * 4, rowL = (size_t)cfg->Kx * 2 * N1D * (N1D + 1);
+  if ((rc = dev_alloc_halo(h, &h->U[0], nU, rowU)) || (rc = dev_alloc_halo(h, &h->U[1], nU, rowU))) return bail(rc);
   if (mode == MODE_SUBCELL) {
     if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)) ||
-        (rc = dev_alloc(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1))))
+        (rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL)))
       return bail(rc);
   } else {
     if ((rc = ensure_rhsU(h))) return bail(rc);
@@ -546,6 +636,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
 int32_t p2de_destroy(p2de_handle *h) {
   if (!h) return P2DE_OK;
   cudaSetDevice(h->device);
+  if (h->comm) { if (const NcclApi *n = nccl_api(nullptr)) n->CommDestroy(h->comm); }
   prof_clear(h);
   for (void *p : h->owned) cudaFree(p);
   delete h;
@@ -716,7 +807,45 @@ int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, in
 int64_t p2de_kernel_launch_count(const p2de_handle *h) { return h ? h->launches : 0; }
 void *p2de_device_state_ptr(p2de_handle *h) { return h ? h->U[h->cur] : nullptr; }
 
-int32_t p2de_comm_unique_id(uint8_t id_out[128]) { (void)id_out; g_create_error = "multi-GPU not built yet"; return P2DE_ERR_UNSUPPORTED; }
-int32_t p2de_comm_init(p2de_handle *h, int32_t, int32_t, const uint8_t *) { return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU not built yet"); }
+int32_t p2de_comm_unique_id(uint8_t id_out[128]) {
+  if (!id_out) return fail(nullptr, P2DE_ERR_ARG, "null argument");
+  std::string why;
+  const NcclApi *n = nccl_api(&why);
+  if (!n) return fail(nullptr, P2DE_ERR_NCCL, "%s", why.c_str());
+  ncclUniqueId id;
+  ncclResult_t r = n->GetUniqueId(&id);
+  if (r != ncclSuccess) return fail(nullptr, P2DE_ERR_NCCL, "ncclGetUniqueId: %s", n->GetErrorString(r));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  std::memcpy(id_out, &id, 128);
+  return P2DE_OK;
+}
+
+int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8_t unique_id[128]) {
+  if (!h || !unique_id) return fail(h, P2DE_ERR_ARG, "null argument");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, P2DE_ERR_ARG, "rank %d of %d", rank, nranks);
+  if (h->topo.mapP32) return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU needs the structured mesh path (y-stripes)");
+  if (h->comm) return fail(h, P2DE_ERR_STATE, "communicator already initialised");
+  h->rank = rank; h->nranks = nranks;
+  if (nranks == 1) return P2DE_OK;
+  std::string why;
+  const NcclApi *n = nccl_api(&why);
+  if (!n) return fail(h, P2DE_ERR_NCCL, "%s", why.c_str());
+  ncclUniqueId id;
+  std::memcpy(&id, unique_id, 128);
+  CU(h, cudaSetDevice(h->device));
+  ncclComm_t comm = nullptr;
+  ncclResult_t r = n->CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) return fail(h, P2DE_ERR_NCCL, "ncclCommInitRank: %s", n->GetErrorString(r));
+  h->comm = comm;
+  // y-stripes: rank r owns element rows [r*Ky, (r+1)*Ky) of the global mesh; the stripe below /
+  // above is rank -/+ 1, wrapping around when the global mesh is periodic in y.
+  const bool per_y = h->topo.periodic_y != 0;
+  h->has_lo = rank > 0 || per_y;
+  h->has_hi = rank < nranks - 1 || per_y;
+  h->rank_lo = (rank - 1 + nranks) % nranks;
+  h->rank_hi = (rank + 1) % nranks;
+  h->topo.ghost_lo = h->has_lo; h->topo.ghost_hi = h->has_hi;
+  return P2DE_OK;
+}
 
 }  // extern "C"

@@ -45,6 +45,7 @@ struct Tables2D {
 struct MeshTopo {
   long long K;
   int Kx, Ky, periodic_x, periodic_y;
+  int ghost_lo, ghost_hi;            // multi-GPU y-stripes: element row -1 / row Ky is a halo row owned by rank -/+ 1
   const int *mapP32;                 // generic mode: [K][Nfp] 0-based linear index; nullptr = structured
   const int *bcflag;                 // generic mode: 0 none, >0 inflow (index+1 into Ival), -1 outflow
   const double *Ival;                // generic mode: [nI][4]
@@ -101,6 +102,10 @@ P2DE_DEV Nbr neighbor(const MeshTopo &M, long long k, int ix, int iy, int f) {
   int F = f / N1D, a = f % N1D;
   int jx = ix + (F == 0 ? -1 : F == 1 ? 1 : 0), jy = iy + (F == 2 ? -1 : F == 3 ? 1 : 0);
   bool out = jx < 0 || jx >= M.Kx || jy < 0 || jy >= M.Ky;
+  if (out && ((F == 2 && M.ghost_lo) || (F == 3 && M.ghost_hi))) {
+    nb.kP = jx + (long long)jy * M.Kx; nb.fP = (F ^ 1) * N1D + a;   // jy = -1 or Ky: halo row
+    return nb;
+  }
   if (out) {
     bool wrap = F < 2 ? M.periodic_x : M.periodic_y;
     if (wrap) { jx = (jx + M.Kx) % M.Kx; jy = (jy + M.Ky) % M.Ky; nb.kP = jx + (long long)jy * M.Kx; nb.fP = (F ^ 1) * N1D + a; }

@@ -1,0 +1,75 @@
+"""Run under torchrun (one rank per GPU): each rank advances its y-stripe with halo exchange over
+NCCL; rank 0 also advances the whole mesh on its own GPU.  The stripes must reproduce the
+single-GPU result BITWISE (every element sees the same neighbour data and runs the same code).
+
+    python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 tests/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import problems as P  # noqa: E402
+from p2de_b200 import SubcellLimiter, ZhangShuLimiter  # noqa: E402
+from p2de_b200.api import State  # noqa: E402
+from p2de_b200.partition import local_bcdata, local_param, stripe_rows  # noqa: E402
+from p2de_b200.types import Solver  # noqa: E402
+from p2de_b200 import initialize_data  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    cases = [("dmr-subcell", P.dmr(N=3, K=(16, 12)), (False, False)),
+             ("vortex-periodic-subcell", P.vortex(N=2, K=(6, 8), CFL=0.5), (True, True)),
+             ("kh-periodic-zhangshu", P.kelvin_helmholtz(N=3, K=(8, 8), limiter=ZhangShuLimiter()), (True, True))]
+    for name, problem, periodic in cases:
+        param, rd, md, dd, bc, U0 = P.setup(problem)
+        Kx, Ky = param.K
+        lp = local_param(param, rank, world)
+        lrd, lmd, ldd = initialize_data(lp, light=True)
+        lbc = local_bcdata(param, bc, rank, world)
+        iy0, iy1 = stripe_rows(Ky, rank, world)
+        st = State(Solver(param=lp, rd=lrd, md=lmd, discrete_data=ldd), lbc, device=local, structured_bc=periodic)
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(State.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        st.comm_init(rank, world, bytes(uid.cpu().tolist()))
+        st.set_state(U0[iy0 * Kx:iy1 * Kx])
+        t, dts = param.timestepping_param.t0, []
+        for _ in range(4):
+            dt = st.ssp33_step(t); t += dt; dts.append(dt)
+        mine = torch.from_numpy(st.preallocation.Uq).cuda()
+        parts = [torch.empty((stripe_rows(Ky, r, world)[1] - stripe_rows(Ky, r, world)[0]) * Kx, *mine.shape[1:],
+                             dtype=torch.float64, device="cuda") for r in range(world)]
+        dist.all_gather(parts, mine) if len({p.shape for p in parts}) == 1 else [dist.broadcast(parts[r] if r != rank else mine, r) for r in range(world)]
+        if len({p.shape for p in parts}) != 1:
+            parts[rank] = mine
+        if rank == 0:
+            full = State(Solver(param=param, rd=rd, md=md, discrete_data=dd), bc, device=local)
+            full.set_state(U0)
+            t2, dts2 = param.timestepping_param.t0, []
+            for _ in range(4):
+                dt = full.ssp33_step(t2); t2 += dt; dts2.append(dt)
+            ref = full.preallocation.Uq
+            got = torch.cat(parts).cpu().numpy()
+            same = np.array_equal(got, ref) and dts == dts2
+            print(f"[multigpu_check] {name}: world={world} bitwise_equal={same} max|diff|={np.abs(got - ref).max():.3e} dt={dts[-1]:.6e}")
+            ok = ok and same
+        dist.barrier()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,10 @@
 
 using namespace p2de;
 
+#ifndef P2DE_EPB
+#define P2DE_EPB 16   // elements per CTA (x 2*N1D line threads)
+#endif
+
 namespace {
 
 thread_local std::string g_create_error;
@@ -202,7 +206,7 @@ template <> Tables2D<3> &tables<3>(p2de_handle *h) { return h->t3; }
 template <> Tables2D<4> &tables<4>(p2de_handle *h) { return h->t4; }
 template <> Tables2D<5> &tables<5>(p2de_handle *h) { return h->t5; }
 
-template <int N1D> struct Launch { static constexpr int EPB = (N1D <= 4) ? 32 : 16; };
+template <int N1D> struct Launch { static constexpr int EPB = P2DE_EPB; };
 
 // Extract the per-line tables from the caller's operators and verify the structure this
 // kernel family relies on (tensor-product LGL collocation on a Cartesian mesh).

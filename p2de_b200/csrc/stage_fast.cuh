@@ -18,7 +18,7 @@
 namespace p2de {
 
 #ifndef P2DE_FAST_MIN_BLOCKS
-#define P2DE_FAST_MIN_BLOCKS 2
+#define P2DE_FAST_MIN_BLOCKS 4
 #endif
 
 // reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (error ~ seed^4)
@@ -144,7 +144,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 
   // ---- line phase.  G = wJ * (rhsxyH - rhsxyL) along this line (SUBCELL) or the two parts.
   int pos[N1D];
-  double G[N1D][4], GHs[N1D][4];
+  double G[N1D][4];
   double dF0[4];
   double wJ[N1D], rwJ[N1D];
   const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
@@ -196,12 +196,9 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         }
         lamPair[N1D - 1] = 0.0;
       }
+      double BFH[2][4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) dF0[c] = 0.0;
-#pragma unroll
-      for (int a = 0; a < N1D; ++a)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) GHs[a][c] = 0.0;
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ae = e ? N1D - 1 : 0;
@@ -223,7 +220,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
           double lf = lamB * (up[c] - uf[c]);
           GL[ae][c] -= bfs - lf;                         // - BF_L
-          GHs[ae][c] -= nb[e].bc ? bfs : bfs - lf;       // - BF_H (LFc = 0 on inflow/outflow faces)
+          BFH[e][c] = nb[e].bc ? bfs : bfs - lf;         // BF_H (LFc = 0 on inflow/outflow faces)
           if (e == 0 && nb[e].bc) dF0[c] = lf;           // BF_H - BF_L on the seed face
         }
         lamFace[e] = lamB;
@@ -240,8 +237,14 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
             lamp[(d * 3 + 2) * S + pos[a]] = a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0);
           }
         }
+        // G starts as -wJ rhsxyL - BF_H; the volume pairs below add the rest of wJ rhsxyH.
+        // (MODE_SUBCELL keeps only the difference; the other modes keep wJ rhsxyH by itself.)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) G[a][c] = -GL[a][c];
+        for (int c = 0; c < 4; ++c) {
+          double bh = a == 0 ? BFH[0][c] : 0.0;
+          if (a == N1D - 1) bh += BFH[1][c];
+          G[a][c] = (MODE == MODE_SUBCELL ? -GL[a][c] : 0.0) - bh;
+        }
       }
     }
     if (DO_HIGH) {
@@ -261,17 +264,15 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           fS_rot(A.half_inv_gm1, q[i], q[j], F);
           double Sv = T.SH[d][line][i][j];
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; GHs[i][c] -= Sf; GHs[j][c] += Sf; }
+          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
         }
     }
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       if (MODE != MODE_SUBCELL && DO_HIGH) {
-        partsH[(d * 2 + 0) * S + pos[a]] = make_double2(GHs[a][0] * rwJ[a], GHs[a][1] * rwJ[a]);
-        partsH[(d * 2 + 1) * S + pos[a]] = make_double2(GHs[a][2] * rwJ[a], GHs[a][3] * rwJ[a]);
+        partsH[(d * 2 + 0) * S + pos[a]] = make_double2(G[a][0] * rwJ[a], G[a][1] * rwJ[a]);
+        partsH[(d * 2 + 1) * S + pos[a]] = make_double2(G[a][2] * rwJ[a], G[a][3] * rwJ[a]);
       }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) G[a][c] += GHs[a][c];   // wJ (rhsxyH - rhsxyL)
     }
   }
   __syncthreads();
@@ -305,8 +306,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     for (int s = 1; s < NF; ++s)
 #pragma unroll
       for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + G[s - 1][c];
-    Cons2 uL[N1D];
-    double Lrho[N1D], Lrhoe[N1D], c0[N1D];
+    // node by node: u^L = Uq + dt rhsL (subcell.jl:269), its bounds, and the two subcell faces
+    // next to it (P = -/+ 4 dt (fH - fL) / wJ, subcell.jl:300,312,328,340)
+    double lv[NF];
+#pragma unroll
+    for (int s = 0; s < NF; ++s) lv[s] = 1.0;
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       const double *o = nodes + pos[a];
@@ -314,35 +318,32 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
       // the other direction's share is in ITS rotated frame: momentum components swap
       double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
-      uL[a].rho = o[0 * S] + dtl * r0; uL[a].m1 = o[(1 + d) * S] + dtl * r1;
-      uL[a].m2 = o[(2 - d) * S] + dtl * r2; uL[a].E = o[3 * S] + dtl * r3;
-      Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
-      c0[a] = quad_coeff_c(uL[a], Lrhoe[a]);
+      Cons2 uL;
+      uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
+      uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
+      const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoe2(uL);
+      const double c0 = quad_coeff_c(uL, Lrhoe);
       if (d == 0) {
         const int node = a + line * N1D;
         double r[4] = {r0, r1, r2, r3};
         store4(A.rhsL + (k * Nq + node) * 4, r);
         if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
       }
-    }
-    double lv[NF];
-#pragma unroll
-    for (int s = 0; s < NF; ++s) {
-      double l = 1.0;
-      if (s < N1D) {   // node to the right/top of the face: P = -4 dt (fH - fL) / wJ (subcell.jl:300,328)
-        double Pv[4], kk = -4 * dtl * rwJ[s];
-#pragma unroll
-        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]));
+      if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
+        const int node = d == 0 ? a + line * N1D : line + a * N1D;
+        double *hd = A.rhsH_diag + (k * Nq + node) * 4;
+        atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
+        atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
       }
-      if (s >= 1) {    // node to the left/bottom: P = +4 dt (fH - fL) / wJ (subcell.jl:312,340)
-        double Pv[4], kk = 4 * dtl * rwJ[s - 1];
+      const double kk = 4 * dtl * rwJ[a];
+      double Pm[4], Pp[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
-      }
-      lv[s] = jl_min(l, A.blend);
+      for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
+      lv[a] = jl_min(lv[a], limiting_param_pos(A.ZEROTOL, uL, c0, Pm, Lrho, Lrhoe));
+      lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos(A.ZEROTOL, uL, c0, Pp, Lrho, Lrhoe));
     }
+#pragma unroll
+    for (int s = 0; s < NF; ++s) lv[s] = jl_min(lv[s], A.blend);
     // dF is stored in the line's rotated frame (update_kernel knows)
     double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
 #pragma unroll
@@ -350,15 +351,6 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     double *ldst = A.lpre + (k * 2 + d) * (N1D * NF);
 #pragma unroll
     for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
-    if (A.rhsH_diag) {   // diagnostics: rhsH = rhsL + sum_d G_d / wJ; each line adds its share (buffer pre-zeroed)
-#pragma unroll
-      for (int a = 0; a < N1D; ++a) {
-        const int node = d == 0 ? a + line * N1D : line + a * N1D;
-        double *hd = A.rhsH_diag + (k * Nq + node) * 4;
-        atomicAdd(hd + 0, GHs[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, GHs[a][1] * rwJ[a]);
-        atomicAdd(hd + 2 - d, GHs[a][2] * rwJ[a]); atomicAdd(hd + 3, GHs[a][3] * rwJ[a]);
-      }
-    }
     return;
   }
 

@@ -103,6 +103,7 @@ struct p2de_handle {
   double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
+  double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
   double *Lz = nullptr;       // [K, Ns]
   double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
@@ -459,7 +460,19 @@ int launch_update_t(p2de_handle *h, const UpdateArgs &A) {
   return 0;
 }
 template <int N1D>
+int launch_update_fast(p2de_handle *h, const UpdateArgs &A) {
+  constexpr int EPB = 16;
+  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  prof_begin(h, 1);
+  update_kernel_fast<N1D, EPB><<<grid, EPB * 16, 0, h->stream>>>(A, h->topo, tables<N1D>(h));
+  prof_end(h);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+template <int N1D>
 int launch_update_n(p2de_handle *h, const UpdateArgs &A) {
+  if (h->mode == MODE_SUBCELL && h->fast) return launch_update_fast<N1D>(h, A);
   if (h->mode == MODE_SUBCELL) return launch_update_t<N1D, MODE_SUBCELL>(h, A);
   return launch_update_t<N1D, MODE_LOW>(h, A);
 }
@@ -477,6 +490,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   StageArgs A{};
   A.Uq = Uq;
   A.rhsL = h->rhsL; A.dF = h->dF; A.lpre = h->lpre; A.rhsU = h->rhsU;
+  A.rpre = h->rpre; A.dFend = h->dFend;
   A.Lout = h->Lz ? h->Lz + h->K * (nstage - 1) : nullptr;
   A.rhsH_diag = h->rhsH_diag; A.rhsL_diag = h->rhsL_diag;
   A.dt_bits = h->dt_bits;
@@ -528,6 +542,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   }
   UpdateArgs B{};
   B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
+  B.rpre = h->rpre; B.dFend = h->dFend;
   B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)(h->Nq + h->N1D) * 2 * h->K * (nstage - 1) : nullptr;
   B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
@@ -619,8 +634,10 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   const size_t rowU = (size_t)cfg->Kx * h->Nq * 4, rowL = (size_t)cfg->Kx * 2 * N1D * (N1D + 1);
   if ((rc = dev_alloc_halo(h, &h->U[0], nU, rowU)) || (rc = dev_alloc_halo(h, &h->U[1], nU, rowU))) return bail(rc);
   if (mode == MODE_SUBCELL) {
-    if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)) ||
-        (rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL)))
+    if ((rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL))) return bail(rc);
+    if (h->fast) {
+      if ((rc = dev_alloc(h, &h->rpre, nU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
+    } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
   } else {
     if ((rc = ensure_rhsU(h))) return bail(rc);

@@ -55,7 +55,8 @@ struct MeshTopo {
 
 struct StageArgs {
   const double *Uq;
-  double *rhsL, *dF, *lpre;          // MODE_SUBCELL scratch
+  double *rhsL, *dF, *lpre;          // MODE_SUBCELL scratch (generic kernel: rhsL, dF, lpre; FAST: rpre, dFend, lpre)
+  double *rpre, *dFend;
   double *rhsU;                      // other modes
   double *Lout;                      // MODE_ZHANGSHU: L[:, nstage]
   double *rhsH_diag, *rhsL_diag;     // optional full fields (keep_diagnostics)
@@ -71,6 +72,7 @@ struct StageArgs {
 
 struct UpdateArgs {
   const double *rhsL, *dF, *lpre;    // MODE_SUBCELL inputs
+  const double *rpre, *dFend;        // FAST stage kernel's scratch (update_kernel_fast)
   const double *rhsU_in;             // other modes
   double *Llocal_out;                // symmetrised L_local[:, :, :, nstage] or nullptr
   double *rhsU_out;                  // or nullptr

@@ -63,21 +63,39 @@ P2DE_DEV double wavespeed_rot(double gamma, double gm1, double rinv, double mn, 
 P2DE_DEV void flux_rot(const ConsR &U, double un, double ut, double p, double f[4]) {
   f[0] = U.mn; f[1] = U.mn * un + p; f[2] = U.rho * un * ut; f[3] = un * (U.E + p);
 }
+// three independent quotients n_i / a_i, written in lock step so that the three MUFU + Newton
+// chains overlap in the instruction stream (ptxas keeps source order for straight-line code)
+P2DE_DEV void div3_fast(double n0, double a0, double n1, double a1, double n2, double a2,
+                        double &q0, double &q1, double &q2) {
+  double x0, x1, x2;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x0) : "d"(a0));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x1) : "d"(a1));
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x2) : "d"(a2));
+  double e0 = fma(-a0, x0, 1.0), e1 = fma(-a1, x1, 1.0), e2 = fma(-a2, x2, 1.0);
+  x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
+  e0 = fma(-a0, x0, 1.0); e1 = fma(-a1, x1, 1.0); e2 = fma(-a2, x2, 1.0);
+  x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
+  q0 = n0 * x0; q1 = n1 * x1; q2 = n2 * x2;
+  double r0 = fma(-a0, q0, n0), r1 = fma(-a1, q1, n1), r2 = fma(-a2, q2, n2);
+  q0 = fma(r0, x0, q0); q1 = fma(r1, x1, q1); q2 = fma(r2, x2, q2);
+}
+
 // fS (:220-249) along the line's own axis, three reciprocals (see fS_fast in physics.cuh)
 P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double F[4]) {
   double da = R.rho - L.rho, aavg = 0.5 * (R.rho + L.rho);
   bool ser = fabs(da) < 1e-4 * fabs(aavg);
-  double q = div_fast(da, ser ? aavg : (R.rholog - L.rholog));
-  double v = q * q;
-  double rholog = ser ? aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857))) : q;
   double db = R.beta - L.beta, bavg = 0.5 * (R.beta + L.beta);
   bool serb = fabs(db) < 1e-4 * fabs(bavg);
-  double qb = div_fast(serb ? 1.0 : (R.betalog - L.betalog), serb ? bavg : db);
+  double q, qb, pa;
+  div3_fast(da, ser ? aavg : (R.rholog - L.rholog),
+            serb ? 1.0 : (R.betalog - L.betalog), serb ? bavg : db,
+            aavg, L.beta + R.beta, q, qb, pa);
+  double v = q * q;
+  double rholog = ser ? aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857))) : q;
   double fb = db * qb, vb = fb * fb;
   double inv_betalog = serb ? qb * (1 + vb * (0.2 + vb * 0.0912)) : qb;
   double unavg = 0.5 * (L.un + R.un), utavg = 0.5 * (L.ut + R.ut);
   double unorm = L.un * R.un + L.ut * R.ut;
-  double pa = div_fast(aavg, L.beta + R.beta);
   double f4aux = rholog * inv_betalog * half_inv_gm1 + pa + 0.5 * rholog * unorm;
   double F1 = rholog * unavg;
   F[0] = F1; F[1] = F1 * unavg + pa; F[2] = F1 * utavg; F[3] = f4aux * unavg;
@@ -135,9 +153,14 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       double beta = 0.5 * U.rho * rcp_fast(p);
       o[0 * S] = U.rho; o[1 * S] = U.m1; o[2 * S] = U.m2; o[3 * S] = U.E;
       o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv; o[6 * S] = p; o[7 * S] = beta;
+#ifdef P2DE_EXP_NONODE
+      if (DO_HIGH) { o[8 * S] = U.rho; o[9 * S] = beta; }
+      o[10 * S] = U.m1 * rinv; o[11 * S] = U.m2 * rinv;
+#else
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
       o[10 * S] = wavespeed_rot(gamma, gm1, rinv, U.m1, U.E);
       o[11 * S] = wavespeed_rot(gamma, gm1, rinv, U.m2, U.E);
+#endif
     }
   }
   __syncthreads();
@@ -261,7 +284,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 #pragma unroll
         for (int i = j + 1; i < N1D; ++i) {
           double F[4];
+#ifdef P2DE_EXP_NOPAIRS
+          F[0] = q[i].rho + q[j].un; F[1] = q[i].ut; F[2] = q[j].beta; F[3] = q[i].rholog;
+#else
           fS_rot(A.half_inv_gm1, q[i], q[j], F);
+#endif
           double Sv = T.SH[d][line][i][j];
 #pragma unroll
           for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
@@ -294,9 +321,15 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 
-  if (!active && MODE != MODE_ZHANGSHU) return;
+  if (!active && MODE != MODE_ZHANGSHU && MODE != MODE_SUBCELL) return;
 
   if (MODE == MODE_SUBCELL) {
+    // shared-memory staging of this kernel's outputs (regions that are dead by now: node fields
+    // 4..11 are only read before the barrier above, lamp only by the CFL block)
+    double2 *tbuf = reinterpret_cast<double2 *>(nodes + 4 * S);   // [d][half][S]
+    double *lstage = lamp;                                        // [EPB][2*N1D*NF], L_local layout
+    if (MODE == MODE_SUBCELL && A.nstage == 1) __syncthreads();   // CFL block done with lamp
+    if (active) {
     // ---- f_bar_H - f_bar_L by prefix sum (subcell.jl:163-206) and the limiting coefficients of
     //      this line's N1D+1 subcell faces (subcell.jl:248-349)
     double dFv[NF][4];
@@ -323,11 +356,10 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
       const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoe2(uL);
       const double c0 = quad_coeff_c(uL, Lrhoe);
-      if (d == 0) {
+      if (d == 0 && A.rhsL_diag) {
         const int node = a + line * N1D;
         double r[4] = {r0, r1, r2, r3};
-        store4(A.rhsL + (k * Nq + node) * 4, r);
-        if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+        store4(A.rhsL_diag + (k * Nq + node) * 4, r);
       }
       if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
         const int node = d == 0 ? a + line * N1D : line + a * N1D;
@@ -339,18 +371,46 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       double Pm[4], Pp[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
+#ifdef P2DE_EXP_NOLIM
+      lv[a] = jl_min(lv[a], Pm[0] + c0 + Lrho); lv[a + 1] = jl_min(lv[a + 1], Pp[1] + Lrhoe);
+#else
       lv[a] = jl_min(lv[a], limiting_param_pos(A.ZEROTOL, uL, c0, Pm, Lrho, Lrhoe));
       lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos(A.ZEROTOL, uL, c0, Pp, Lrho, Lrhoe));
+#endif
     }
 #pragma unroll
     for (int s = 0; s < NF; ++s) lv[s] = jl_min(lv[s], A.blend);
-    // dF is stored in the line's rotated frame (update_kernel knows)
-    double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
+    // this line's share of the un-symmetrised limited rhs (subcell.jl:841-924 with the line's own
+    // coefficients): t_d = rhsxyL_d + (l_{a+1} dF_{a+1} - l_a dF_a) / wJ, in the line's rotated frame
 #pragma unroll
-    for (int s = 0; s < NF; ++s) store4(dst + s * 4, dFv[s]);
-    double *ldst = A.lpre + (k * 2 + d) * (N1D * NF);
+    for (int a = 0; a < N1D; ++a) {
+      double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
+      tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + (lv[a + 1] * dFv[a + 1][0] - lv[a] * dFv[a][0]) * rwJ[a],
+                                                    m0.y + (lv[a + 1] * dFv[a + 1][1] - lv[a] * dFv[a][1]) * rwJ[a]);
+      tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (lv[a + 1] * dFv[a + 1][2] - lv[a] * dFv[a][2]) * rwJ[a],
+                                                    m1.y + (lv[a + 1] * dFv[a + 1][3] - lv[a] * dFv[a][3]) * rwJ[a]);
+    }
+    // end-face dF (rotated frame) for the interface correction in update_kernel_fast
+    store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
+    store4(A.dFend + (k * (4 * N1D) + (2 * d + 1) * N1D + line) * 4, dFv[N1D]);
 #pragma unroll
-    for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
+    for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
+    }   // active
+    __syncthreads();
+    // ---- flat, coalesced output phase: rpre = x share + y share (y share un-rotated), lpre
+    const long long kb = (long long)blockIdx.x * EPB;
+    for (int n = tid; n < S; n += NT) {
+      const int e2 = n / Nq, node = n % Nq;
+      if (kb + e2 < M.K) {
+        const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
+        double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
+        double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
+        store4(A.rpre + ((kb + e2) * Nq + node) * 4, r);
+      }
+    }
+    constexpr int NL = 2 * N1D * NF;
+    for (int n = tid; n < EPB * NL; n += NT)
+      if (kb + n / NL < M.K) A.lpre[kb * NL + n] = lstage[n];
     return;
   }
 
@@ -404,6 +464,79 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       store4(A.rhsU + (k * Nq + node) * 4, r);
       if (A.rhsL_diag && DO_LOW) store4(A.rhsL_diag + (k * Nq + node) * 4, rL[a]);
       if (A.rhsH_diag && DO_HIGH) store4(A.rhsH_diag + (k * Nq + node) * 4, rH[a]);
+    }
+  }
+}
+
+// update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation
+// of the coefficients (subcell.jl:418-456) as a correction of the un-symmetrised limited rhs,
+//   rhsU = rpre -+ (min(l, l_P) - l) dF_end / wJ   on the nodes of the element boundary,
+// then the SSP stage combine (SSPRK33.jl:31-39).  16 threads per element: one per face node for
+// the corrections, then one per volume node with fully coalesced 32-byte accesses.
+template <int N1D, int EPB>
+__global__ void __launch_bounds__(EPB * 16)
+update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__ MeshTopo M,
+                   const __grid_constant__ Tables2D<N1D> Tc) {
+  constexpr int Nq = N1D * N1D, Nfp = 4 * N1D, NF = N1D + 1, NL = 2 * N1D * NF, TPE = 16;
+  __shared__ double corr[EPB * Nfp * 4];
+  __shared__ double s_rwJ[Nq];
+  __shared__ int s_fq2q[Nfp];
+  const int tid = threadIdx.x, el = tid / TPE, tl = tid % TPE;
+  const long long k = (long long)blockIdx.x * EPB + el;
+  const bool active = k < M.K;
+  if (tid < Nq) s_rwJ[tid] = Tc.rwJ[tid];
+  if (tid < Nfp) s_fq2q[tid] = Tc.fq2q[tid];
+  __syncthreads();
+  if (active) {
+    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
+    for (int f = tl; f < Nfp; f += TPE) {
+      const int F = f / N1D, line = f % N1D, d = F >> 1, e = F & 1;
+      const int s = e ? N1D : 0;
+      const int lidx = d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D);
+      const double lv = A.lpre[k * NL + lidx];
+      Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
+      const double lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
+      const double lsym = jl_min(lv, lP);
+      const double w = (e ? (lsym - lv) : -(lsym - lv)) * s_rwJ[s_fq2q[f]];
+      Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
+      double *c = corr + (el * Nfp + f) * 4;
+      c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
+      if (A.Llocal_out) A.Llocal_out[k * NL + lidx] = lsym;
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+  if (A.Llocal_out)   // interior subcell faces: the stage kernel's coefficients are final
+    for (int n = tl; n < NL; n += TPE) {
+      const int dd = n / (N1D * NF), r = n % (N1D * NF);
+      const int s = dd == 0 ? r % NF : r / N1D;
+      if (s != 0 && s != N1D) A.Llocal_out[k * NL + n] = A.lpre[k * NL + n];
+    }
+  for (int node = tl; node < Nq; node += TPE) {
+    const int i = node % N1D, j = node / N1D;
+    const long long off = (k * Nq + node) * 4;
+    Cons2 rp = load_cons(A.rpre + off);
+    double r[4] = {rp.rho, rp.m1, rp.m2, rp.E};
+    const double *cb = corr + el * Nfp * 4;
+    if (i == 0) { const double *c = cb + (0 * N1D + j) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
+    if (i == N1D - 1) { const double *c = cb + (1 * N1D + j) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
+    if (j == 0) { const double *c = cb + (2 * N1D + i) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
+    if (j == N1D - 1) { const double *c = cb + (3 * N1D + i) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
+    if (A.rhsU_out) store4(A.rhsU_out + off, r);
+    if (A.Uq_out) {
+      Cons2 u = load_cons(A.Uq_in + off);
+      double un[4], uo[4] = {u.rho, u.m1, u.m2, u.E};
+      if (A.b == 1.0 && A.a == 0.0) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) un[c] = uo[c] + dt * r[c];
+      } else {
+        Cons2 w = load_cons(A.resW + off);
+        const double wv[4] = {w.rho, w.m1, w.m2, w.E};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) un[c] = A.a * wv[c] + A.b * (uo[c] + dt * r[c]);
+      }
+      store4(A.Uq_out + off, un);
     }
   }
 }

@@ -10,7 +10,7 @@ import os
 from .abi import BCDataC, Config, GeometryC, OperatorsC
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libp2de_b200.so")
+SO_PATH = os.environ.get("P2DE_B200_LIB", os.path.join(HERE, "libp2de_b200.so"))
 
 EXPORTS = [
     "p2de_create", "p2de_destroy", "p2de_last_error", "p2de_set_stream", "p2de_set_state", "p2de_get_state",

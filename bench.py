@@ -232,6 +232,11 @@ def run_ours(args):
         e2e_ms = float(tm.item())
     e2e_value = 3.0 * dof_per_stage * e2e_steps / (e2e_ms * 1e-3)
 
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload, {}).get("per_stage_total_bytes")
     peak, peak_src = peaks()
     A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
     stage_total_ms = (stage_ms + upd_ms) / max(n_stage, 1)          # both kernels of one stage, device time
@@ -245,7 +250,8 @@ def run_ours(args):
                    "l2": "state arrays (2.1 GB each at S-DMR) are far larger than the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (y-stripes)" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_note": "DRAM bytes of one stage (both kernels) from one ncu --set full capture, profiles/r1_traffic.json",
                      "kernel": "stage_kernel + update_kernel (one RK stage)", "algorithmic_bytes_per_dof_update": A,
                      "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
                      "stage_kernel_share": stage_ms / max(stage_ms + upd_ms, 1e-30)},

@@ -446,7 +446,13 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) dtloc = jl_min(dtloc, __shfl_xor_sync(0xffffffffu, dtloc, off));
+    {
+      const unsigned wmask = __activemask();   // the CTA's last warp may be partial
+      for (int off = 16; off > 0; off >>= 1) {
+        double other = __shfl_xor_sync(wmask, dtloc, off);
+        if ((wmask >> ((tid & 31) ^ off)) & 1u) dtloc = jl_min(dtloc, other);
+      }
+    }
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 

@@ -115,7 +115,7 @@ constexpr int fast_smem_doubles_per_elem() {
 }
 
 template <int N1D, int MODE, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, P2DE_FAST_MIN_BLOCKS)
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? 5 : P2DE_FAST_MIN_BLOCKS))
 stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
                   const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
@@ -317,7 +317,13 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) dtloc = jl_min(dtloc, __shfl_xor_sync(0xffffffffu, dtloc, off));
+    {
+      const unsigned wmask = __activemask();   // the CTA's last warp may be partial
+      for (int off = 16; off > 0; off >>= 1) {
+        double other = __shfl_xor_sync(wmask, dtloc, off);
+        if ((wmask >> ((tid & 31) ^ off)) & 1u) dtloc = jl_min(dtloc, other);
+      }
+    }
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 

@@ -77,7 +77,7 @@ enum {
   P2DE_FIELD_RHSH = 2,        /* [Nc,Nq,K]  (kept only when cfg.keep_diagnostics != 0)   */
   P2DE_FIELD_RHSL = 3,        /* [Nc,Nq,K]  (kept only when cfg.keep_diagnostics != 0)   */
   P2DE_FIELD_L = 4,           /* [K,Ns]     Zhang-Shu coefficient per element and stage  */
-  P2DE_FIELD_L_LOCAL = 5,     /* [Nq+N1D,Nd,K,Ns] subcell coefficients (1D: [Nq+1,1,K,Ns]) */
+  P2DE_FIELD_L_LOCAL = 5,     /* [Nq+N1D,Nd,K,Ns] subcell coefficients (1D: first Nq+1 used) */
   P2DE_FIELD_THETA = 6,       /* [K,Ns]                                                  */
   P2DE_FIELD_THETA_LOCAL = 7, /* [Nfp,K,Ns]                                              */
   P2DE_FIELD_RESW = 8         /* [Nc,Nq,K]  previous-step copy used by SSP33!            */

@@ -76,7 +76,7 @@ class Preallocation:
     @property
     def L_local(self):    # reference: L_local[idx, d, k, nstage] -> here [nstage, k, d, idx]
         sz = self._s.sizes
-        return self._field(T.FIELD_L_LOCAL, (sz.Ns, sz.K, sz.Nd, sz.Nq + sz.N1D))
+        return self._field(T.FIELD_L_LOCAL, (sz.Ns, sz.K, sz.Nd, sz.Nq + sz.N1D))   # 1D: entries > Nq+1 unused (= 1)
 
     @property
     def theta(self):

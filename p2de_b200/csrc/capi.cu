@@ -18,6 +18,7 @@
 #include "../../include/p2de_b200.h"
 #include "kernels2d.cuh"
 #include "stage_fast.cuh"
+#include "kernels1d.cuh"
 
 using namespace p2de;
 
@@ -81,6 +82,10 @@ const NcclApi *nccl_api(std::string *why) {
 struct p2de_handle {
   p2de_config cfg{};
   int N1D = 0, Nq = 0, Nfp = 0, Nc = 0, Nd = 0, Ns = 3;
+  int dim = 2;
+  long long nLloc = 0;    // L_local entries per element: (Nq + N1D) * Nd
+  Tables1D<2> u2{}; Tables1D<3> u3{}; Tables1D<4> u4{}; Tables1D<5> u5{};   // 1D path
+  double rxJ1 = 1.0;
   long long K = 0;
   int mode = 0;
   bool fast = false;   // default flux configuration -> FAST kernel variant (kernels2d.cuh)
@@ -505,15 +510,156 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
 }
 
 int ensure_rhsU(p2de_handle *h) {
-  if (!h->rhsU) return dev_alloc(h, &h->rhsU, (size_t)h->K * h->Nq * 4);
+  if (!h->rhsU) return dev_alloc(h, &h->rhsU, (size_t)h->K * h->Nq * h->Nc);
   return 0;
 }
 int ensure_Llocal(p2de_handle *h) {
   if (!h->Llocal) {
-    size_t n = (size_t)(h->Nq + h->N1D) * 2 * h->K * h->Ns;
+    size_t n = (size_t)h->nLloc * h->K * h->Ns;
     if (int rc = dev_alloc(h, &h->Llocal, n)) return rc;
     CU(h, cudaMemsetAsync(h->Llocal, 0, n * sizeof(double), h->stream));
   }
+  return 0;
+}
+
+template <int N1D> Tables1D<N1D> &tables1(p2de_handle *h);
+template <> Tables1D<2> &tables1<2>(p2de_handle *h) { return h->u2; }
+template <> Tables1D<3> &tables1<3>(p2de_handle *h) { return h->u3; }
+template <> Tables1D<4> &tables1<4>(p2de_handle *h) { return h->u4; }
+template <> Tables1D<5> &tables1<5>(p2de_handle *h) { return h->u5; }
+
+template <int N1D>
+int build_tables1d(p2de_handle *h, const p2de_operators *o) {
+  constexpr int Nq = N1D, Nh = N1D + 2;
+  Tables1D<N1D> &T = tables1<N1D>(h);
+  for (int i = 0; i < Nh; ++i) for (int j = 0; j < Nh; ++j) T.Srh[i][j] = o->Srsh_db[0][i + (size_t)j * Nh];
+  for (int i = 0; i < Nq; ++i) for (int j = 0; j < Nq; ++j) T.S0[i][j] = o->Srs0[0][i + (size_t)j * Nq];
+  bool gather = true;
+  for (int f = 0; f < 2; ++f) {
+    T.Br[f] = o->Brs[0][f];
+    T.fq2q[f] = (int)o->fq2q[f] - 1;
+    if (T.fq2q[f] < 0 || T.fq2q[f] >= Nq) return fail(h, P2DE_ERR_ARG, "fq2q[%d] out of range", f);
+    for (int j = 0; j < Nq; ++j) {
+      T.Vf[f][j] = o->Vf[f + (size_t)j * 2];
+      if (T.Vf[f][j] != (j == T.fq2q[f] ? 1.0 : 0.0)) gather = false;
+    }
+  }
+  T.vf_is_gather = gather;
+  for (int i = 0; i < Nq; ++i) {
+    T.wq[i] = o->wq[i];
+    for (int hh = 0; hh < Nh; ++hh) T.MinvVhT[i][hh] = o->MinvVhT[i + (size_t)hh * Nq];
+    for (int f = 0; f < 2; ++f) T.MinvVfT[i][f] = o->MinvVfT[i + (size_t)f * Nq];
+  }
+  return 0;
+}
+
+template <int N1D>
+int run_stage_1d_t(p2de_handle *h, const Args1D &A, const Upd1D &B, bool do_update) {
+  unsigned grid = (unsigned)((h->K + 63) / 64);
+  prof_begin(h, 0);
+  stage1d_kernel<N1D><<<grid, 64, 0, h->stream>>>(A, tables1<N1D>(h));
+  prof_end(h);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  if (do_update) {
+    prof_begin(h, 1);
+    update1d_kernel<N1D><<<grid, 64, 0, h->stream>>>(B, tables1<N1D>(h));
+    prof_end(h);
+    CU(h, cudaGetLastError());
+    h->launches++;
+  }
+  return 0;
+}
+
+int run_stage_1d(p2de_handle *h, const double *Uin, int nstage, double dt_host, bool limiter_dt_dev, bool update_dt_dev,
+                 double *Uout, const double *resW, double a, double b, bool want_outputs) {
+  Args1D A{};
+  A.Uq = Uin; A.rhsL = h->rhsL; A.dF = h->dF; A.lpre = h->lpre; A.rhsU = h->rhsU;
+  A.Lout = h->Lz + h->K * (nstage - 1); A.rhsH_diag = h->rhsH_diag; A.rhsL_diag = h->rhsL_diag;
+  A.dt_bits = h->dt_bits; A.dt_dev = reinterpret_cast<const double *>(h->dt_bits);
+  A.dt_host = dt_host; A.use_dt_dev = limiter_dt_dev; A.nstage = nstage; A.K = h->K;
+  A.mapP32 = h->mapP32; A.bcflag = h->bcflag; A.Ival = h->Ival;
+  A.gamma = h->cfg.gamma; A.ZEROTOL = h->cfg.ZEROTOL; A.POSTOL = h->cfg.POSTOL; A.zeta = h->cfg.zeta; A.CFL = h->cfg.CFL;
+  A.Jq = h->Jq; A.rxJ = h->rxJ1; A.blend = 1.0; A.mode = h->mode;
+  A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
+  A.roundtrip = h->cfg.lgl_projection_roundtrip;
+  Upd1D B{};
+  B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
+  B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)h->nLloc * h->K * (nstage - 1) : nullptr;
+  B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
+  B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
+  B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
+  B.mode = h->mode; B.K = h->K; B.Jq = h->Jq;
+  const bool upd = h->mode == MODE_SUBCELL || Uout;
+  switch (h->N1D) {
+    case 2: return run_stage_1d_t<2>(h, A, B, upd);
+    case 3: return run_stage_1d_t<3>(h, A, B, upd);
+    case 4: return run_stage_1d_t<4>(h, A, B, upd);
+    case 5: return run_stage_1d_t<5>(h, A, B, upd);
+  }
+  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+
+// 1D: device state, gather tables (mapP is always explicit here: K is small), BC flags
+int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *geom, const p2de_bcdata *bc) {
+  const int N1D = h->N1D, Nq = h->Nq;
+  const long long K = h->K;
+  if (h->cfg.proj_limiter != P2DE_PROJLIM_NONE) return fail(h, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation (SURVEY.md 8f-1)");
+  if (geom->uniform) { h->Jq = geom->J_const; h->Jcons = geom->J_const; h->rxJ1 = geom->GJ_const[0]; }
+  else {
+    if (!geom->Jq || !geom->GJh[0]) return fail(h, P2DE_ERR_ARG, "geometry arrays missing");
+    h->Jq = geom->Jq[0]; h->Jcons = geom->J ? geom->J[0] : geom->Jq[0]; h->rxJ1 = geom->GJh[0][0];
+    for (size_t i = 0; i < (size_t)Nq * K; ++i) if (geom->Jq[i] != h->Jq) return fail(h, P2DE_ERR_UNSUPPORTED, "non-uniform Jq");
+    for (size_t i = 0; i < (size_t)(Nq + 2) * K; ++i) if (geom->GJh[0][i] != h->rxJ1) return fail(h, P2DE_ERR_UNSUPPORTED, "non-uniform rxJ");
+  }
+  int rc = 0;
+  switch (N1D) {
+    case 2: rc = build_tables1d<2>(h, ops); break;
+    case 3: rc = build_tables1d<3>(h, ops); break;
+    case 4: rc = build_tables1d<4>(h, ops); break;
+    case 5: rc = build_tables1d<5>(h, ops); break;
+  }
+  if (rc) return rc;
+  h->wq.assign(ops->wq, ops->wq + Nq);
+  if (2 * K >= (1ll << 31)) return fail(h, P2DE_ERR_UNSUPPORTED, "K too large for the 1D path");
+  std::vector<int> m32((size_t)2 * K), fl((size_t)2 * K, 0);
+  for (long long k = 0; k < K; ++k)
+    for (int f = 0; f < 2; ++f) {
+      long long v;
+      if (bc->mapP) v = bc->mapP[k * 2 + f] - 1;
+      else {
+        long long kn = f == 0 ? k - 1 : k + 1;
+        bool out = kn < 0 || kn >= K;
+        if (out && bc->periodic_x) { kn = (kn + K) % K; out = false; }
+        v = out ? k * 2 + f : kn * 2 + (1 - f);
+      }
+      if (v < 0 || v >= 2 * K) return fail(h, P2DE_ERR_ARG, "mapP out of range");
+      m32[k * 2 + f] = (int)v;
+    }
+  for (long long i = 0; i < bc->nI; ++i) { long long idx = bc->mapI[i] - 1; if (idx < 0 || idx >= 2 * K) return fail(h, P2DE_ERR_ARG, "mapI out of range"); fl[idx] = (int)(i + 1); }
+  for (long long i = 0; i < bc->nO; ++i) { long long idx = bc->mapO[i] - 1; if (idx < 0 || idx >= 2 * K) return fail(h, P2DE_ERR_ARG, "mapO out of range"); fl[idx] = -1; }
+  if ((rc = dev_alloc(h, &h->mapP32, m32.size())) || (rc = dev_alloc(h, &h->bcflag, fl.size()))) return rc;
+  CU(h, cudaMemcpy(h->mapP32, m32.data(), m32.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CU(h, cudaMemcpy(h->bcflag, fl.data(), fl.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (bc->nI > 0) {
+    if ((rc = dev_alloc(h, &h->Ival, (size_t)bc->nI * 3))) return rc;
+    CU(h, cudaMemcpy(h->Ival, bc->Ival, (size_t)bc->nI * 3 * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  h->topo.K = K; h->topo.Kx = (int)K; h->topo.Ky = 1;
+  const size_t nU = (size_t)K * Nq * 3;
+  if ((rc = dev_alloc(h, &h->U[0], nU)) || (rc = dev_alloc(h, &h->U[1], nU)) || (rc = dev_alloc(h, &h->rhsU, nU)) ||
+      (rc = dev_alloc(h, &h->Lz, (size_t)K * h->Ns)) || (rc = dev_alloc(h, &h->dt_bits, 1)) ||
+      (rc = dev_alloc(h, &h->partial, 1024 + (size_t)Nq)))
+    return rc;
+  CU(h, cudaMemset(h->Lz, 0, (size_t)K * h->Ns * sizeof(double)));
+  CU(h, cudaMemcpy(h->partial + 1024, h->wq.data(), Nq * sizeof(double), cudaMemcpyHostToDevice));
+  if (h->mode == MODE_SUBCELL)
+    if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)K * (Nq + 1) * 3)) || (rc = dev_alloc(h, &h->lpre, (size_t)K * (Nq + 1)))) return rc;
+  if (h->cfg.keep_diagnostics) {
+    if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return rc;
+    CU(h, cudaMemset(h->rhsH_diag, 0, nU * sizeof(double))); CU(h, cudaMemset(h->rhsL_diag, 0, nU * sizeof(double)));
+  }
+  h->fast = false;
   return 0;
 }
 
@@ -527,8 +673,9 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
     CU(h, cudaGetLastError());
     h->launches++;
   }
+  if (h->dim == 1) return run_stage_1d(h, Uin, nstage, dt_host, limiter_dt_dev, update_dt_dev, Uout, resW, a, b, want_outputs);
   if (h->rhsH_diag && h->mode == MODE_SUBCELL)
-    CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * 4 * sizeof(double), h->stream));
+    CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * h->Nc * sizeof(double), h->stream));
   // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
   if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
@@ -543,7 +690,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   UpdateArgs B{};
   B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
   B.rpre = h->rpre; B.dFend = h->dFend;
-  B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)(h->Nq + h->N1D) * 2 * h->K * (nstage - 1) : nullptr;
+  B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)h->nLloc * h->K * (nstage - 1) : nullptr;
   B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
   B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
@@ -563,13 +710,15 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if (!cfg || !ops || !geom || !bc || !out) return fail(nullptr, P2DE_ERR_ARG, "null argument");
   *out = nullptr;
   if (cfg->abi_version != P2DE_ABI_VERSION) return fail(nullptr, P2DE_ERR_ARG, "abi_version %d != %d", cfg->abi_version, P2DE_ABI_VERSION);
-  if (cfg->dim != 2) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "dim=%d: only the 2D path has a GPU kernel in this build", cfg->dim);
+  if (cfg->dim != 1 && cfg->dim != 2) return fail(nullptr, P2DE_ERR_ARG, "dim=%d", cfg->dim);
   if (cfg->N < 1 || cfg->N > 4) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "N=%d outside 1..4", cfg->N);
   const int N1D = cfg->N + 1;
-  if (cfg->Nq != N1D * N1D || cfg->Nfp != 4 * N1D || cfg->Nh != cfg->Nq + cfg->Nfp || cfg->Np != cfg->Nq)
-    return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d quad", cfg->N);
+  const bool d1 = cfg->dim == 1;
+  if (d1 ? (cfg->Nq != N1D || cfg->Nfp != 2 || cfg->Nh != N1D + 2 || cfg->Np != N1D)
+         : (cfg->Nq != N1D * N1D || cfg->Nfp != 4 * N1D || cfg->Nh != cfg->Nq + cfg->Nfp || cfg->Np != cfg->Nq))
+    return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d %s", cfg->N, d1 ? "line" : "quad");
   if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
-  if (cfg->basis != P2DE_BASIS_LOBATTO) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "GaussCollocation has no GPU kernel in this build (SURVEY.md 8f-1)");
+  if (!d1 && cfg->basis != P2DE_BASIS_LOBATTO) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "2D GaussCollocation has no GPU kernel in this build (SURVEY.md 8f-1)");
   if (cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation has no GPU kernel in this build (SURVEY.md 8f-1)");
   if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture has no GPU kernel in this build (SURVEY.md 8f-2)");
   int mode;
@@ -599,10 +748,18 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
                    !cfg->lgl_projection_roundtrip;
     h->fast = mode == MODE_LOW ? low_ok : mode == MODE_HIGH ? high_ok : (low_ok && high_ok);
   }
-  h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = 4; h->Nd = 2; h->K = cfg->K; h->mode = mode;
+  h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = d1 ? 3 : 4; h->Nd = d1 ? 1 : 2; h->K = cfg->K; h->mode = mode;
+  h->dim = cfg->dim;
+  h->nLloc = d1 ? 2 * N1D : 2 * N1D * (N1D + 1);   // State.jl:21: zeros(Nq + N1D, Nd, K, Ns); 1D uses the first Nq+1
   auto bail = [&](int rc) { g_create_error = h->err; p2de_destroy(h); return rc; };
   if (cfg->device >= 0) { if (cudaSetDevice(cfg->device) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device)); }
   cudaGetDevice(&h->device);
+  if (d1) {
+    int rc1 = create_1d(h, ops, geom, bc);
+    if (rc1) return bail(rc1);
+    *out = h;
+    return P2DE_OK;
+  }
 
   // geometry: uniform meshes only (the reference builds nothing else, init.jl:137)
   double GJ[4];
@@ -678,7 +835,7 @@ int32_t p2de_synchronize(p2de_handle *h) {
 
 int32_t p2de_set_state_async(p2de_handle *h, const double *Uq_host) {
   if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
-  CU(h, cudaMemcpyAsync(h->U[h->cur], Uq_host, (size_t)h->K * h->Nq * 4 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->U[h->cur], Uq_host, (size_t)h->K * h->Nq * h->Nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->have_state = true;
   return P2DE_OK;
 }
@@ -689,7 +846,7 @@ int32_t p2de_set_state(p2de_handle *h, const double *Uq_host) {
 int32_t p2de_get_state_async(p2de_handle *h, double *Uq_host) {
   if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
   if (!h->have_state) return fail(h, P2DE_ERR_STATE, "get_state before set_state");
-  CU(h, cudaMemcpyAsync(Uq_host, h->U[h->cur], (size_t)h->K * h->Nq * 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(Uq_host, h->U[h->cur], (size_t)h->K * h->Nq * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return P2DE_OK;
 }
 int32_t p2de_get_state(p2de_handle *h, double *Uq_host) {
@@ -765,7 +922,7 @@ int32_t p2de_ssp33_run(p2de_handle *h, double *t_inout, int64_t max_steps, int64
 
 int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
   if (!h || !dst) return fail(h, P2DE_ERR_ARG, "null argument");
-  const int64_t nU = h->K * h->Nq * 4;
+  const int64_t nU = h->K * h->Nq * h->Nc;
   const double *src = nullptr;
   int64_t cnt = 0;
   switch (field) {
@@ -775,7 +932,7 @@ int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
     case P2DE_FIELD_RHSH: src = h->rhsH_diag; cnt = nU; break;
     case P2DE_FIELD_RHSL: src = h->rhsL_diag; cnt = nU; break;
     case P2DE_FIELD_L: src = h->Lz; cnt = h->K * h->Ns; break;
-    case P2DE_FIELD_L_LOCAL: src = h->Llocal; cnt = (int64_t)(h->Nq + h->N1D) * 2 * h->K * h->Ns; break;
+    case P2DE_FIELD_L_LOCAL: src = h->Llocal; cnt = (int64_t)h->nLloc * h->K * h->Ns; break;
     case P2DE_FIELD_THETA: cnt = h->K * h->Ns; break;          // NoEntropyProjectionLimiter: never written (zeros)
     case P2DE_FIELD_THETA_LOCAL: cnt = (int64_t)h->Nfp * h->K * h->Ns; break;
     default: return fail(h, P2DE_ERR_ARG, "unknown field %d", field);
@@ -792,7 +949,8 @@ int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out) {
   if (!h || !out) return P2DE_ERR_ARG;
   if (what < 0 || what > 2) return fail(h, P2DE_ERR_ARG, "unknown reduction %d", what);
   const int blocks = 1024;
-  reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->partial + 1024, h->Nq, h->K * h->Nq, h->Jcons, what, h->partial);
+  if (h->dim == 1) reduce1d_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->partial + 1024, h->Nq, h->K * h->Nq, h->Jcons, what, h->partial);
+  else reduce_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->partial + 1024, h->Nq, h->K * h->Nq, h->Jcons, what, h->partial);
   CU(h, cudaGetLastError());
   h->launches++;
   std::vector<double> part(blocks);
@@ -844,7 +1002,7 @@ int32_t p2de_comm_unique_id(uint8_t id_out[128]) {
 int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8_t unique_id[128]) {
   if (!h || !unique_id) return fail(h, P2DE_ERR_ARG, "null argument");
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, P2DE_ERR_ARG, "rank %d of %d", rank, nranks);
-  if (h->topo.mapP32) return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU needs the structured mesh path (y-stripes)");
+  if (h->topo.mapP32 || h->dim == 1) return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU needs the structured 2D mesh path (y-stripes)");
   if (h->comm) return fail(h, P2DE_ERR_STATE, "communicator already initialised");
   h->rank = rank; h->nranks = nranks;
   if (nranks == 1) return P2DE_OK;

@@ -114,6 +114,49 @@ def dmr(N=3, K=(64, 16), **kw):
     return make_param(N, K, (0.0, 0.0), (4.0, 1.0), **kw), dmr_ic, dmr_bc
 
 
+# ---- 1D shock tubes (BASELINE.json configs 1-2; the reference ships no Sod script, SURVEY.md §0.1:
+#      standard data, inflow left via mapI=[1], outflow right via mapO=[2K] as in
+#      examples/convergence/leblanc-convergence.jl:45-52) ------------------------------------
+def sod(N=3, K=200, **kw):
+    kw.setdefault("T", 0.2); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3)
+
+    def ic(param, x):
+        left = x < 0.5
+        return primitive_to_conservative(param.equation, (np.where(left, 1.0, 0.125), 0 * x, np.where(left, 1.0, 0.1)))
+
+    def bc(param, md):
+        Ival = np.array([primitive_to_conservative(param.equation, (1.0, 0.0, 1.0))])
+        return BCData(md.mapP, [1], [2 * md.K], Ival)
+    return make_param(N, K, 0.0, 1.0, dim=1, **kw), ic, bc
+
+
+def shu_osher(N=3, K=64, **kw):
+    """examples/1D/shu-osher.jl:9-30: Mach-3 shock into a density sine wave on [-5, 5]."""
+    kw.setdefault("T", 1.8); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3)
+    post = (3.857143, 2.629369, 10.3333)
+
+    def ic(param, x):
+        left = x < -4.0
+        return primitive_to_conservative(param.equation, (np.where(left, post[0], 1 + 0.2 * np.sin(5 * x)),
+                                                         np.where(left, post[1], 0.0), np.where(left, post[2], 1.0)))
+
+    def bc(param, md):
+        Ival = np.array([primitive_to_conservative(param.equation, post)])
+        return BCData(md.mapP, [1], [2 * md.K], Ival)
+    return make_param(N, K, -5.0, 5.0, dim=1, **kw), ic, bc
+
+
+def density_wave_1d(N=3, K=16, **kw):
+    kw.setdefault("T", 1.0); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-2)
+
+    def ic(param, x):
+        return primitive_to_conservative(param.equation, (1 + 0.5 * np.sin(2 * np.pi * x), 0.7 + 0 * x, 1.0 + 0 * x))
+
+    def bc(param, md):
+        return BCData(make_periodic(md, (True, False)).mapP, [], [], [])
+    return make_param(N, K, 0.0, 1.0, dim=1, **kw), ic, bc
+
+
 def setup(problem):
     """(param, ic, bc_callback) -> (param, rd, md, discrete_data, bcdata, U0)."""
     param, ic, bcf = problem

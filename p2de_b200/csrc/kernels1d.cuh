@@ -11,7 +11,8 @@
 //   update1d_kernel = symmetrisation (subcell.jl:405-416, hard-coded periodic neighbours k-1/k+1
 //                     like the reference), limited reassembly (subcell.jl:826-892), SSP combine.
 // Reference-order arithmetic (1D formulas of compressible_Navier_Stokes.jl:1-218).
-// Deviations from HEAD D1/D2 as in oracle/p2de_oracle.cpp (1D Bx argument order, shadowed dim/bound).
+// HEAD is broken in 1D (Bx argument order rhs_utils.jl:18, shadowed dim/bound subcell.jl:230-231); the
+// evident intent is implemented.
 #pragma once
 #include "kernels2d.cuh"
 

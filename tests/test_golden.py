@@ -9,7 +9,8 @@ import pytest
 import problems as P
 from oracle.make_golden import CASES, run_case
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = [p for p in sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+        if os.path.basename(p)[:-4] in CASES]      # (weno5_shuosher_sub.npz is reference data, see test_oracle_1d.py)
 
 
 def rel(a, b):

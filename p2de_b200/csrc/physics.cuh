@@ -22,8 +22,9 @@ namespace p2de {
 struct Cons2 { double rho, m1, m2, E; };
 
 // Julia's min/max propagate NaN (oracle deviation D3): fmin/fmax do not, so spell it out.
-P2DE_DEV double jl_min(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
-P2DE_DEV double jl_max(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
+// (a < b || a is NaN) ? a : b   -> NaN if either is NaN, else the smaller one
+P2DE_DEV double jl_min(double a, double b) { return (a < b || a != a) ? a : b; }
+P2DE_DEV double jl_max(double a, double b) { return (a > b || a != a) ? a : b; }
 
 // pfun, compressible_Navier_Stokes.jl:24-28
 P2DE_DEV double pfun2(double gm1, const Cons2 &U) {
@@ -158,14 +159,20 @@ __device__ __noinline__ double rhoe_quadratic_roots(double ZEROTOL, double a, do
 // The quadratic q(l) = a l^2 + b l + c has no root in (0, 1] when q(0) > 0, q(1) > 0 and its
 // vertex is not an interior minimum; the reference then returns either 1 or a root > 1, which
 // the trailing min(., 1.0) turns into 1, so the sqrt and the two divisions are skipped.
-P2DE_DEV double limiting_param_pos(double ZEROTOL, const Cons2 &U, double c, const double Pv[4], double Lrho, double Lrhoe) {
+__device__ __noinline__ double limiting_param_pos_slow(double ZEROTOL, double rho, double P0, double Lrho, double a, double b, double c) {
   double l = 1.0;
-  if (U.rho + Pv[0] < Lrho) l = jl_max((Lrho - U.rho) / Pv[0], 0.0);
-  double a, b;
-  quad_coeff_ab(U, Pv, Lrhoe, a, b);
+  if (rho + P0 < Lrho) l = jl_max((Lrho - rho) / P0, 0.0);
   bool no_root = (c > 0.0) && (a + b + c > 0.0) && !(a > 0.0 && b < 0.0 && -b < 2.0 * a);
   if (!no_root) l = jl_min(l, rhoe_quadratic_roots(ZEROTOL, a, b, c));
   return jl_min(l, 1.0);
+}
+P2DE_DEV double limiting_param_pos(double ZEROTOL, const Cons2 &U, double c, const double Pv[4], double Lrho, double Lrhoe) {
+  double a, b;
+  quad_coeff_ab(U, Pv, Lrhoe, a, b);
+  // common case: density bound inactive and no root in (0, 1]  ->  1 (no min, no division)
+  bool easy = !(U.rho + Pv[0] < Lrho) && (c > 0.0) && (a + b + c > 0.0) && !(a > 0.0 && b < 0.0 && -b < 2.0 * a);
+  if (easy) return 1.0;
+  return limiting_param_pos_slow(ZEROTOL, U.rho, Pv[0], Lrho, a, b, c);
 }
 
 }  // namespace p2de

@@ -75,9 +75,7 @@ P2DE_DEV void div3_fast(double n0, double a0, double n1, double a1, double n2, d
   x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
   e0 = fma(-a0, x0, 1.0); e1 = fma(-a1, x1, 1.0); e2 = fma(-a2, x2, 1.0);
   x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
-  q0 = n0 * x0; q1 = n1 * x1; q2 = n2 * x2;
-  double r0 = fma(-a0, q0, n0), r1 = fma(-a1, q1, n1), r2 = fma(-a2, q2, n2);
-  q0 = fma(r0, x0, q0); q1 = fma(r1, x1, q1); q2 = fma(r2, x2, q2);
+  q0 = n0 * x0; q1 = n1 * x1; q2 = n2 * x2;   // <= ~1.5 ulp each; no residual correction needed at 1e-12
 }
 
 // fS (:220-249) along the line's own axis, three reciprocals (see fS_fast in physics.cuh)
@@ -360,8 +358,10 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       Cons2 uL;
       uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
       uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
-      const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoe2(uL);
-      const double c0 = quad_coeff_c(uL, Lrhoe);
+      // rhoe_ufun (:75-78) with a Newton reciprocal; c = E rho - |m|^2/2 - rho Lrhoe = (1 - zeta) rho rhoe
+      const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
+      const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
+      const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
       if (d == 0 && A.rhsL_diag) {
         const int node = a + line * N1D;
         double r[4] = {r0, r1, r2, r3};

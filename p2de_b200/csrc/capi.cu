@@ -109,6 +109,9 @@ struct p2de_handle {
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
   double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
+  double *VDM_inv = nullptr;                  // [Np, Nq] (Hennemann indicator)
+  unsigned long long *smin_bits = nullptr;    // global min of s_modified at t0 (min-entropy bounds)
+  int entropy_bound = 0;                      // 0 none, 1 min entropy, 2 relaxed min entropy
   double *Lz = nullptr;       // [K, Ns]
   double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
@@ -388,6 +391,15 @@ int setup_topology(p2de_handle *h, const p2de_bcdata *bc) {
 
 __global__ void set_dt_kernel(unsigned long long *dt_bits, double v) { *dt_bits = (unsigned long long)__double_as_longlong(v); }
 
+// minimum(s_modified) over all nodes (initialize_s_modified!, subcell.jl:19-35); s_modified > 0
+__global__ void smin_kernel(const double *U, long long n_nodes, double gamma, unsigned long long *out_bits) {
+  double m = INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_nodes; i += (long long)gridDim.x * blockDim.x)
+    m = fmin(m, s_modified(gamma, load_cons(U + i * 4)));
+  for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m < INFINITY) atomicMin(out_bits, (unsigned long long)__double_as_longlong(m));
+}
+
 __global__ void reduce_kernel(const double *U, const double *wq, int Nq, long long n_nodes, double J, int what, double *partial) {
   __shared__ double sh[256];
   double acc = what == P2DE_REDUCE_CONSERVATION ? 0.0 : INFINITY;
@@ -503,6 +515,10 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.dt_host = dt_host; A.use_dt_dev = use_dt_dev; A.nstage = nstage;
   A.gamma = h->cfg.gamma; A.ZEROTOL = h->cfg.ZEROTOL; A.POSTOL = h->cfg.POSTOL; A.zeta = h->cfg.zeta;
   A.CFL = h->cfg.CFL; A.Jq = h->Jq; A.blend = 1.0;
+  A.hennemann = h->cfg.shockcapture == P2DE_SHOCKCAPTURE_HENNEMANN;
+  A.entropy_bound = h->entropy_bound; A.N = h->cfg.N;
+  A.hen_a = h->cfg.hennemann_a; A.hen_c = h->cfg.hennemann_c;
+  A.VDM_inv = h->VDM_inv; A.smin_dev = reinterpret_cast<const double *>(h->smin_bits);
   A.roundtrip = h->cfg.lgl_projection_roundtrip;
   A.half_inv_gm1 = 1.0 / (2.0 * (h->cfg.gamma - 1.0));
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
@@ -676,6 +692,13 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   if (h->dim == 1) return run_stage_1d(h, Uin, nstage, dt_host, limiter_dt_dev, update_dt_dev, Uout, resW, a, b, want_outputs);
   if (h->rhsH_diag && h->mode == MODE_SUBCELL)
     CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * h->Nc * sizeof(double), h->stream));
+  if (h->entropy_bound && nstage == 1 && t == h->cfg.t0) {   // subcell.jl:32-34: global minimum of the initial condition
+    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->smin_bits, INFINITY);
+    smin_kernel<<<1024, 256, 0, h->stream>>>(Uin, h->K * h->Nq, h->cfg.gamma, h->smin_bits);
+    CU(h, cudaGetLastError());
+    h->launches += 2;
+    if (h->comm) NC(h, nccl_api(nullptr)->AllReduce(h->smin_bits, h->smin_bits, 1, ncclDouble, ncclMin, h->comm, h->stream));
+  }
   // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
   if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
@@ -720,14 +743,17 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
   if (!d1 && cfg->basis != P2DE_BASIS_LOBATTO) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "2D GaussCollocation has no GPU kernel in this build (SURVEY.md 8f-1)");
   if (cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation has no GPU kernel in this build (SURVEY.md 8f-1)");
-  if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture has no GPU kernel in this build (SURVEY.md 8f-2)");
+  if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE && (d1 || !ops->VDM_inv))
+    return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture: 2D only and needs ops.VDM_inv");
   int mode;
   if (cfg->rhs_type == P2DE_RHS_LOW_ORDER_POSITIVITY) mode = MODE_LOW;
   else if (cfg->rhs_type == P2DE_RHS_FLUX_DIFF) mode = MODE_HIGH;
   else if (cfg->rhs_type == P2DE_RHS_LIMITED_DG) {
     if (cfg->limiter == P2DE_LIMITER_ZHANGSHU) mode = MODE_ZHANGSHU;
     else if (cfg->limiter == P2DE_LIMITER_SUBCELL) {
-      if (cfg->bound != P2DE_BOUND_POSITIVITY) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "only PositivityBound has a GPU kernel in this build (SURVEY.md 8f-2)");
+      const bool ent = cfg->bound == P2DE_BOUND_POS_MIN_ENTROPY || cfg->bound == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY;
+      if (cfg->bound != P2DE_BOUND_POSITIVITY && !(ent && !d1 && ops->VDM_inv))
+        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "bound %d: PositivityBound (1D/2D) and the two min-entropy bounds (2D) have GPU kernels; cell-entropy / TVD bounds do not (SURVEY.md 8f-2)", cfg->bound);
       mode = MODE_SUBCELL;
     } else return fail(nullptr, P2DE_ERR_UNSUPPORTED, "LimitedDG needs ZhangShuLimiter or SubcellLimiter");
   } else return fail(nullptr, P2DE_ERR_ARG, "rhs_type %d", cfg->rhs_type);
@@ -748,6 +774,8 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
                    !cfg->lgl_projection_roundtrip;
     h->fast = mode == MODE_LOW ? low_ok : mode == MODE_HIGH ? high_ok : (low_ok && high_ok);
   }
+  if (mode == MODE_SUBCELL) h->entropy_bound = cfg->bound == P2DE_BOUND_POS_MIN_ENTROPY ? 1 : (cfg->bound == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY ? 2 : 0);
+  if (h->entropy_bound || cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) h->fast = false;   // generic kernel has these features
   h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = d1 ? 3 : 4; h->Nd = d1 ? 1 : 2; h->K = cfg->K; h->mode = mode;
   h->dim = cfg->dim;
   h->nLloc = d1 ? 2 * N1D : 2 * N1D * (N1D + 1);   // State.jl:21: zeros(Nq + N1D, Nd, K, Ns); 1D uses the first Nq+1
@@ -805,7 +833,12 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return bail(rc);
     cudaMemset(h->rhsH_diag, 0, nU * sizeof(double)); cudaMemset(h->rhsL_diag, 0, nU * sizeof(double));
   }
-  if ((rc = dev_alloc(h, &h->dt_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->dt_bits, 1)) || (rc = dev_alloc(h, &h->smin_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
+  cudaMemset(h->smin_bits, 0, sizeof(unsigned long long));   // s_modified_min starts at 0.0 (State.jl:180)
+  if (ops->VDM_inv) {
+    if ((rc = dev_alloc(h, &h->VDM_inv, (size_t)h->Nq * h->Nq))) return bail(rc);
+    if (cudaMemcpy(h->VDM_inv, ops->VDM_inv, (size_t)h->Nq * h->Nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy VDM_inv"));
+  }
   if (cudaMemcpy(h->partial + 1024, h->wq.data(), h->Nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy wq"));
   *out = h;
   return P2DE_OK;

@@ -68,6 +68,13 @@ struct StageArgs {
   int vol_flux, surf_low, surf_high; // P2DE_VOLFLUX_*, P2DE_SURFFLUX_*
   int roundtrip;                     // evaluate u(v(U)) at LGL face nodes instead of using U
   double half_inv_gm1;               // 1 / (2 (gamma - 1))
+  // generic kernel only: shock capturing and minimum-entropy bounds
+  int hennemann;                     // HennemannShockCapture: blending factor from the modal indicator
+  int entropy_bound;                 // 0 none, 1 PositivityAndMinEntropyBound, 2 PositivityAndRelaxedMinEntropyBound
+  int N;                             // polynomial degree
+  double hen_a, hen_c;
+  const double *VDM_inv;             // [Np, Nq] column-major (device)
+  const double *smin_dev;            // global minimum of s_modified at t0 (device scalar)
 };
 
 struct UpdateArgs {
@@ -151,7 +158,26 @@ P2DE_DEV double find_alpha(double POSTOL, const Cons2 &ui, const Cons2 &ut) {
 template <int N1D, int MODE>
 constexpr int stage_smem_doubles_per_elem() {
   constexpr int Nq = N1D * N1D;
-  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D;
+  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D + 4 * Nq + 3 * 2 * N1D;
+}
+
+// s_modified_ufun, compressible_Navier_Stokes.jl:80-85
+P2DE_DEV double s_modified(double gamma, const Cons2 &U) { return rhoe2(U) * pow(U.rho, -gamma); }
+
+// bisection, src/math/nonlinear_solvers.jl:3-20, on f(l) = s_modified(U + l P) >= Lphi - POSTOL
+// (limiting_param_bound_phi, limiter_utils.jl:42-50)
+__device__ __noinline__ double limiting_param_phi(double gamma, double POSTOL, const Cons2 &U, const double Pv[4], double Lphi, double lpos) {
+  auto f = [&](double l) {
+    Cons2 w; w.rho = U.rho + l * Pv[0]; w.m1 = U.m1 + l * Pv[1]; w.m2 = U.m2 + l * Pv[2]; w.E = U.E + l * Pv[3];
+    return s_modified(gamma, w) >= Lphi - POSTOL;
+  };
+  if (f(lpos)) return lpos;
+  double x_valid = 0.0, x_invalid = lpos;
+  for (int iter = 0; iter <= 20; ++iter) {
+    double x_new = 0.5 * (x_valid + x_invalid);
+    if (f(x_new)) x_valid = x_new; else x_invalid = x_new;
+  }
+  return x_valid;
 }
 
 // FAST = default flux configuration (Chandrashekar volume flux, Lax-Friedrichs surface fluxes on
@@ -173,6 +199,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   double *partsH = partsL + 8 * EPB * Nq;         // [EPB*Nq][2][4]   (not MODE_SUBCELL)
   double *lamp = partsH + ((MODE == MODE_SUBCELL) ? 0 : 8 * EPB * Nq);  // [EPB*Nq][6]
   double *lmin = lamp + 6 * EPB * Nq;             // [EPB][N1D]
+  double *smod = lmin + EPB * N1D;                // [S] s_modified at the nodes
+  double *lbnd = smod + S;                        // [S] indicator rho*p, later the lower bound on s_modified
+  double *ghst = lbnd + S;                        // [2][S] s_modified across the x / y face of boundary nodes
+  double *ered = ghst + 2 * S;                    // [EPB][TPE][3] modal energy partial sums
 
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
@@ -205,9 +235,43 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       beta = U.rho / (2 * p);
       o[6 * S] = p; o[7 * S] = beta;
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
+      if (A.entropy_bound) smod[nbase + node] = s_modified(gamma, U);
+      if (A.hennemann || A.entropy_bound == 2) lbnd[nbase + node] = U.rho * p;   // indicator, shock_capture.jl:82-94
     }
   }
   __syncthreads();
+
+  // ---- modal smoothness indicator (shock_capture.jl:47-80), blending factor (:111-132) and
+  //      smoothness factor of the relaxed bound (subcell.jl:932-956); per element, every thread
+  double blend = A.blend, epsk = A.entropy_bound == 1 ? 1.0 : 0.0;
+  if (A.hennemann || A.entropy_bound == 2) {
+    double eN = 0.0, eNm1 = 0.0, etot = 0.0;
+    if (active)
+      for (int m = ln; m < Nq; m += TPE) {
+        double coef = 0.0;
+        for (int j = 0; j < Nq; ++j) coef += A.VDM_inv[m + j * Nq] * lbnd[nbase + j];
+        double e = coef * coef;
+        int mi = m % N1D, mj = m / N1D;
+        if (mi == N1D - 1 || mj == N1D - 1) eN += e;
+        if (mi == N1D - 2 || mj == N1D - 2) eNm1 += e;
+        etot += e;
+      }
+    ered[(el * TPE + ln) * 3 + 0] = eN; ered[(el * TPE + ln) * 3 + 1] = eNm1; ered[(el * TPE + ln) * 3 + 2] = etot;
+    __syncthreads();
+    eN = eNm1 = etot = 0.0;
+    for (int t2 = 0; t2 < TPE; ++t2) { eN += ered[(el * TPE + t2) * 3]; eNm1 += ered[(el * TPE + t2) * 3 + 1]; etot += ered[(el * TPE + t2) * 3 + 2]; }
+    const double sigma = jl_max(eN / etot, eNm1 / etot);
+    if (A.hennemann) {
+      const double TN = A.hen_a * pow(10.0, -A.hen_c * pow((double)(A.N + 1), 0.25));
+      const double s_factor = log((1 - 0.0001) / 0.0001);
+      const double al = 1.0 / (1.0 + exp(-s_factor / TN * (sigma - TN)));
+      blend = jl_max(jl_min(1.0 - al, 1.0), 0.5);
+    }
+    if (A.entropy_bound == 2) {
+      const double kappa = 1.0, s0 = log10(pow((double)A.N, -4.0)), sk = log10(sigma);
+      epsk = sk < s0 - kappa ? 0.0 : (sk > s0 + kappa ? 1.0 : 0.5 - 0.5 * sin(3.141592653589793 * (sk - s0) / (2 * kappa)));
+    }
+  }
 
   // ---- line phase
   Cons2 U[N1D];
@@ -235,6 +299,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     for (int e = 0; e < 2; ++e) {
       nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
       Unb[e] = load_cons(A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4);
+    }
+    if (A.entropy_bound) {   // low_order_stencil across the element boundary (limiter_utils.jl:184-231)
+      ghst[d * S + nbase + (d == 0 ? 0 + line * N1D : line)] = s_modified(gamma, Unb[0]);
+      ghst[d * S + nbase + (d == 0 ? (N1D - 1) + line * N1D : line + (N1D - 1) * N1D)] = s_modified(gamma, Unb[1]);
     }
     double fl[N1D][4];                      // nodal flux along d
 #pragma unroll
@@ -431,6 +499,22 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   }
   __syncthreads();
 
+  // ---- lower bound on s_modified: stencil minimum relaxed towards the global minimum
+  //      (initialize_lower_bound!, subcell.jl:55-75)
+  if (A.entropy_bound) {
+    if (active)
+      for (int node = ln; node < Nq; node += TPE) {
+        const int i = node % N1D, j = node / N1D;
+        double lb = smod[nbase + node];
+        lb = jl_min(lb, i > 0 ? smod[nbase + node - 1] : ghst[0 * S + nbase + node]);
+        lb = jl_min(lb, i < N1D - 1 ? smod[nbase + node + 1] : ghst[0 * S + nbase + node]);
+        lb = jl_min(lb, j > 0 ? smod[nbase + node - N1D] : ghst[1 * S + nbase + node]);
+        lb = jl_min(lb, j < N1D - 1 ? smod[nbase + node + N1D] : ghst[1 * S + nbase + node]);
+        lbnd[nbase + node] = epsk * lb + (1 - epsk) * (*A.smin_dev);
+      }
+    __syncthreads();
+  }
+
   // ---- CFL: dt = min_i CFL * 0.5 * wJ_i / lambda_i, low_order_graph_viscosity.jl:222-281
   if (DO_LOW && A.nstage == 1) {
     double dtloc = INFINITY;
@@ -494,15 +578,19 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         double Pv[4], kk = -4 * dtl * rwJ[s];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]));
+        double lp = limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]);
+        if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s], Pv, lbnd[nbase + (d == 0 ? s + line * N1D : line + s * N1D)], lp);
+        l = jl_min(l, lp);
       }
       if (s >= 1) {    // node to the left/bottom: P = +4 dt (fH - fL) / wJ (subcell.jl:312,340)
         double Pv[4], kk = 4 * dtl * rwJ[s - 1];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        l = jl_min(l, limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]));
+        double lp = limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]);
+        if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s - 1], Pv, lbnd[nbase + (d == 0 ? (s - 1) + line * N1D : line + (s - 1) * N1D)], lp);
+        l = jl_min(l, lp);
       }
-      lv[s] = jl_min(l, A.blend);
+      lv[s] = jl_min(l, blend);
     }
     double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
 #pragma unroll
@@ -553,7 +641,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
     for (int j = 0; j < N1D; ++j) l = jl_min(l, lmin[el * N1D + j]);
     if (ln == 0) A.Lout[k] = l;
-    l = jl_min(l, A.blend);
+    l = jl_min(l, blend);
   }
   if (d == 0) {
 #pragma unroll

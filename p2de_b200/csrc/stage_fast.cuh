@@ -503,10 +503,12 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
       Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
       const double lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
       const double lsym = jl_min(lv, lP);
-      const double w = (e ? (lsym - lv) : -(lsym - lv)) * s_rwJ[s_fq2q[f]];
-      Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
       double *c = corr + (el * Nfp + f) * 4;
-      c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
+      if (lsym != lv) {   // the neighbour limits this face harder than this element did
+        const double w = (e ? (lsym - lv) : -(lsym - lv)) * s_rwJ[s_fq2q[f]];
+        Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
+        c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
+      } else { c[0] = 0.0; c[1] = 0.0; c[2] = 0.0; c[3] = 0.0; }   // dFend is not even read
       if (A.Llocal_out) A.Llocal_out[k * NL + lidx] = lsym;
     }
   }

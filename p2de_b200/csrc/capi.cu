@@ -702,6 +702,11 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
   if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
+  // stages 2/3 of the FAST subcell path: the limiter's dt is the step's dt, so the stage kernel can
+  // already form the SSP combine of the un-corrected rhs and the update kernel only adds corrections
+  const bool fuse = h->fast && h->mode == MODE_SUBCELL && Uout && !want_outputs && nstage > 1 &&
+                    limiter_dt_dev == update_dt_dev;
+  if (fuse) { A.fuse = 1; A.fuse_a = a; A.fuse_b = b; A.fuse_resW = resW; }
   if (int rc = launch_stage(h, A)) return rc;
   if (h->comm) {
     if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
@@ -717,7 +722,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.rhsU_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->rhsU : nullptr;
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
   B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
-  B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0;
+  B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0; B.pre_updated = fuse ? 1 : 0;
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
   return 0;
 }

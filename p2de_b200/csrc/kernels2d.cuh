@@ -75,6 +75,10 @@ struct StageArgs {
   double hen_a, hen_c;
   const double *VDM_inv;             // [Np, Nq] column-major (device)
   const double *smin_dev;            // global minimum of s_modified at t0 (device scalar)
+  // FAST subcell kernel, stages 2 and 3: write a*resW + b*(Uq + dt*rpre) instead of rpre
+  int fuse;
+  double fuse_a, fuse_b;
+  const double *fuse_resW;
 };
 
 struct UpdateArgs {
@@ -90,6 +94,7 @@ struct UpdateArgs {
   double dt_host;
   int use_dt_dev;
   int rotated;                       // dF of y-lines is stored in the rotated frame (FAST stage kernel)
+  int pre_updated;                   // rpre already holds the SSP combine of the un-corrected rhs (StageArgs.fuse)
   double Jq;
 };
 

@@ -145,6 +145,8 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     const long long k2 = (long long)blockIdx.x * EPB + e2;
     if (k2 < M.K) {
       Cons2 U = load_cons(A.Uq + (k2 * Nq + node) * 4);
+      if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + (k2 * Nq + node) * 4));
       double *o = nodes + node_pos<N1D>(e2, node % N1D, node / N1D);
       double rinv = rcp_fast(U.rho);
       double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
@@ -411,6 +413,13 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
         double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
         double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
+        if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
+          Cons2 w = load_cons(A.fuse_resW + ((kb + e2) * Nq + node) * 4);
+          r[0] = A.fuse_a * w.rho + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
+          r[1] = A.fuse_a * w.m1 + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
+          r[2] = A.fuse_a * w.m2 + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
+          r[3] = A.fuse_a * w.E + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
+        }
         store4(A.rpre + ((kb + e2) * Nq + node) * 4, r);
       }
     }
@@ -531,6 +540,17 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
     if (i == N1D - 1) { const double *c = cb + (1 * N1D + j) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
     if (j == 0) { const double *c = cb + (2 * N1D + i) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
     if (j == N1D - 1) { const double *c = cb + (3 * N1D + i) * 4; r[0] += c[0]; r[1] += c[1]; r[2] += c[2]; r[3] += c[3]; }
+    if (A.pre_updated) {   // rpre already holds a*resW + b*(Uq + dt*rhs_uncorrected): add b*dt*correction
+      const double *cb2 = corr + el * Nfp * 4;
+      double un[4] = {rp.rho, rp.m1, rp.m2, rp.E};
+      const double bd = A.b * dt;
+      if (i == 0) { const double *c = cb2 + (0 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+      if (i == N1D - 1) { const double *c = cb2 + (1 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+      if (j == 0) { const double *c = cb2 + (2 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+      if (j == N1D - 1) { const double *c = cb2 + (3 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+      store4(A.Uq_out + off, un);
+      continue;
+    }
     if (A.rhsU_out) store4(A.rhsU_out + off, r);
     if (A.Uq_out) {
       Cons2 u = load_cons(A.Uq_in + off);

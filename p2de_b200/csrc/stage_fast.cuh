@@ -139,28 +139,56 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     const double *src = reinterpret_cast<const double *>(&Tc);
     for (int i = tid; i < TBLC; i += NT) sm[i] = src[i];
   }
+  // ---- the two neighbour face nodes of this line: issue the loads now (one 32-byte node each, two
+  //      16-byte loads) so that their latency is covered by the node phase
+  Nbr nb[2];
+  Cons2 UnbC[2];
+  if (active) {
+    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
+      UnbC[e] = load_cons(A.Uq + (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4);
+    }
+  }
   // ---- node phase (every volume node once): primitives, logs, axis wavespeeds
+  constexpr bool LAZY_LOGS = DO_HIGH && Nq == 16 && NT % 32 == 0 && S % NT == 0;
+#pragma unroll
   for (int n = tid; n < S; n += NT) {
     const int e2 = n / Nq, node = n % Nq;
     const long long k2 = (long long)blockIdx.x * EPB + e2;
-    if (k2 < M.K) {
-      Cons2 U = load_cons(A.Uq + (k2 * Nq + node) * 4);
-      if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + (k2 * Nq + node) * 4));
+    const bool valid = k2 < M.K;
+    if (valid || LAZY_LOGS) {
+      Cons2 U;
+      U.rho = 1.0; U.m1 = 0.0; U.m2 = 0.0; U.E = 1.0;
+      if (valid) {
+        U = load_cons(A.Uq + (k2 * Nq + node) * 4);
+        if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + (k2 * Nq + node) * 4));
+      }
       double *o = nodes + node_pos<N1D>(e2, node % N1D, node / N1D);
       double rinv = rcp_fast(U.rho);
       double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
       double beta = 0.5 * U.rho * rcp_fast(p);
       o[0 * S] = U.rho; o[1 * S] = U.m1; o[2 * S] = U.m2; o[3 * S] = U.E;
       o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv; o[6 * S] = p; o[7 * S] = beta;
-#ifdef P2DE_EXP_NONODE
-      if (DO_HIGH) { o[8 * S] = U.rho; o[9 * S] = beta; }
-      o[10 * S] = U.m1 * rinv; o[11 * S] = U.m2 * rinv;
-#else
-      if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
+      if (DO_HIGH) {
+        // log(rho), log(beta) are only read by the non-series branch of logmean (:307-321), i.e. by a
+        // node pair with |da| >= 1e-4 |aavg|.  If rho and beta each vary by less than 6.2e-5
+        // relative over the whole element (compared on the high words of the doubles: 65 units of
+        // 2^-20), no pair of this element can take that branch and the logs are never looked at.
+        bool need = true;
+        if (LAZY_LOGS) {
+          const unsigned hm = 0xFFFFu << (tid & 16);    // the 16 lanes holding this element's nodes
+          const unsigned hr = (unsigned)__double2hiint(U.rho), hb = (unsigned)__double2hiint(beta);
+          const unsigned dr = __reduce_max_sync(hm, hr) - __reduce_min_sync(hm, hr);
+          const unsigned db = __reduce_max_sync(hm, hb) - __reduce_min_sync(hm, hb);
+          need = (dr | db) > 64u;
+        }
+        if (need) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
+      }
       o[10 * S] = wavespeed_rot(gamma, gm1, rinv, U.m1, U.E);
       o[11 * S] = wavespeed_rot(gamma, gm1, rinv, U.m2, U.E);
-#endif
     }
   }
   __syncthreads();
@@ -179,14 +207,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     wJ[a] = A.Jq * T.wq[node]; rwJ[a] = T.rwJ[node];
   }
   if (active) {
-    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
-    Nbr nb[2];
     ConsR Unb[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
-      const double *p = A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4;
-      Unb[e].rho = p[0]; Unb[e].mn = p[1 + d]; Unb[e].mt = p[2 - d]; Unb[e].E = p[3];
+      Unb[e].rho = UnbC[e].rho; Unb[e].mn = d ? UnbC[e].m2 : UnbC[e].m1;
+      Unb[e].mt = d ? UnbC[e].m1 : UnbC[e].m2; Unb[e].E = UnbC[e].E;
     }
     double lamPair[N1D], lamFace[2];
     {

@@ -117,6 +117,7 @@ struct p2de_handle {
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
   unsigned long long *dt_bits = nullptr;
   double *partial = nullptr;  // reduction scratch
+  double *tab_dev = nullptr;  // device copy of the Tables2D<N1D> struct (coalesced load into shared memory)
   int *mapP32 = nullptr, *bcflag = nullptr;
   double *Ival = nullptr;
   unsigned char *bc_type[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -521,6 +522,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.VDM_inv = h->VDM_inv; A.smin_dev = reinterpret_cast<const double *>(h->smin_bits);
   A.roundtrip = h->cfg.lgl_projection_roundtrip;
   A.half_inv_gm1 = 1.0 / (2.0 * (h->cfg.gamma - 1.0));
+  A.tab_dev = h->tab_dev;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   return A;
 }
@@ -845,6 +847,12 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if (cudaMemcpy(h->VDM_inv, ops->VDM_inv, (size_t)h->Nq * h->Nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy VDM_inv"));
   }
   if (cudaMemcpy(h->partial + 1024, h->wq.data(), h->Nq * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy wq"));
+  {
+    const void *src = N1D == 2 ? (const void *)&h->t2 : N1D == 3 ? (const void *)&h->t3 : N1D == 4 ? (const void *)&h->t4 : (const void *)&h->t5;
+    const size_t nb = N1D == 2 ? sizeof(h->t2) : N1D == 3 ? sizeof(h->t3) : N1D == 4 ? sizeof(h->t4) : sizeof(h->t5);
+    if ((rc = dev_alloc(h, &h->tab_dev, (nb + 7) / 8 + 2))) return bail(rc);
+    if (cudaMemcpy(h->tab_dev, src, nb, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy tables"));
+  }
   *out = h;
   return P2DE_OK;
 }

@@ -79,6 +79,7 @@ struct StageArgs {
   int fuse;
   double fuse_a, fuse_b;
   const double *fuse_resW;
+  const double *tab_dev;             // Tables2D<N1D> in global memory (same bytes as the kernel parameter)
 };
 
 struct UpdateArgs {

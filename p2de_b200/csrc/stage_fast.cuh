@@ -135,16 +135,18 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   const bool active = k < M.K;
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
 
-  {
-    const double *src = reinterpret_cast<const double *>(&Tc);
-    for (int i = tid; i < TBLC; i += NT) sm[i] = src[i];
-  }
+  // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a
+  // lane-serialised constant-bank access)
+  for (int i = tid; i < TBLC; i += NT) sm[i] = A.tab_dev[i];
+  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   // ---- the two neighbour face nodes of this line: issue the loads now (one 32-byte node each, two
   //      16-byte loads) so that their latency is covered by the node phase
   Nbr nb[2];
   Cons2 UnbC[2];
   if (active) {
-    const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
+    int ix, iy;
+    if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
+    else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
@@ -176,14 +178,15 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         // log(rho), log(beta) are only read by the non-series branch of logmean (:307-321), i.e. by a
         // node pair with |da| >= 1e-4 |aavg|.  If rho and beta each vary by less than 6.2e-5
         // relative over the whole element (compared on the high words of the doubles: 65 units of
-        // 2^-20), no pair of this element can take that branch and the logs are never looked at.
+        // 2^-20 at most), no pair of this element can take that branch and the logs are never looked at.
         bool need = true;
         if (LAZY_LOGS) {
-          const unsigned hm = 0xFFFFu << (tid & 16);    // the 16 lanes holding this element's nodes
-          const unsigned hr = (unsigned)__double2hiint(U.rho), hb = (unsigned)__double2hiint(beta);
-          const unsigned dr = __reduce_max_sync(hm, hr) - __reduce_min_sync(hm, hr);
-          const unsigned db = __reduce_max_sync(hm, hb) - __reduce_min_sync(hm, hb);
-          need = (dr | db) > 64u;
+          // every node within 32 units of the element's first node => spread <= 64 units
+          const int hr = __double2hiint(U.rho), hb = __double2hiint(beta);
+          const int lead = tid & 16;                     // first of the 16 lanes holding this element's nodes
+          const int er = hr - __shfl_sync(0xffffffffu, hr, lead), eb = hb - __shfl_sync(0xffffffffu, hb, lead);
+          const bool far = (unsigned)(er + 32) > 64u || (unsigned)(eb + 32) > 64u;
+          need = ((__ballot_sync(0xffffffffu, far) >> lead) & 0xFFFFu) != 0u;
         }
         if (need) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
       }
@@ -198,7 +201,6 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   double G[N1D][4];
   double dF0[4];
   double wJ[N1D], rwJ[N1D];
-  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
 #pragma unroll
   for (int a = 0; a < N1D; ++a) {
     const int i = d == 0 ? a : line, j = d == 0 ? line : a;
@@ -429,17 +431,29 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 #pragma unroll
     for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
     }   // active
-    __syncthreads();
     // ---- flat, coalesced output phase: rpre = x share + y share (y share un-rotated), lpre
     const long long kb = (long long)blockIdx.x * EPB;
-    for (int n = tid; n < S; n += NT) {
+    constexpr int NIT = (S + NT - 1) / NT;
+    Cons2 wres[NIT];
+    if (A.fuse) {   // resW of this thread's nodes: in flight across the barrier
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int n = tid + it * NT;
+        if (n < S && kb + n / Nq < M.K) wres[it] = load_cons(A.fuse_resW + (kb * Nq + n) * 4);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int n = tid + it * NT;
+      if (n >= S) break;
       const int e2 = n / Nq, node = n % Nq;
       if (kb + e2 < M.K) {
         const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
         double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
         double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
         if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
-          Cons2 w = load_cons(A.fuse_resW + ((kb + e2) * Nq + node) * 4);
+          const Cons2 w = wres[it];
           r[0] = A.fuse_a * w.rho + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
           r[1] = A.fuse_a * w.m1 + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
           r[2] = A.fuse_a * w.m2 + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
@@ -449,8 +463,12 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       }
     }
     constexpr int NL = 2 * N1D * NF;
-    for (int n = tid; n < EPB * NL; n += NT)
-      if (kb + n / NL < M.K) A.lpre[kb * NL + n] = lstage[n];
+    if (kb + EPB <= M.K) {
+      for (int n = tid; n < EPB * NL; n += NT) A.lpre[kb * NL + n] = lstage[n];
+    } else {
+      for (int n = tid; n < EPB * NL; n += NT)
+        if (kb + n / NL < M.K) A.lpre[kb * NL + n] = lstage[n];
+    }
     return;
   }
 

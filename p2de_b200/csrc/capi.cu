@@ -106,6 +106,7 @@ struct p2de_handle {
 
   // device memory
   double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
+  double *Uc = nullptr;               // FAST subcell path: third state buffer (stage-2 result)
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
   double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
@@ -489,6 +490,26 @@ int launch_update_fast(p2de_handle *h, const UpdateArgs &A) {
   return 0;
 }
 template <int N1D>
+int launch_fix_n(p2de_handle *h, const UpdateArgs &A) {
+  constexpr int EPB = 16;
+  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  prof_begin(h, 1);
+  interface_fix_kernel<N1D, EPB><<<grid, EPB * 16, 0, h->stream>>>(A, h->topo, tables<N1D>(h));
+  prof_end(h);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+int launch_fix(p2de_handle *h, const UpdateArgs &A) {
+  switch (h->N1D) {
+    case 2: return launch_fix_n<2>(h, A);
+    case 3: return launch_fix_n<3>(h, A);
+    case 4: return launch_fix_n<4>(h, A);
+    case 5: return launch_fix_n<5>(h, A);
+  }
+  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+template <int N1D>
 int launch_update_n(p2de_handle *h, const UpdateArgs &A) {
   if (h->mode == MODE_SUBCELL && h->fast) return launch_update_fast<N1D>(h, A);
   if (h->mode == MODE_SUBCELL) return launch_update_t<N1D, MODE_SUBCELL>(h, A);
@@ -708,7 +729,11 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   // already form the SSP combine of the un-corrected rhs and the update kernel only adds corrections
   const bool fuse = h->fast && h->mode == MODE_SUBCELL && Uout && !want_outputs && nstage > 1 &&
                     limiter_dt_dev == update_dt_dev;
+  // ... and when the output buffer is not the input buffer it writes the new state itself; the
+  // interface symmetrisation is then a sparse fix-up (interface_fix_kernel)
+  const bool direct = fuse && Uout != Uin && Uout != resW;
   if (fuse) { A.fuse = 1; A.fuse_a = a; A.fuse_b = b; A.fuse_resW = resW; }
+  if (direct) A.rpre = Uout;
   if (int rc = launch_stage(h, A)) return rc;
   if (h->comm) {
     if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
@@ -725,6 +750,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
   B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
   B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0; B.pre_updated = fuse ? 1 : 0;
+  if (direct) return launch_fix(h, B);
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
   return 0;
 }
@@ -829,6 +855,8 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if ((rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL))) return bail(rc);
     if (h->fast) {
       if ((rc = dev_alloc(h, &h->rpre, nU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
+      const char *nd = getenv("P2DE_NO_DIRECT");   // testing aid: keep the in-place two-kernel schedule for stages 2/3
+      if (!(nd && atoi(nd)) && (rc = dev_alloc_halo(h, &h->Uc, nU, rowU))) return bail(rc);
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
   } else {
@@ -925,8 +953,11 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
   const bool has_cfl = h->mode != MODE_HIGH;                          // FluxDiffRHS never changes dt (rhs.jl:38)
   // stage 1: limiter sees the cap (rhs.jl:46,52), the combine sees the CFL-limited dt
   if (int rc = run_stage(h, Ua, 1, t, cap, false, has_cfl, Ub, Ua, 0.0, 1.0, outs)) return rc;
-  if (int rc = run_stage(h, Ub, 2, t, cap, has_cfl, has_cfl, Ub, Ua, 3.0 / 4.0, 1.0 / 4.0, outs)) return rc;
-  if (int rc = run_stage(h, Ub, 3, t, cap, has_cfl, has_cfl, Ub, Ua, 1.0 / 3.0, 2.0 / 3.0, outs)) return rc;
+  // with a third buffer (FAST subcell path) stages 2 and 3 go Ub -> Uc -> Ub out of place, so that the
+  // stage kernel can write the new state directly (run_stage: `direct`)
+  double *U2 = (h->Uc && !outs) ? h->Uc : Ub;
+  if (int rc = run_stage(h, Ub, 2, t, cap, has_cfl, has_cfl, U2, Ua, 3.0 / 4.0, 1.0 / 4.0, outs)) return rc;
+  if (int rc = run_stage(h, U2, 3, t, cap, has_cfl, has_cfl, Ub, Ua, 1.0 / 3.0, 2.0 / 3.0, outs)) return rc;
   h->cur = 1 - h->cur;
   return P2DE_OK;
 }

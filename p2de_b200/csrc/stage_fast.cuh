@@ -612,4 +612,62 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
   }
 }
 
+// Stages 2 and 3 of the FAST subcell path write a*resW + b*(Uq + dt*rhs_uncorrected) straight into
+// the next state buffer (StageArgs.fuse with rpre = that buffer), so what is left of the interface
+// symmetrisation (subcell.jl:418-456) is a SPARSE fix-up: only where the neighbour's coefficient is
+// smaller than this element's own, b*dt*(l_sym - l)*dF_end/wJ is added to the node on the element
+// boundary.  On interior faces f_H - f_L is rounding noise (identity LGL projection), so both sides
+// almost always return 1 and this kernel reads the interface coefficients and exits.
+// 16 threads per element, one per face node (N1D = 5: strided).  Same arithmetic, in the same
+// order, as update_kernel_fast's pre_updated branch.
+template <int N1D, int EPB>
+__global__ void __launch_bounds__(EPB * 16)
+interface_fix_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ MeshTopo M,
+                     const __grid_constant__ Tables2D<N1D> Tc) {
+  constexpr int Nq = N1D * N1D, Nfp = 4 * N1D, NF = N1D + 1, NL = 2 * N1D * NF, TPE = 16;
+  __shared__ double corr[EPB * Nfp * 4];
+  const int tid = threadIdx.x, el = tid / TPE, tl = tid % TPE;
+  const long long k = (long long)blockIdx.x * EPB + el;
+  const bool active = k < M.K;
+  int any = 0;
+  if (active) {
+    int ix, iy;
+    if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
+    else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
+    for (int f = tl; f < Nfp; f += TPE) {
+      const int F = f / N1D, line = f % N1D, d = F >> 1, e = F & 1;
+      const int s = e ? N1D : 0;
+      const int lidx = d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D);
+      const double lv = A.lpre[k * NL + lidx];
+      Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
+      const double lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
+      const double lsym = jl_min(lv, lP);
+      double *c = corr + (el * Nfp + f) * 4;
+      if (lsym != lv) {   // the neighbour limits this face harder than this element did
+        const double w = (e ? (lsym - lv) : -(lsym - lv)) * Tc.rwJ[Tc.fq2q[f]];
+        Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
+        c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
+        any = 1;
+      } else { c[0] = 0.0; c[1] = 0.0; c[2] = 0.0; c[3] = 0.0; }
+    }
+  }
+  if (!__syncthreads_or(any)) return;
+  if (!active) return;
+  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+  const double bd = A.b * dt;
+  const double *cb = corr + el * Nfp * 4;
+  for (int node = tl; node < Nq; node += TPE) {
+    const int i = node % N1D, j = node / N1D;
+    if (i != 0 && i != N1D - 1 && j != 0 && j != N1D - 1) continue;
+    const long long off = (k * Nq + node) * 4;
+    Cons2 rp = load_cons(A.Uq_out + off);
+    double un[4] = {rp.rho, rp.m1, rp.m2, rp.E};
+    if (i == 0) { const double *c = cb + (0 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+    if (i == N1D - 1) { const double *c = cb + (1 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+    if (j == 0) { const double *c = cb + (2 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+    if (j == N1D - 1) { const double *c = cb + (3 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
+    store4(A.Uq_out + off, un);
+  }
+}
+
 }  // namespace p2de

@@ -251,3 +251,25 @@ def test_limiter_variants_on_shocks(variant):
     assert (L < 1.0).any()
     param, Ug, Uo, st, orc = run_both(P.sedov(N=2, K=(8, 8), limiter=VARIANTS[variant]), 8)
     assert rel(Ug, Uo) < 1e-7
+
+
+def test_direct_stage_output_is_bitwise_equal_to_two_kernel_schedule(monkeypatch):
+    """Stages 2/3 of the FAST subcell path write the new state from the stage kernel and fix the
+    interfaces sparsely (capi.cu run_stage: `direct`); P2DE_NO_DIRECT=1 keeps the dense update
+    kernel.  Same arithmetic, so the states must be identical."""
+    from p2de_b200.api import State
+    from p2de_b200.types import Solver
+    for prob in (P.dmr(N=3, K=(24, 16)), P.sedov(N=3, K=(12, 12))):
+        param, rd, md, dd, bc, U0 = P.setup(prob)
+        out = []
+        for flag in ("1", "0"):
+            monkeypatch.setenv("P2DE_NO_DIRECT", flag)
+            st = State(Solver(param=param, rd=rd, md=md, discrete_data=dd), bc)
+            st.set_state(U0)
+            t, dts = 0.0, []
+            for _ in range(6):
+                dt = st.ssp33_step(t); t += dt; dts.append(dt)
+            out.append((st.preallocation.Uq, dts))
+            st.close()
+        assert out[0][1] == out[1][1]
+        assert np.array_equal(out[0][0], out[1][0])

@@ -80,7 +80,7 @@ enum {
   P2DE_FIELD_L_LOCAL = 5,     /* [Nq+N1D,Nd,K,Ns] subcell coefficients (1D: first Nq+1 used) */
   P2DE_FIELD_THETA = 6,       /* [K,Ns]                                                  */
   P2DE_FIELD_THETA_LOCAL = 7, /* [Nfp,K,Ns]                                              */
-  P2DE_FIELD_RESW = 8         /* [Nc,Nq,K]  previous-step copy used by SSP33!            */
+  P2DE_FIELD_RESW = 8         /* [Nc,Nq,K]  the other state buffer (scratch of SSP33!; content after a step is unspecified) */
 };
 
 /* ---- reductions (p2de_reduce) ------------------------------------------------------ */

@@ -106,7 +106,7 @@ struct p2de_handle {
 
   // device memory
   double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
-  double *Uc = nullptr;               // FAST subcell path: third state buffer (stage-2 result)
+  bool direct = false;                // FAST subcell path: stages 2/3 write the state from the stage kernel
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
   double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
@@ -731,7 +731,8 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
                     limiter_dt_dev == update_dt_dev;
   // ... and when the output buffer is not the input buffer it writes the new state itself; the
   // interface symmetrisation is then a sparse fix-up (interface_fix_kernel)
-  const bool direct = fuse && Uout != Uin && Uout != resW;
+  // (Uout == resW is fine: a node's resW is read by the one thread that then writes that node)
+  const bool direct = fuse && Uout != Uin;
   if (fuse) { A.fuse = 1; A.fuse_a = a; A.fuse_b = b; A.fuse_resW = resW; }
   if (direct) A.rpre = Uout;
   if (int rc = launch_stage(h, A)) return rc;
@@ -854,9 +855,9 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if (mode == MODE_SUBCELL) {
     if ((rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL))) return bail(rc);
     if (h->fast) {
-      if ((rc = dev_alloc(h, &h->rpre, nU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
-      const char *nd = getenv("P2DE_NO_DIRECT");   // testing aid: keep the in-place two-kernel schedule for stages 2/3
-      if (!(nd && atoi(nd)) && (rc = dev_alloc_halo(h, &h->Uc, nU, rowU))) return bail(rc);
+      if ((rc = dev_alloc_halo(h, &h->rpre, nU, rowU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
+      const char *nd = getenv("P2DE_NO_DIRECT");   // testing aid: keep the dense update kernel after every stage
+      h->direct = !(nd && atoi(nd));
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
   } else {
@@ -951,13 +952,20 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
   double *Ua = h->U[h->cur], *Ub = h->U[1 - h->cur];
   double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // SSPRK33.jl:30
   const bool has_cfl = h->mode != MODE_HIGH;                          // FluxDiffRHS never changes dt (rhs.jl:38)
+  if (h->direct && h->fast && h->mode == MODE_SUBCELL && h->dim == 2 && !outs) {
+    // Direct schedule: stages 2 and 3 write their result from the stage kernel (run_stage: `direct`), which
+    // needs an output buffer other than the stage input: U1 -> Ub (dense update, dt only known after the
+    // stage-1 kernel), U2 -> the rpre buffer (free once the stage-1 update has consumed it), U^{n+1} -> over
+    // U^n, which stage 3 reads only as its own resW, node by node, by the thread that then writes the node.
+    if (int rc = run_stage(h, Ua, 1, t, cap, false, true, Ub, Ua, 0.0, 1.0, false)) return rc;
+    if (int rc = run_stage(h, Ub, 2, t, cap, true, true, h->rpre, Ua, 3.0 / 4.0, 1.0 / 4.0, false)) return rc;
+    if (int rc = run_stage(h, h->rpre, 3, t, cap, true, true, Ua, Ua, 1.0 / 3.0, 2.0 / 3.0, false)) return rc;
+    return P2DE_OK;
+  }
   // stage 1: limiter sees the cap (rhs.jl:46,52), the combine sees the CFL-limited dt
   if (int rc = run_stage(h, Ua, 1, t, cap, false, has_cfl, Ub, Ua, 0.0, 1.0, outs)) return rc;
-  // with a third buffer (FAST subcell path) stages 2 and 3 go Ub -> Uc -> Ub out of place, so that the
-  // stage kernel can write the new state directly (run_stage: `direct`)
-  double *U2 = (h->Uc && !outs) ? h->Uc : Ub;
-  if (int rc = run_stage(h, Ub, 2, t, cap, has_cfl, has_cfl, U2, Ua, 3.0 / 4.0, 1.0 / 4.0, outs)) return rc;
-  if (int rc = run_stage(h, U2, 3, t, cap, has_cfl, has_cfl, Ub, Ua, 1.0 / 3.0, 2.0 / 3.0, outs)) return rc;
+  if (int rc = run_stage(h, Ub, 2, t, cap, has_cfl, has_cfl, Ub, Ua, 3.0 / 4.0, 1.0 / 4.0, outs)) return rc;
+  if (int rc = run_stage(h, Ub, 3, t, cap, has_cfl, has_cfl, Ub, Ua, 1.0 / 3.0, 2.0 / 3.0, outs)) return rc;
   h->cur = 1 - h->cur;
   return P2DE_OK;
 }

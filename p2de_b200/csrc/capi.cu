@@ -274,10 +274,19 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
   for (int i = 0; i < Nq; ++i) {
     T.wq[i] = o->wq[i];
     T.rwJ[i] = 1.0 / (h->Jq * o->wq[i]);
+    T.rwJl[0][i / N1D][i % N1D] = T.rwJ[i]; T.rwJl[1][i % N1D][i / N1D] = T.rwJ[i];
     T.minv[i] = o->MinvVhT[i + (size_t)i * Nq];
     if (std::fabs(T.minv[i] * o->wq[i] - 1.0) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "MinvVhT diagonal is not 1/wq");
     for (int j = 0; j < Nq; ++j)
       if (j != i && o->MinvVhT[i + (size_t)j * Nq] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "mass matrix is not diagonal");
+  }
+  for (int e4 = 0; e4 < 4; ++e4) {
+    for (int node = 0; node < Nq; ++node) T.posn[e4][node] = node_pos<N1D>(e4, node % N1D, node / N1D) - e4 * Nq;
+    for (int line = 0; line < N1D; ++line)
+      for (int a = 0; a < N1D; ++a) {
+        T.posl[0][e4][line][a] = node_pos<N1D>(e4, a, line) - e4 * Nq;
+        T.posl[1][e4][line][a] = node_pos<N1D>(e4, line, a) - e4 * Nq;
+      }
   }
   for (int f = 0; f < Nfp; ++f) {
     T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
@@ -425,6 +434,7 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
   constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
   size_t smem = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
+  if (const char *pad = getenv("P2DE_SMEM_PAD")) smem += (size_t)atoi(pad);   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
   if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, false>;
   static bool attr_set = false;

@@ -37,6 +37,10 @@ struct Tables2D {
   double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
   double wq[N1D * N1D];
   double rwJ[N1D * N1D];        // 1 / (Jq * wq)
+  double rwJl[2][N1D][N1D];     // the same per grid line: [d][line][a]
+  // shared-memory positions used by stage_kernel_fast (see node_pos there), as look-up tables:
+  int posl[2][4][N1D][N1D];     // [d][el & 3][line][a]: node_pos(el, .) - el * Nq of the a-th node of a line
+  int posn[4][N1D * N1D];       // [el & 3][node]: the same for a flat node index
   double minv[N1D * N1D];       // MinvVhT[i, i]
   double minvf[4 * N1D];        // MinvVfT[fq2q[f], f]
   int fq2q[4 * N1D];            // 0-based

@@ -21,15 +21,17 @@ namespace p2de {
 #define P2DE_FAST_MIN_BLOCKS 4
 #endif
 
-// reciprocal: MUFU.RCP64H seed (~20 bits) + two Newton steps (error ~ seed^4)
+// constants of logmean's series branch (:315-317) and its reciprocal: read as constant-bank operands
+__constant__ double kSeries[5] = {-0.2, 0.0512, 0.026038857142857, 0.2, 0.0912};
+
+// reciprocal: MUFU.RCP64H seed (>= 20 bits) + one third-order step x (1 + e + e^2), e = 1 - a x
+// (error ~ e^3 < 2^-60: three dependent FMAs instead of the four of two Newton steps)
 P2DE_DEV double rcp_fast(double a) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
   double e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  e = fma(-a, x, 1.0);
-  x = fma(x, e, x);
-  return x;
+  double t = fma(e, e, e);
+  return fma(x, t, x);
 }
 // n / a with one residual correction (last-bit accurate for normal operands)
 P2DE_DEV double div_fast(double n, double a) {
@@ -72,9 +74,8 @@ P2DE_DEV void div3_fast(double n0, double a0, double n1, double a1, double n2, d
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x1) : "d"(a1));
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x2) : "d"(a2));
   double e0 = fma(-a0, x0, 1.0), e1 = fma(-a1, x1, 1.0), e2 = fma(-a2, x2, 1.0);
-  x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
-  e0 = fma(-a0, x0, 1.0); e1 = fma(-a1, x1, 1.0); e2 = fma(-a2, x2, 1.0);
-  x0 = fma(x0, e0, x0); x1 = fma(x1, e1, x1); x2 = fma(x2, e2, x2);
+  double t0 = fma(e0, e0, e0), t1 = fma(e1, e1, e1), t2 = fma(e2, e2, e2);
+  x0 = fma(x0, t0, x0); x1 = fma(x1, t1, x1); x2 = fma(x2, t2, x2);
   q0 = n0 * x0; q1 = n1 * x1; q2 = n2 * x2;   // <= ~1.5 ulp each; no residual correction needed at 1e-12
 }
 
@@ -89,9 +90,9 @@ P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double
             serb ? 1.0 : (R.betalog - L.betalog), serb ? bavg : db,
             aavg, L.beta + R.beta, q, qb, pa);
   double v = q * q;
-  double rholog = ser ? aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857))) : q;
+  double rholog = ser ? aavg * (1 + v * (kSeries[0] - v * (kSeries[1] - v * kSeries[2]))) : q;
   double fb = db * qb, vb = fb * fb;
-  double inv_betalog = serb ? qb * (1 + vb * (0.2 + vb * 0.0912)) : qb;
+  double inv_betalog = serb ? qb * (1 + vb * (kSeries[3] + vb * kSeries[4])) : qb;
   double unavg = 0.5 * (L.un + R.un), utavg = 0.5 * (L.ut + R.ut);
   double unorm = L.un * R.un + L.ut * R.ut;
   double f4aux = rholog * inv_betalog * half_inv_gm1 + pa + 0.5 * rholog * unorm;
@@ -101,16 +102,24 @@ P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double
 
 // shared-memory position of node (i, j) of CTA-local element el
 template <int N1D>
-P2DE_DEV int node_pos(int el, int i, int j) {
+__host__ __device__ __forceinline__ int node_pos(int el, int i, int j) {
   if (N1D == 4) return el * 16 + 4 * ((j + el) & 3) + ((i + j) & 3);
   return el * (N1D * N1D) + i + j * N1D;
 }
 
+// doubles of shared memory per element, besides the tables: 12 node fields, rhsxyL shares (partsL),
+// rhsxyH shares (partsH, not MODE_SUBCELL), the CFL lambda sums [2][Nq] that are later reused as the
+// L_local staging [2*N1D*(N1D+1)], and lmin
+template <int N1D>
+__host__ __device__ constexpr int fast_lamp_per_elem() {
+  return 2 * N1D * N1D > 2 * N1D * (N1D + 1) ? 2 * N1D * N1D : 2 * N1D * (N1D + 1);
+}
 template <int N1D, int MODE>
 constexpr int fast_smem_doubles_per_elem() {
   constexpr int Nq = N1D * N1D;
-  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D;
+  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + fast_lamp_per_elem<N1D>() + N1D;
 }
+
 
 template <int N1D, int MODE, int EPB>
 __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? 5 : P2DE_FAST_MIN_BLOCKS))
@@ -126,49 +135,82 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   double *nodes = sm + TBL;                       // [NFLD][S]   swizzled node positions
   double2 *partsL = reinterpret_cast<double2 *>(nodes + NFLD * S);   // [d][half][S]
   double2 *partsH = partsL + 4 * S;                                   // [d][half][S] (not MODE_SUBCELL)
-  double *lamp = reinterpret_cast<double *>(partsH + ((MODE == MODE_SUBCELL) ? 0 : 4 * S));  // [6][S]
-  double *lmin = lamp + 6 * S;                    // [EPB][N1D]
+  double *lamp = reinterpret_cast<double *>(partsH + ((MODE == MODE_SUBCELL) ? 0 : 4 * S));  // [2][S] / lstage
+  double *lmin = lamp + EPB * fast_lamp_per_elem<N1D>();   // [EPB][N1D]
 
   const int tid = threadIdx.x;
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
-  const long long k = (long long)blockIdx.x * EPB + el;
+  const long long kb = (long long)blockIdx.x * EPB;      // first element of this CTA's batch
+  const long long k = kb + el;
   const bool active = k < M.K;
+  const bool full = kb + EPB <= M.K;                      // no partial batch: skip the per-element guards
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
+  const double *Ubase = A.Uq + kb * (Nq * 4);             // this batch's states; 32-bit offsets from here on
 
   // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a
   // lane-serialised constant-bank access)
-  for (int i = tid; i < TBLC; i += NT) sm[i] = A.tab_dev[i];
+  {
+    const double2 *src = reinterpret_cast<const double2 *>(A.tab_dev);
+    double2 *dst = reinterpret_cast<double2 *>(sm);
+    for (int i = tid; i < TBL / 2; i += NT) dst[i] = src[i];
+  }
   const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   // ---- the two neighbour face nodes of this line: issue the loads now (one 32-byte node each, two
   //      16-byte loads) so that their latency is covered by the node phase
   Nbr nb[2];
   Cons2 UnbC[2];
-  if (active) {
-    int ix, iy;
-    if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
-    else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
+  {
+    // Structured mesh, batch strictly inside the domain (the common case, CTA-uniform): the neighbours
+    // are k -+ 1 / k -+ Kx, no boundary condition, and the partner face node follows from the LGL face
+    // map that p2de_create verified (build_tables: fq2q).
+    bool interior = false;
+    if (!M.mapP32 && full && M.K < 0x7fffffffll) {
+      const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
+      interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
+    }
+    if (interior) {
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
-      UnbC[e] = load_cons(A.Uq + (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4);
+      for (int e = 0; e < 2; ++e) {
+        nb[e].bc = 0; nb[e].ival = nullptr; nb[e].kP = 0; nb[e].fP = 0;
+        // partner node: d=0: (N1D-1, line) of k-1 / (0, line) of k+1;  d=1: (line, N1D-1) of k-Kx / (line, 0) of k+Kx
+        const int node = d == 0 ? (e ? 0 : N1D - 1) + line * N1D : line + (e ? 0 : N1D - 1) * N1D;
+        const int dk = d == 0 ? (e ? 1 : -1) : (e ? M.Kx : -M.Kx);
+        UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
+      }
+    } else if (active) {
+      int ix, iy;
+      if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
+      else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
+        UnbC[e] = load_cons(A.Uq + (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4);
+      }
     }
   }
   // ---- node phase (every volume node once): primitives, logs, axis wavespeeds
   constexpr bool LAZY_LOGS = DO_HIGH && Nq == 16 && NT % 32 == 0 && S % NT == 0;
+  constexpr int NITN = (S + NT - 1) / NT;
+  Cons2 Uraw[NITN];
 #pragma unroll
-  for (int n = tid; n < S; n += NT) {
+  for (int it = 0; it < NITN; ++it) {   // all of this thread's loads are in flight before anything waits
+    const int n = tid + it * NT;
+    Uraw[it].rho = 1.0; Uraw[it].m1 = 0.0; Uraw[it].m2 = 0.0; Uraw[it].E = 1.0;
+    if (n < S && (full || kb + n / Nq < M.K)) {
+      Uraw[it] = load_cons(Ubase + n * 4);
+      if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
+    }
+  }
+  __syncthreads();   // tables are in shared memory
+#pragma unroll
+  for (int it = 0; it < NITN; ++it) {
+    const int n = tid + it * NT;
     const int e2 = n / Nq, node = n % Nq;
-    const long long k2 = (long long)blockIdx.x * EPB + e2;
-    const bool valid = k2 < M.K;
-    if (valid || LAZY_LOGS) {
-      Cons2 U;
-      U.rho = 1.0; U.m1 = 0.0; U.m2 = 0.0; U.E = 1.0;
-      if (valid) {
-        U = load_cons(A.Uq + (k2 * Nq + node) * 4);
-        if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + (k2 * Nq + node) * 4));
-      }
-      double *o = nodes + node_pos<N1D>(e2, node % N1D, node / N1D);
+    const bool valid = n < S && (full || kb + e2 < M.K);
+    if (valid || (LAZY_LOGS && n < S)) {
+      const Cons2 U = Uraw[it];
+      double *o = nodes + e2 * Nq + T.posn[e2 & 3][node];
       double rinv = rcp_fast(U.rho);
       double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
       double beta = 0.5 * U.rho * rcp_fast(p);
@@ -200,14 +242,9 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   int pos[N1D];
   double G[N1D][4];
   double dF0[4];
-  double wJ[N1D], rwJ[N1D];
 #pragma unroll
-  for (int a = 0; a < N1D; ++a) {
-    const int i = d == 0 ? a : line, j = d == 0 ? line : a;
-    pos[a] = node_pos<N1D>(el, i, j);
-    const int node = i + j * N1D;
-    wJ[a] = A.Jq * T.wq[node]; rwJ[a] = T.rwJ[node];
-  }
+  for (int a = 0; a < N1D; ++a) pos[a] = el * Nq + T.posl[d][el & 3][line][a];
+  const double *rwJ = T.rwJl[d][line];   // 1 / (Jq wq) of this line's nodes
   if (active) {
     ConsR Unb[2];
 #pragma unroll
@@ -240,7 +277,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           const double ui[4] = {U[i].rho, U[i].mn, U[i].mt, U[i].E}, uj[4] = {U[j].rho, U[j].mn, U[j].mt, U[j].E};
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
-            double SF = 2.0 * Sv * (0.5 * (fl[i][c] + fl[j][c])) - lam * (uj[c] - ui[c]);
+            double SF = Sv * (fl[i][c] + fl[j][c]) - lam * (uj[c] - ui[c]);   // 2 Sv (f_i + f_j)/2: the scalings by 2 are exact
             GL[i][c] -= SF; GL[j][c] += SF;          // GL = -Q0F1
           }
         }
@@ -281,11 +318,8 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         if (DO_LOW) {
           partsL[(d * 2 + 0) * S + pos[a]] = make_double2(GL[a][0] * rwJ[a], GL[a][1] * rwJ[a]);
           partsL[(d * 2 + 1) * S + pos[a]] = make_double2(GL[a][2] * rwJ[a], GL[a][3] * rwJ[a]);
-          if (A.nstage == 1) {
-            lamp[(d * 3 + 0) * S + pos[a]] = a > 0 ? lamPair[a - 1] : 0.0;
-            lamp[(d * 3 + 1) * S + pos[a]] = lamPair[a];
-            lamp[(d * 3 + 2) * S + pos[a]] = a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0);
-          }
+          if (A.nstage == 1)   // this direction's share of lambda_i (:222-281): its two volume pairs and its face
+            lamp[d * S + pos[a]] = ((a > 0 ? lamPair[a - 1] : 0.0) + lamPair[a]) + (a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0));
         }
         // G starts as -wJ rhsxyL - BF_H; the volume pairs below add the rest of wJ rhsxyH.
         // (MODE_SUBCELL keeps only the difference; the other modes keep wJ rhsxyH by itself.)
@@ -337,10 +371,8 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     if (active && d == 0) {
 #pragma unroll
       for (int a = 0; a < N1D; ++a) {
-        double li = 0.0;
-        li += lamp[3 * S + pos[a]]; li += lamp[0 * S + pos[a]]; li += lamp[1 * S + pos[a]]; li += lamp[4 * S + pos[a]];
-        li += lamp[2 * S + pos[a]]; li += lamp[5 * S + pos[a]];
-        dtloc = jl_min(dtloc, A.CFL * 0.5 * wJ[a] / li);
+        const double li = lamp[0 * S + pos[a]] + lamp[1 * S + pos[a]];
+        dtloc = jl_min(dtloc, A.CFL * 0.5 * (A.Jq * T.wq[a + line * N1D]) / li);
       }
     }
 #pragma unroll
@@ -432,42 +464,48 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
     }   // active
     // ---- flat, coalesced output phase: rpre = x share + y share (y share un-rotated), lpre
-    const long long kb = (long long)blockIdx.x * EPB;
     constexpr int NIT = (S + NT - 1) / NT;
-    Cons2 wres[NIT];
-    if (A.fuse) {   // resW of this thread's nodes: in flight across the barrier
+    constexpr int NL = 2 * N1D * NF;
+    double2 wres[NIT][2];
+    {
+      const double *rw = A.fuse_resW + kb * (Nq * 4);
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
+      for (int it = 0; it < NIT; ++it) {   // resW of this thread's nodes: in flight across the barrier
         const int n = tid + it * NT;
-        if (n < S && kb + n / Nq < M.K) wres[it] = load_cons(A.fuse_resW + (kb * Nq + n) * 4);
+        wres[it][0] = make_double2(0.0, 0.0); wres[it][1] = make_double2(0.0, 0.0);
+        if (A.fuse && n < S && (full || kb + n / Nq < M.K)) {
+          const double2 *q = reinterpret_cast<const double2 *>(rw + n * 4);
+          wres[it][0] = q[0]; wres[it][1] = q[1];
+        }
       }
     }
     __syncthreads();
+    double *out = A.rpre + kb * (Nq * 4);
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int n = tid + it * NT;
-      if (n >= S) break;
       const int e2 = n / Nq, node = n % Nq;
-      if (kb + e2 < M.K) {
-        const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
+      if (n < S && (full || kb + e2 < M.K)) {
+        const int p2 = e2 * Nq + T.posn[e2 & 3][node];
         double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
         double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
         if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
-          const Cons2 w = wres[it];
-          r[0] = A.fuse_a * w.rho + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
-          r[1] = A.fuse_a * w.m1 + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
-          r[2] = A.fuse_a * w.m2 + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
-          r[3] = A.fuse_a * w.E + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
+          r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
+          r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
+          r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
+          r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
         }
-        store4(A.rpre + ((kb + e2) * Nq + node) * 4, r);
+        store4(out + n * 4, r);
       }
     }
-    constexpr int NL = 2 * N1D * NF;
-    if (kb + EPB <= M.K) {
-      for (int n = tid; n < EPB * NL; n += NT) A.lpre[kb * NL + n] = lstage[n];
+    double *lout = A.lpre + kb * NL;
+    if (full && (EPB * NL) % 2 == 0) {   // 16-byte copies
+      const double2 *ls2 = reinterpret_cast<const double2 *>(lstage);
+      double2 *lo2 = reinterpret_cast<double2 *>(lout);
+      for (int n = tid; n < EPB * NL / 2; n += NT) lo2[n] = ls2[n];
     } else {
       for (int n = tid; n < EPB * NL; n += NT)
-        if (kb + n / NL < M.K) A.lpre[kb * NL + n] = lstage[n];
+        if (kb + n / NL < M.K) lout[n] = lstage[n];
     }
     return;
   }

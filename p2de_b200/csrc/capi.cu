@@ -254,7 +254,7 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
     for (int line = 0; line < N1D; ++line) {
       for (int a = 0; a < N1D; ++a)
         for (int b = 0; b < N1D; ++b)
-          T.SH[d][line][a][b] = g * S[node(d, line, a) + (size_t)node(d, line, b) * Nh];
+          T.SHt[d][a][b][line] = T.SH[d][line][a][b] = g * S[node(d, line, a) + (size_t)node(d, line, b) * Nh];
       for (int a = 0; a < N1D; ++a) {
         T.S0[d][line][a] = (a + 1 < N1D) ? g * S0[node(d, line, a + 1) + (size_t)node(d, line, a) * Nq] : 0.0;
         for (int b = 0; b < N1D; ++b)   // low-order operator must be nearest-neighbour

@@ -33,6 +33,7 @@ enum { MODE_SUBCELL = 0, MODE_ZHANGSHU = 1, MODE_LOW = 2, MODE_HIGH = 3 };
 template <int N1D>
 struct Tables2D {
   double SH[2][N1D][N1D][N1D];  // physical hybridized S: [d][line][a][b] = GJ_dd * Srsh_db[d][node(a), node(b)]
+  double SHt[2][N1D][N1D][N1D]; // the same as [d][a][b][line]: bank-conflict free when the lanes of a warp differ in `line`
   double S0[2][N1D][N1D];       // physical low-order S0 of pair (a+1, a): [d][line][a]
   double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
   double wq[N1D * N1D];

@@ -159,6 +159,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   //      16-byte loads) so that their latency is covered by the node phase
   Nbr nb[2];
   Cons2 UnbC[2];
+  int nbpos[2] = {-1, -1};
   {
     // Structured mesh, batch strictly inside the domain (the common case, CTA-uniform): the neighbours
     // are k -+ 1 / k -+ Kx, no boundary condition, and the partner face node follows from the LGL face
@@ -175,7 +176,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         // partner node: d=0: (N1D-1, line) of k-1 / (0, line) of k+1;  d=1: (line, N1D-1) of k-Kx / (line, 0) of k+Kx
         const int node = d == 0 ? (e ? 0 : N1D - 1) + line * N1D : line + (e ? 0 : N1D - 1) * N1D;
         const int dk = d == 0 ? (e ? 1 : -1) : (e ? M.Kx : -M.Kx);
-        UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
+        // an x-neighbour inside this batch is read from shared memory after the node phase (nbpos >= 0)
+        const bool in_batch = d == 0 && (e ? el + 1 < EPB : el > 0);
+        nbpos[e] = -1;
+        if (in_batch) nbpos[e] = (el + dk) * Nq;   // completed with the swizzle table once the tables are loaded
+        else UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
       }
     } else if (active) {
       int ix, iy;
@@ -249,6 +254,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     ConsR Unb[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
+      if (nbpos[e] >= 0) {   // x-neighbour of this batch: its state is in `nodes`
+        const int eln = e ? el + 1 : el - 1;
+        const double *o = nodes + nbpos[e] + T.posl[0][eln & 3][line][e ? 0 : N1D - 1];
+        UnbC[e].rho = o[0 * S]; UnbC[e].m1 = o[1 * S]; UnbC[e].m2 = o[2 * S]; UnbC[e].E = o[3 * S];
+      }
       Unb[e].rho = UnbC[e].rho; Unb[e].mn = d ? UnbC[e].m2 : UnbC[e].m1;
       Unb[e].mt = d ? UnbC[e].m1 : UnbC[e].m2; Unb[e].E = UnbC[e].E;
     }
@@ -350,7 +360,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 #else
           fS_rot(A.half_inv_gm1, q[i], q[j], F);
 #endif
-          double Sv = T.SH[d][line][i][j];
+          double Sv = T.SHt[d][i][j][line];
 #pragma unroll
           for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
         }

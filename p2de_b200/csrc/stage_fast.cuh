@@ -678,17 +678,34 @@ interface_fix_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant
   const long long k = (long long)blockIdx.x * EPB + el;
   const bool active = k < M.K;
   int any = 0;
+  // batch strictly inside a structured mesh (CTA-uniform): the partner of face node f is k -+ 1 / k -+ Kx
+  bool interior = false;
+  const long long kb = (long long)blockIdx.x * EPB;
+  if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {
+    const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
+    interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
+  }
   if (active) {
-    int ix, iy;
-    if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
-    else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
+    int ix = 0, iy = 0;
+    if (!interior) {
+      if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
+      else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
+    }
+    const double *lbase = A.lpre + kb * NL;
     for (int f = tl; f < Nfp; f += TPE) {
       const int F = f / N1D, line = f % N1D, d = F >> 1, e = F & 1;
       const int s = e ? N1D : 0;
       const int lidx = d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D);
-      const double lv = A.lpre[k * NL + lidx];
-      Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
-      const double lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
+      const double lv = lbase[el * NL + lidx];
+      double lP;
+      if (interior) {
+        const int sP = e ? 0 : N1D;   // the partner's opposite end face
+        const int dk = d == 0 ? (e ? 1 : -1) : (e ? M.Kx : -M.Kx);
+        lP = lbase[(long long)(el + dk) * NL + d * (N1D * NF) + (d == 0 ? sP + line * NF : line + sP * N1D)];
+      } else {
+        Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
+        lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
+      }
       const double lsym = jl_min(lv, lP);
       double *c = corr + (el * Nfp + f) * 4;
       if (lsym != lv) {   // the neighbour limits this face harder than this element did

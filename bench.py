@@ -272,11 +272,17 @@ def run_ours(args):
     for s2 in states[1:]:
         s2.close()
 
-    traffic = None
+    traffic, fp64 = None, None
     tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get("per_stage_total_bytes")
+            tj = json.load(f).get(args.workload, {})
+        traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
+    fp64_peak = None
+    ppath = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
+    if os.path.exists(ppath):
+        with open(ppath) as f:
+            fp64_peak = json.load(f)
     peak, peak_src = peaks()
     A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
     stage_total_ms = (stage_ms + upd_ms) / max(n_stage, 1)          # both kernels of one stage, device time
@@ -291,10 +297,22 @@ def run_ours(args):
                    "parallelism": f"dp{world} (y-stripes)" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes of one stage (both kernels) from one ncu --set full capture, profiles/r1_traffic.json",
+                     "traffic_note": "DRAM bytes per stage (stage kernel + update / interface-fix kernel, averaged over the 3 stages of a step) from one ncu --set full capture, profiles/r1_traffic.json",
                      "kernel": "stage_kernel + update_kernel (one RK stage)", "algorithmic_bytes_per_dof_update": A,
                      "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
                      "stage_kernel_share": stage_ms / max(stage_ms + upd_ms, 1e-30)},
+        # second view of the same stage: the stage kernel is bound by the FP64 CUDA-core pipe, not by HBM.
+        # flops per DOF-update counted by ncu (DFMA = 2), peak = DFMA micro-benchmark on this GPU type
+        # (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)
+        "roofline_fp64": ({"bound": "fp64", "unit": "TFLOP/s",
+                           "achieved": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3) / 1e12,
+                           "peak": fp64_peak["dfma_tflops"],
+                           "frac": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3) / 1e12 / fp64_peak["dfma_tflops"],
+                           "pipe_frac": fp64["lane_ops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3)
+                                        / (fp64_peak["dadd_per_clk_sm"] * fp64_peak["sms"] * fp64_peak["clock_mhz"] * 1e6),
+                           "kernel": "stage_kernel_fast", "flops_per_dof_update": fp64["flops_per_dof_update"],
+                           "source": "ncu thread-instruction counts (profiles/r1_traffic.json) and tools/fp64_peak.cu (profiles/r1_fp64_peak.json)"}
+                          if (fp64 and fp64_peak and n_stage) else None),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
                 "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others",

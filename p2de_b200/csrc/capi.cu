@@ -217,7 +217,10 @@ template <> Tables2D<3> &tables<3>(p2de_handle *h) { return h->t3; }
 template <> Tables2D<4> &tables<4>(p2de_handle *h) { return h->t4; }
 template <> Tables2D<5> &tables<5>(p2de_handle *h) { return h->t5; }
 
-template <int N1D> struct Launch { static constexpr int EPB = N1D == 5 ? 8 : P2DE_EPB; };   // N=4: 83 KB of smem at 16
+#ifndef P2DE_EPB5
+#define P2DE_EPB5 12   // N=4 (N1D=5): elements per CTA (120 threads, 3 CTAs/SM at 168 registers: measured best of 6..16)
+#endif
+template <int N1D> struct Launch { static constexpr int EPB = N1D == 5 ? P2DE_EPB5 : P2DE_EPB; };
 
 // Extract the per-line tables from the caller's operators and verify the structure this
 // kernel family relies on (tensor-product LGL collocation on a Cartesian mesh).

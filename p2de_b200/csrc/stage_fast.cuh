@@ -13,12 +13,16 @@
 //     interior face contributes nothing to f_H - f_L; only inflow/outflow faces do;
 //   * phases are ordered so that at most one 4-node accumulator set is live at a time.
 #pragma once
+#include <type_traits>
 #include "kernels2d.cuh"
 
 namespace p2de {
 
 #ifndef P2DE_FAST_MIN_BLOCKS
 #define P2DE_FAST_MIN_BLOCKS 4
+#endif
+#ifndef P2DE_FAST_MIN_BLOCKS5
+#define P2DE_FAST_MIN_BLOCKS5 3   // N=4 (N1D=5): 168 registers, no spills
 #endif
 
 // constants of logmean's series branch (:315-317) and its reciprocal: read as constant-bank operands
@@ -100,6 +104,18 @@ P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double
   F[0] = F1; F[1] = F1 * unavg + pa; F[2] = F1 * utavg; F[3] = f4aux * unavg;
 }
 
+// compile-time loop over the node pairs (j, i), j < i, j outer: indices are constants for every N1D, so the
+// per-node arrays of the caller stay in registers (a `#pragma unroll` nest is not unrolled at N1D = 5)
+template <int N1D, int J, int I>
+struct PairLoop {
+  template <class F>
+  static P2DE_DEV void run(F &&f) {
+    f(std::integral_constant<int, J>{}, std::integral_constant<int, I>{});
+    if constexpr (I + 1 < N1D) PairLoop<N1D, J, I + 1>::run(f);
+    else if constexpr (J + 2 < N1D) PairLoop<N1D, J + 1, J + 2>::run(f);
+  }
+};
+
 // shared-memory position of node (i, j) of CTA-local element el
 template <int N1D>
 __host__ __device__ __forceinline__ int node_pos(int el, int i, int j) {
@@ -122,7 +138,7 @@ constexpr int fast_smem_doubles_per_elem() {
 
 
 template <int N1D, int MODE, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? 5 : P2DE_FAST_MIN_BLOCKS))
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
 stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
                   const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
@@ -350,20 +366,14 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         q[a].rho = o[0 * S]; q[a].un = o[(4 + d) * S]; q[a].ut = o[(5 - d) * S];
         q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
       }
+      PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
+        constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
+        double F[4];
+        fS_rot(A.half_inv_gm1, q[i], q[j], F);
+        double Sv = T.SHt[d][i][j][line];
 #pragma unroll
-      for (int j = 0; j < N1D; ++j)
-#pragma unroll
-        for (int i = j + 1; i < N1D; ++i) {
-          double F[4];
-#ifdef P2DE_EXP_NOPAIRS
-          F[0] = q[i].rho + q[j].un; F[1] = q[i].ut; F[2] = q[j].beta; F[3] = q[i].rholog;
-#else
-          fS_rot(A.half_inv_gm1, q[i], q[j], F);
-#endif
-          double Sv = T.SHt[d][i][j][line];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
-        }
+        for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+      });
     }
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {

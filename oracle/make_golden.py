@@ -16,7 +16,11 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as P  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
-from p2de_b200 import SubcellLimiter, ZhangShuLimiter  # noqa: E402
+from p2de_b200 import (ESLimitedLowOrderPos, GaussCollocation, LaxFriedrichsOnProjectedVal,  # noqa: E402
+                       NodewiseScaledExtrapolation, SubcellLimiter, ZhangShuLimiter)
+
+GAUSS = dict(basis=GaussCollocation(), entropyproj_limiter=NodewiseScaledExtrapolation(),
+             rhs=ESLimitedLowOrderPos(LaxFriedrichsOnProjectedVal(), LaxFriedrichsOnProjectedVal()))
 
 CASES = {
     # test/test_smoke.jl:44-67: vortex, K=(5,5), T=2e-2, CFL=1, dt0=1e-2 -> 2 steps
@@ -24,7 +28,10 @@ CASES = {
        for N in (1, 2, 3, 4) for name, lim in (("subcell", SubcellLimiter()), ("zhangshu", ZhangShuLimiter()))},
     "dmr_N3_subcell": (lambda: P.dmr(N=3, K=(16, 4)), 5),
     "sedov_N2_zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 5),
+    # row 8f-1 (oracle only so far): the configuration of examples/2D/kelvin-helmholtz.jl:44-55
+    "kh_N3_gauss_nodewise_subcell": (lambda: P.kelvin_helmholtz(N=3, K=(6, 6), **GAUSS), 3),
 }
+ORACLE_ONLY = {"kh_N3_gauss_nodewise_subcell"}     # no GPU kernel yet (p2de_create: P2DE_ERR_UNSUPPORTED)
 
 
 def run_case(factory, nsteps):

@@ -21,6 +21,8 @@
 //   D2  1D `subcell_bound_limiter!` shadows `dim`/`bound` (subcell.jl:230-231); restated
 //       with the 2D routine as template, factor 2 instead of 4 (subcell.jl:232,239).
 //   D3  Julia `min`/`max` propagate NaN; jl_min/jl_max below do the same.
+//   D4  NodewiseScaledExtrapolation (filter.jl) is broken at HEAD by argument shadowing; restated from
+//       the evident intent (see compute_entropyproj_limiting_param).
 #include <algorithm>
 #include <array>
 #include <cmath>
@@ -404,6 +406,60 @@ struct Oracle : OracleBase {
         vt[Nq + i] = acc;
         ut[Nq + i] = ph.u_vfun(acc);
       }
+    }
+  }
+
+  // ------------------------------------------------------------------ filter.jl
+  // compute_entropyproj_limiting_param!(::GaussCollocation) :6-15 with calc_face_values! :26-41,
+  // solve_theta!(::NodewiseScaledExtrapolation) :48-58, update_limited_entropyproj_vars_on_face_node!
+  // :110-130, check_bound_on_face_node :84-98 and bisection (math/nonlinear_solvers.jl:3-20).
+  // Deviation D4: HEAD calls `equation(solver)` with `equation` shadowed by the method's own argument
+  // (filter.jl:26,35,38) and the LobattoCollocation method references undefined names (:1-3); the
+  // evident intent is restated: theta_local = 1 for Lobatto, the bisection below for Gauss.
+  void compute_entropyproj_limiting_param(int nstage) {
+    const double eps = cfg.POSTOL, zeta = cfg.zeta, eta = cfg.eta;
+    const size_t off = (size_t)Nfp * K * (size_t)(nstage - 1);
+    for (size_t i = 0; i < (size_t)Nfp * K; ++i) theta_local[off + i] = 1.0;     // :18-20
+    if (cfg.basis != P2DE_BASIS_GAUSS) return;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < K; ++k) {
+      const Vec *Uq_k = &Uq[(size_t)Nq * k];
+      Vec *vq_k = &vq[(size_t)Nq * k];
+      for (int i = 0; i < Nq; ++i) vq_k[i] = ph.v_ufun(Uq_k[i]);
+      double thsum = 0.0;
+      for (int i = 0; i < Nfp; ++i) {
+        Vec Ufi{}, VUfi{};                                                        // mul!(Uf, Vf, Uq), mul!(VUf, Vf, vq)
+        for (int j = 0; j < Nq; ++j) {
+          double w = Vf[i + (size_t)j * Nfp];
+          for (int c = 0; c < Nc; ++c) { Ufi[c] += w * Uq_k[j][c]; VUfi[c] += w * vq_k[j][c]; }
+        }
+        const double rhoefi = ph.rhoe_ufun(Ufi);
+        auto f = [&](double th) {
+          Vec vt{};
+          for (int j = 0; j < Nq; ++j) {
+            double w = th * Vf[i + (size_t)j * Nfp] + (1 - th) * Vf_low[i + (size_t)j * Nfp];
+            for (int c = 0; c < Nc; ++c) vt[c] += w * vq_k[j][c];
+          }
+          if (!(vt[Nc - 1] < -eps)) return false;                                 // :124
+          Vec ut = ph.u_vfun(vt);
+          double v3 = vt[Nc - 1], rho = ut[0], rhoe = ph.rhoe_ufun(ut);
+          return v3 < jl_min(zeta * VUfi[Nc - 1], -eps) && rho > jl_max((1 - eta) * Ufi[0], eps) &&
+                 rho < (1 + eta) * Ufi[0] && rhoe > jl_max((1 - eta) * rhoefi, eps) && rhoe < (1 + eta) * rhoefi;
+        };
+        double th;
+        if (f(1.0)) th = 1.0;
+        else {
+          double xv = 0.0, xi = 1.0;
+          for (int it = 0; it <= 20; ++it) {
+            double xn = 0.5 * (xv + xi);
+            if (f(xn)) xv = xn; else xi = xn;
+          }
+          th = xv;
+        }
+        theta_local[off + i + (size_t)Nfp * k] = th;
+        thsum += th;
+      }
+      theta[k + K * (size_t)(nstage - 1)] = thsum / Nfp;                          // :57
     }
   }
 
@@ -1112,6 +1168,7 @@ struct Oracle : OracleBase {
   // ------------------------------------------------------------------ rhs.jl:5-55
   double rhs(double t, double dt_in, int nstage) override {
     double dt = dt_in;
+    if (cfg.proj_limiter == P2DE_PROJLIM_NODEWISE) compute_entropyproj_limiting_param(nstage);   // init_rhs! :15-19
     switch (cfg.rhs_type) {
       case P2DE_RHS_LOW_ORDER_POSITIVITY:
         dt = rhs_low_graph_visc(t, dt_in, nstage, true);
@@ -1219,7 +1276,6 @@ void *oracle_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     g_err = "cell-entropy bounds are not restated yet (SURVEY.md §8f-2)";
     return nullptr;
   }
-  if (cfg->proj_limiter == P2DE_PROJLIM_NODEWISE) { g_err = "NodewiseScaledExtrapolation is not restated yet (SURVEY.md §8f-1)"; return nullptr; }
   try {
     if (cfg->dim == 1) return static_cast<OracleBase *>(new Oracle<1>(*cfg, *ops, *geom, *bc));
     return static_cast<OracleBase *>(new Oracle<2>(*cfg, *ops, *geom, *bc));

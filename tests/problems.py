@@ -15,7 +15,7 @@ from p2de_b200 import (BCData, CompressibleEulerIdealGas, ESLimitedLowOrderPos, 
 
 
 def make_param(N, K, xL, xR, *, limiter=None, rhs=None, T=1.0, CFL=0.5, dt0=1e-2, t0=0.0, gamma=1.4,
-               zeta=0.1, eta=0.5, basis=None, dim=2):
+               zeta=0.1, eta=0.5, basis=None, dim=2, entropyproj_limiter=None):
     return Param(N=N, K=K, xL=xL, xR=xR,
                  global_constants=GlobalConstant(POSTOL=1e-14, ZEROTOL=5e-16),
                  timestepping_param=TimesteppingParameter(T=T, CFL=CFL, dt0=dt0, t0=t0),
@@ -24,7 +24,7 @@ def make_param(N, K, xL, xR, *, limiter=None, rhs=None, T=1.0, CFL=0.5, dt0=1e-2
                  equation=CompressibleEulerIdealGas(dim, gamma),
                  rhs=rhs if rhs is not None else ESLimitedLowOrderPos(LaxFriedrichsOnNodalVal(), LaxFriedrichsOnProjectedVal()),
                  approximation_basis=basis if basis is not None else LobattoCollocation(),
-                 entropyproj_limiter=NoEntropyProjectionLimiter(),
+                 entropyproj_limiter=entropyproj_limiter if entropyproj_limiter is not None else NoEntropyProjectionLimiter(),
                  rhs_limiter=limiter if limiter is not None else SubcellLimiter(bound=PositivityBound()))
 
 

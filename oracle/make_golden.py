@@ -28,10 +28,10 @@ CASES = {
        for N in (1, 2, 3, 4) for name, lim in (("subcell", SubcellLimiter()), ("zhangshu", ZhangShuLimiter()))},
     "dmr_N3_subcell": (lambda: P.dmr(N=3, K=(16, 4)), 5),
     "sedov_N2_zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 5),
-    # row 8f-1 (oracle only so far): the configuration of examples/2D/kelvin-helmholtz.jl:44-55
+    # row 8f-1: the configuration of examples/2D/kelvin-helmholtz.jl:44-55
     "kh_N3_gauss_nodewise_subcell": (lambda: P.kelvin_helmholtz(N=3, K=(6, 6), **GAUSS), 3),
 }
-ORACLE_ONLY = {"kh_N3_gauss_nodewise_subcell"}     # no GPU kernel yet (p2de_create: P2DE_ERR_UNSUPPORTED)
+ORACLE_ONLY = set()     # cases without a GPU kernel (none at present)
 
 
 def run_case(factory, nsteps):

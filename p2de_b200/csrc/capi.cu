@@ -18,6 +18,7 @@
 #include "../../include/p2de_b200.h"
 #include "kernels2d.cuh"
 #include "stage_fast.cuh"
+#include "gauss.cuh"
 #include "kernels1d.cuh"
 
 using namespace p2de;
@@ -89,6 +90,10 @@ struct p2de_handle {
   long long K = 0;
   int mode = 0;
   bool fast = false;   // default flux configuration -> FAST kernel variant (kernels2d.cuh)
+  bool gauss = false;     // 2D GaussCollocation: entropy projection kernel + generic stage kernel
+  bool nodewise = false;  // NodewiseScaledExtrapolation
+  double *utf = nullptr;          // [K][Nfp][4] entropy-projected face states (halo rows like the state)
+  double *theta_local_dev = nullptr, *theta_dev = nullptr;   // [Ns][K][Nfp], [Ns][K]
   int device = 0;
   cudaStream_t stream = nullptr;
   std::string err;
@@ -237,12 +242,22 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
     if ((int)o->fq2q[f] - 1 != expect) return fail(h, P2DE_ERR_UNSUPPORTED, "fq2q[%d]=%lld is not the LGL tensor-product face map", f, (long long)o->fq2q[f]);
     T.fq2q[f] = expect;
   }
-  // Vf must be the 0/1 gather (collocated face nodes)
+  // Vf: the 0/1 gather of collocated face nodes (Lobatto), or an extrapolation along the face node's own grid
+  // line (Gauss); Vf_low must be the 0/1 gather fq2q in both cases (init.jl:178-185,324-336)
   for (int f = 0; f < Nfp; ++f)
     for (int j = 0; j < Nq; ++j) {
+      const int F = f / N1D, a = f % N1D;
+      const bool on_line = F < 2 ? (j / N1D == a) : (j % N1D == a);
       double v = o->Vf[f + (size_t)j * Nfp], e = (j == T.fq2q[f]) ? 1.0 : 0.0;
-      if (std::fabs(v - e) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "Vf is not a 0/1 gather: only Lobatto collocation has a GPU kernel in this build");
+      if (!h->gauss && std::fabs(v - e) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "Vf is not a 0/1 gather but the basis is not GaussCollocation");
+      if (h->gauss && !on_line && v != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "Vf couples a face node with nodes off its grid line");
+      if (h->gauss && (!o->Vf_low || std::fabs(o->Vf_low[f + (size_t)j * Nfp] - e) > 1e-13)) return fail(h, P2DE_ERR_UNSUPPORTED, "Vf_low is not the nearest-node gather");
     }
+  for (int d = 0; d < 2; ++d)
+    for (int line = 0; line < N1D; ++line)
+      for (int e = 0; e < 2; ++e)
+        for (int a = 0; a < N1D; ++a)
+          T.VfL[d][line][e][a] = o->Vf[((2 * d + e) * N1D + line) + (size_t)node(d, line, a) * Nfp];
   for (int d = 0; d < 2; ++d) {
     const double *S = o->Srsh_db[d], *S0 = o->Srs0[d];
     const double g = GJ[d == 0 ? 0 : 3];
@@ -266,6 +281,11 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
       }
       for (int e = 0; e < 2; ++e) {
         int f = (2 * d + e) * N1D + line;
+        for (int a = 0; a < N1D; ++a) {   // hybridized block -B E (face row, volume column) and its transpose E^T B
+          T.SHf[d][line][e][a] = g * S[(Nq + f) + (size_t)node(d, line, a) * Nh];
+          if (S[(Nq + f) + (size_t)node(d, line, a) * Nh] != -S[node(d, line, a) + (size_t)(Nq + f) * Nh])
+            return fail(h, P2DE_ERR_UNSUPPORTED, "Srsh_db is not skew-symmetric in its face-volume block");
+        }
         T.Bf[d][line][e] = g * o->Brs[d][f];
         if (o->Brs[1 - d][f] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "face %d has a tangential boundary weight", f);
       }
@@ -293,7 +313,8 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
   }
   for (int f = 0; f < Nfp; ++f) {
     T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
-    if (std::fabs(T.minvf[f] * o->wq[T.fq2q[f]] - 1.0) > 1e-13) return fail(h, P2DE_ERR_UNSUPPORTED, "MinvVfT is not the 1/wq-scaled face gather");
+    for (int i = 0; i < Nq; ++i)   // M^-1 Vf^T = (1/wq) Vf^T (LGL: the 1/wq-scaled face gather)
+      if (std::fabs(o->MinvVfT[i + (size_t)f * Nq] * o->wq[i] - o->Vf[f + (size_t)i * Nfp]) > 1e-12) return fail(h, P2DE_ERR_UNSUPPORTED, "MinvVfT is not (1/wq) Vf^T");
   }
   return 0;
 }
@@ -557,6 +578,8 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.roundtrip = h->cfg.lgl_projection_roundtrip;
   A.half_inv_gm1 = 1.0 / (2.0 * (h->cfg.gamma - 1.0));
   A.tab_dev = h->tab_dev;
+  A.gauss = h->gauss ? 1 : 0; A.utf = h->utf;
+  A.theta_local = (h->gauss && h->nodewise) ? h->theta_local_dev + (size_t)h->K * h->Nfp * (nstage - 1) : nullptr;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   return A;
 }
@@ -715,6 +738,33 @@ int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *ge
   return 0;
 }
 
+template <int N1D>
+int launch_project_n(p2de_handle *h, const double *Uin, int nstage) {
+  constexpr int EPB = 8;
+  ProjArgs P{};
+  P.Uq = Uin; P.utf = h->utf;
+  P.theta_local = h->nodewise ? h->theta_local_dev + (size_t)h->K * h->Nfp * (nstage - 1) : nullptr;
+  P.theta = h->nodewise ? h->theta_dev + (size_t)h->K * (nstage - 1) : nullptr;
+  P.gamma = h->cfg.gamma; P.POSTOL = h->cfg.POSTOL; P.zeta = h->cfg.zeta; P.eta = h->cfg.eta;
+  P.nodewise = h->nodewise ? 1 : 0;
+  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  prof_begin(h, 2);
+  gauss_project_kernel<N1D, EPB><<<grid, EPB * 2 * N1D, 0, h->stream>>>(P, h->topo, tables<N1D>(h));
+  prof_end(h);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+int launch_project(p2de_handle *h, const double *Uin, int nstage) {
+  switch (h->N1D) {
+    case 2: return launch_project_n<2>(h, Uin, nstage);
+    case 3: return launch_project_n<3>(h, Uin, nstage);
+    case 4: return launch_project_n<4>(h, Uin, nstage);
+    case 5: return launch_project_n<5>(h, Uin, nstage);
+  }
+  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+
 // one stage: stage_kernel + update_kernel.  `Uin` is the stage input; if `Uout` != nullptr the
 // SSP combine Uout = a*resW + b*(Uin + dt*rhsU) is fused into the update kernel.
 int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt_host, bool limiter_dt_dev,
@@ -737,6 +787,10 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   }
   // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
   if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
+  if (h->gauss) {   // entropy projection (+ NodewiseScaledExtrapolation) to the face nodes; its halo rows travel like E1
+    if (int rc = launch_project(h, Uin, nstage)) return rc;
+    if (int rc = exchange_rows(h, h->utf, (size_t)h->cfg.Kx * h->Nfp * 4)) return rc;
+  }
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
   // stages 2/3 of the FAST subcell path: the limiter's dt is the step's dt, so the stage kernel can
   // already form the SSP combine of the un-corrected rhs and the update kernel only adds corrections
@@ -788,8 +842,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
          : (cfg->Nq != N1D * N1D || cfg->Nfp != 4 * N1D || cfg->Nh != cfg->Nq + cfg->Nfp || cfg->Np != cfg->Nq))
     return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d %s", cfg->N, d1 ? "line" : "quad");
   if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
-  if (!d1 && cfg->basis != P2DE_BASIS_LOBATTO) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "2D GaussCollocation has no GPU kernel in this build (SURVEY.md 8f-1)");
-  if (cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation has no GPU kernel in this build (SURVEY.md 8f-1)");
+  if (d1 && cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation: 2D only in this build (SURVEY.md 8f-1)");
   if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE && (d1 || !ops->VDM_inv))
     return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture: 2D only and needs ops.VDM_inv");
   int mode;
@@ -823,6 +876,9 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   }
   if (mode == MODE_SUBCELL) h->entropy_bound = cfg->bound == P2DE_BOUND_POS_MIN_ENTROPY ? 1 : (cfg->bound == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY ? 2 : 0);
   if (h->entropy_bound || cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) h->fast = false;   // generic kernel has these features
+  h->gauss = !d1 && cfg->basis == P2DE_BASIS_GAUSS;
+  h->nodewise = cfg->proj_limiter == P2DE_PROJLIM_NODEWISE;
+  if (h->gauss) h->fast = false;
   h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = d1 ? 3 : 4; h->Nd = d1 ? 1 : 2; h->K = cfg->K; h->mode = mode;
   h->dim = cfg->dim;
   h->nLloc = d1 ? 2 * N1D : 2 * N1D * (N1D + 1);   // State.jl:21: zeros(Nq + N1D, Nd, K, Ns); 1D uses the first Nq+1
@@ -882,6 +938,15 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return bail(rc);
     cudaMemset(h->rhsH_diag, 0, nU * sizeof(double)); cudaMemset(h->rhsL_diag, 0, nU * sizeof(double));
   }
+  if (h->gauss || h->nodewise) {
+    const size_t nth = (size_t)h->K * h->Nfp * h->Ns, nt = (size_t)h->K * h->Ns;
+    if ((rc = dev_alloc(h, &h->theta_local_dev, nth)) || (rc = dev_alloc(h, &h->theta_dev, nt))) return bail(rc);
+    std::vector<double> ones(nth, 1.0);   // Lobatto + Nodewise: theta_local = 1 (filter.jl:18-20), theta stays 0 as in the reference
+    if (cudaMemcpy(h->theta_local_dev, ones.data(), nth * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memcpy theta"));
+    cudaMemset(h->theta_dev, 0, nt * sizeof(double));
+    if (!h->nodewise) cudaMemset(h->theta_local_dev, 0, nth * sizeof(double));   // NoEntropyProjectionLimiter never writes theta_local
+  }
+  if (h->gauss && (rc = dev_alloc_halo(h, &h->utf, (size_t)h->K * h->Nfp * 4, (size_t)cfg->Kx * h->Nfp * 4))) return bail(rc);
   if ((rc = dev_alloc(h, &h->dt_bits, 1)) || (rc = dev_alloc(h, &h->smin_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
   cudaMemset(h->smin_bits, 0, sizeof(unsigned long long));   // s_modified_min starts at 0.0 (State.jl:180)
   if (ops->VDM_inv) {
@@ -1036,7 +1101,9 @@ int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
     default: return fail(h, P2DE_ERR_ARG, "unknown field %d", field);
   }
   if (n < cnt) return fail(h, P2DE_ERR_ARG, "destination too small: %lld < %lld", (long long)n, (long long)cnt);
-  if (field == P2DE_FIELD_THETA || field == P2DE_FIELD_THETA_LOCAL) { std::memset(dst, 0, cnt * sizeof(double)); return P2DE_OK; }
+  if (field == P2DE_FIELD_THETA && h->theta_dev) src = h->theta_dev;
+  else if (field == P2DE_FIELD_THETA_LOCAL && h->theta_local_dev) src = h->theta_local_dev;
+  else if (field == P2DE_FIELD_THETA || field == P2DE_FIELD_THETA_LOCAL) { std::memset(dst, 0, cnt * sizeof(double)); return P2DE_OK; }
   if (!src) return fail(h, P2DE_ERR_STATE, "field %d is not kept (keep_diagnostics / call p2de_rhs first)", field);
   CU(h, cudaMemcpyAsync(dst, src, cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));

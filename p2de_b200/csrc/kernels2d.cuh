@@ -45,6 +45,9 @@ struct Tables2D {
   double minv[N1D * N1D];       // MinvVhT[i, i]
   double minvf[4 * N1D];        // MinvVfT[fq2q[f], f]
   int fq2q[4 * N1D];            // 0-based
+  // Gauss collocation (face nodes are not volume nodes): per line and line end e
+  double VfL[2][N1D][2][N1D];   // Vf[f, node(a)]: extrapolation weights of the line's nodes to its end face node
+  double SHf[2][N1D][2][N1D];   // physical hybridized S, face row x volume column: GJ_dd * Srsh_db[d][Nq + f, node(a)]
 };
 
 struct MeshTopo {
@@ -85,6 +88,10 @@ struct StageArgs {
   double fuse_a, fuse_b;
   const double *fuse_resW;
   const double *tab_dev;             // Tables2D<N1D> in global memory (same bytes as the kernel parameter)
+  // generic kernel, Gauss collocation: entropy-projected face states u_tilde_f [K][Nfp][4] and the
+  // projection-limiting parameters theta_local [K][Nfp] of this stage, both written by gauss_project_kernel
+  int gauss;
+  const double *utf, *theta_local;
 };
 
 struct UpdateArgs {
@@ -358,7 +365,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       for (int e = 0; e < 2; ++e) {
         Ut[e] = U[e ? N1D - 1 : 0];
         Utnb[e] = Unb[e];
-        if (A.roundtrip) {
+        if (A.gauss) {   // rhs.jl:113-133: u(v_tilde) at the face nodes, mine and my neighbour's
+          Ut[e] = load_cons(A.utf + (k * (4 * N1D) + (2 * d + e) * N1D + line) * 4);
+          Utnb[e] = load_cons(A.utf + (nb[e].kP * (4 * N1D) + nb[e].fP) * 4);
+        } else if (A.roundtrip) {
           Ut[e] = entropy_roundtrip(gamma, gm1, Ut[e]);
           Utnb[e] = entropy_roundtrip(gamma, gm1, Utnb[e]);
         }
@@ -426,14 +436,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer).
       //      GH = -(QF1 + B F*) (LGL: M^-1 Vh^T is a scaled 0/1 gather; the hybridized face-volume
       //      pairs cancel identically and are not formed)
-      if (FAST || A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
-        Prim2 q[N1D];
+      Prim2 q[N1D];
 #pragma unroll
-        for (int a = 0; a < N1D; ++a) {
-          const double *o = nodes + nbase + (d == 0 ? a + line * N1D : line + a * N1D);
-          q[a].rho = U[a].rho; q[a].u = uu[a]; q[a].v = vv[a];
-          q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
-        }
+      for (int a = 0; a < N1D; ++a) {
+        const double *o = nodes + nbase + (d == 0 ? a + line * N1D : line + a * N1D);
+        q[a].rho = U[a].rho; q[a].u = uu[a]; q[a].v = vv[a];
+        q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
+      }
+      if (FAST || A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
 #pragma unroll
         for (int j = 0; j < N1D; ++j)
 #pragma unroll
@@ -453,6 +463,33 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
             for (int c = 0; c < 4; ++c) { double Sf = Sv * (0.5 * (fl[i][c] + fl[j][c])); GH[i][c] -= Sf; GH[j][c] += Sf; }
           }
+      }
+      double GHf[2][4];   // -QF1 at the two hybridized face rows of this line (Gauss)
+#pragma unroll
+      for (int e = 0; e < 2; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) GHf[e][c] = 0.0;
+      if (!FAST && A.gauss) {
+        // hybridized face-volume pairs of Srsh_db = [Q - Q^T, E^T B; -B E, 0] (init.jl:148-155): face row i > volume
+        // column j, QF1[i] += S_ij fS(u_i, u_j), QF1[j] -= the same (flux_differencing.jl:164-211)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          Prim2 pf = prim_of(gm1, Ut[e]);
+          double ff[4];
+          flux_dir(gm1, Ut[e], d, ff);
+#pragma unroll
+          for (int a = 0; a < N1D; ++a) {
+            double F[4];
+            if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) fS_dir(gm1, pf, q[a], d, F);
+            else {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) F[c] = 0.5 * (ff[c] + fl[a][c]);
+            }
+            double Sv = T.SHf[d][line][e][a];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; GHf[e][c] -= Sf; GH[a][c] += Sf; }
+          }
+        }
       }
       if (!FAST) {
         // surface, flux_differencing.jl:90-151,223-272
@@ -479,8 +516,24 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
         }
       }
+      if (!FAST && A.gauss) {
+        // assemble_rhs! (flux_differencing.jl:274-361): M^-1 Vh^T = (1/wq) [I Vf_new^T], Vf_new = theta Vf + (1 - theta) Vf_low
+        // per face node (:288-319); the 1/(wq J) factor is applied below with rwJ
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { GH[0][c] -= BFH[0][c]; GH[N1D - 1][c] -= BFH[1][c]; }
+        for (int e = 0; e < 2; ++e) {
+          const int ae = e ? N1D - 1 : 0;
+          const double th = A.theta_local ? A.theta_local[k * (4 * N1D) + (2 * d + e) * N1D + line] : 1.0;
+#pragma unroll
+          for (int a = 0; a < N1D; ++a) {
+            const double w = th * T.VfL[d][line][e][a] + (1 - th) * (a == ae ? 1.0 : 0.0);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) GH[a][c] += w * (GHf[e][c] - BFH[e][c]);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { GH[0][c] -= BFH[0][c]; GH[N1D - 1][c] -= BFH[1][c]; }
+      }
     }
 
     // ---- publish this line's share of rhsL / rhsH / lambda for the node-wise combination

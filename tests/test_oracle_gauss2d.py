@@ -2,8 +2,7 @@
 (src/dg/filter.jl, rhs.jl:113-133, flux_differencing.jl:288-328, low_order_graph_viscosity.jl:249-327),
 the configuration of every shipped 2D example (e.g. examples/2D/kelvin-helmholtz.jl:44-55).  The
 reference pins no numbers for it (and the path is broken at HEAD, oracle deviation D4), so the
-restatement is held to the invariants of the scheme.  The GPU has no kernel for this row yet:
-p2de_create returns P2DE_ERR_UNSUPPORTED for it."""
+restatement is held to the invariants of the scheme.  GPU parity for the same row: tests/test_gpu_gauss.py."""
 import numpy as np
 import pytest
 

@@ -17,7 +17,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as P  # noqa: E402
 from oracle.oracle import Oracle  # noqa: E402
 from p2de_b200 import (ESLimitedLowOrderPos, GaussCollocation, LaxFriedrichsOnProjectedVal,  # noqa: E402
-                       NodewiseScaledExtrapolation, SubcellLimiter, ZhangShuLimiter)
+                       NodewiseScaledExtrapolation, PositivityAndRelaxedCellEntropyBound, SubcellLimiter,
+                       TVDAndCellEntropyBound, ZhangShuLimiter)
 
 GAUSS = dict(basis=GaussCollocation(), entropyproj_limiter=NodewiseScaledExtrapolation(),
              rhs=ESLimitedLowOrderPos(LaxFriedrichsOnProjectedVal(), LaxFriedrichsOnProjectedVal()))
@@ -30,6 +31,9 @@ CASES = {
     "sedov_N2_zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 5),
     # row 8f-1: the configuration of examples/2D/kelvin-helmholtz.jl:44-55
     "kh_N3_gauss_nodewise_subcell": (lambda: P.kelvin_helmholtz(N=3, K=(6, 6), **GAUSS), 3),
+    # row 8f-2: TVD and cell-entropy bounds on plateau-free data (tests/test_gpu_bounds.py explains why not the vortex)
+    "wave_N3_tvd_cellentropy": (lambda: P.wave2d(N=3, limiter=SubcellLimiter(bound=TVDAndCellEntropyBound())), 3),
+    "wave_N2_relaxed_cellentropy": (lambda: P.wave2d(N=2, limiter=SubcellLimiter(bound=PositivityAndRelaxedCellEntropyBound(beta=0.5))), 3),
 }
 ORACLE_ONLY = set()     # cases without a GPU kernel (none at present)
 
@@ -60,6 +64,9 @@ def run_case(factory, nsteps):
 
 if __name__ == "__main__":
     outdir = os.path.join(ROOT, "tests", "golden")
+    only = set(sys.argv[1:])
     for name, (factory, nsteps) in CASES.items():
+        if only and name not in only:
+            continue
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **run_case(factory, nsteps))
         print("wrote", name)

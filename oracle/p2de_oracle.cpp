@@ -233,6 +233,10 @@ struct Oracle : OracleBase {
   std::vector<double> blending_factor, smooth_factor, lbound_s_modified, s_modified, rhoL, lbound_rho, ubound_rho;
   double s_modified_min = 0;
   std::vector<Vec> f_bar_H[Nd], f_bar_L[Nd], f_bar_lim[Nd];
+  // cell-entropy bounds (State.jl:150-160): vf, psif [Nfp,K]; dvdf[d] [Nq-N1D,K] (1D: [Nq-1,K]); sum_Bpsi, sum_dvfbarL [K]
+  std::vector<Vec> vf_es;
+  std::vector<Nrm> psif_es, sum_Bpsi, sum_dvfbarL;
+  std::vector<double> dvdf[Nd];
 
   double &Lloc(int idx, int d, int64_t k, int s) {
     return L_local[idx + (int64_t)(Nq + N1D) * (d + Nd * (k + K * (int64_t)s))];
@@ -344,7 +348,9 @@ struct Oracle : OracleBase {
       f_bar_H[d].assign((size_t)(Nq + N1D) * K, z);
       f_bar_L[d].assign((size_t)(Nq + N1D) * K, z);
       f_bar_lim[d].assign((size_t)(Nq + N1D) * K, z);
+      dvdf[d].assign((size_t)Nq * K, 0.0);
     }
+    vf_es.assign(nf, z); psif_es.assign(nf, Nrm{}); sum_Bpsi.assign(K, Nrm{}); sum_dvfbarL.assign(K, Nrm{});
     // theta defaults: NoEntropyProjectionLimiter never writes theta; reference leaves zeros.
   }
 
@@ -1077,6 +1083,186 @@ struct Oracle : OracleBase {
         for (int i = 0; i < Nq + N1D; ++i) { double &v = Lloc(i, d, k, s); v = jl_min(v, l_shock); }
     }
   }
+
+  // ------------------------------------------------------------------ subcell.jl:458-823 enforce_ES_subcell!
+  bool bound_has_cell_entropy() const {
+    return cfg.bound == P2DE_BOUND_POS_CELL_ENTROPY || cfg.bound == P2DE_BOUND_POS_RELAXED_CELL_ENTROPY ||
+           cfg.bound == P2DE_BOUND_TVD_CELL_ENTROPY || cfg.bound == P2DE_BOUND_TVD_RELAXED_CELL_ENTROPY;
+  }
+  // :709-716 rhs_es
+  double rhs_es(double sBpsi, double sdvfL, double epsk) const {
+    if (cfg.bound == P2DE_BOUND_POS_CELL_ENTROPY || cfg.bound == P2DE_BOUND_TVD_CELL_ENTROPY) return sBpsi - sdvfL;
+    return (1 - cfg.bound_beta * epsk) * (sBpsi - sdvfL);
+  }
+  // math/compressible_Navier_Stokes.jl:124-132 psi_ufun
+  Nrm psi_ufun(const Vec &U) const {
+    Nrm r;
+    for (int d = 0; d < DIM; ++d) r[d] = (ph.gamma - 1.0) * U[1 + d];
+    return r;
+  }
+  static double dot(const Vec &a, const Vec &b) {   // sum(@. dv * f): left to right
+    double s = 0.0;
+    for (int c = 0; c < Nc; ++c) s += a[c] * b[c];
+    return s;
+  }
+  // :466-565 initialize_ES_subcell_limiting!
+  void initialize_ES_subcell_limiting() {
+    const int N1Dp1 = N1D + 1, N1Dm1 = N1D - 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < K; ++k) {
+      for (int i = 0; i < Nq; ++i) vq[i + (size_t)Nq * k] = ph.v_ufun(Uq[i + (size_t)Nq * k]);
+      Nrm sB{};
+      for (int i = 0; i < Nfp; ++i) {
+        const Vec &uf = Uq[fq2q[i] + (size_t)Nq * k];
+        vf_es[i + (size_t)Nfp * k] = ph.v_ufun(uf);
+        psif_es[i + (size_t)Nfp * k] = psi_ufun(uf);
+        auto Bxy = Bx(i, k);
+        for (int d = 0; d < DIM; ++d) sB[d] += Bxy[d] * psif_es[i + (size_t)Nfp * k][d];
+      }
+      sum_Bpsi[k] = sB;
+      const Vec *vq_k = &vq[(size_t)Nq * k];
+      size_t fb = (size_t)(Nq + N1D) * k;
+      Nrm sdv{};
+      if constexpr (DIM == 1) {
+        double acc = 0.0;
+        for (int si = 1; si <= cfg.N; ++si) {
+          const Vec &fL = f_bar_L[0][fb + si], &fH = f_bar_H[0][fb + si];
+          Vec df, dv;
+          for (int c = 0; c < Nc; ++c) { df[c] = fH[c] - fL[c]; dv[c] = vq_k[si - 1][c] - vq_k[si][c]; }
+          dvdf[0][(si - 1) + (size_t)Nq * k] = dot(dv, df);
+          acc += dot(dv, fL);
+        }
+        sdv[0] = acc;
+      } else {
+        double accx = 0.0, accy = 0.0;
+        for (int sj = 0; sj < N1D; ++sj)
+          for (int si = 1; si < N1D; ++si) {
+            const Vec &fL = f_bar_L[0][fb + si + sj * N1Dp1], &fH = f_bar_H[0][fb + si + sj * N1Dp1];
+            Vec df, dv;
+            for (int c = 0; c < Nc; ++c) { df[c] = fH[c] - fL[c]; dv[c] = vq_k[(si - 1) + sj * N1D][c] - vq_k[si + sj * N1D][c]; }
+            dvdf[0][(si - 1) + sj * N1Dm1 + (size_t)Nq * k] = dot(dv, df);
+            accx += dot(dv, fL);
+          }
+        for (int si = 0; si < N1D; ++si)
+          for (int sj = 1; sj < N1D; ++sj) {
+            const Vec &fL = f_bar_L[1][fb + si + sj * N1D], &fH = f_bar_H[1][fb + si + sj * N1D];
+            Vec df, dv;
+            for (int c = 0; c < Nc; ++c) { df[c] = fH[c] - fL[c]; dv[c] = vq_k[si + (sj - 1) * N1D][c] - vq_k[si + sj * N1D][c]; }
+            dvdf[1][si + (sj - 1) * N1D + (size_t)Nq * k] = dot(dv, df);
+            accy += dot(dv, fL);
+          }
+        sdv[0] = accx; sdv[1] = accy;
+      }
+      sum_dvfbarL[k] = sdv;
+    }
+  }
+  // Base.isless on Float64 (NaN largest, -0.0 < 0.0) and the reverse lexicographic order of
+  // sort!(::Vector{Tuple{Float64,Int}}, alg=QuickSort, rev=true) (subcell.jl:607,673,703): all tuples are
+  // distinct, so the sorted order does not depend on the algorithm
+  static bool jl_isless(double a, double b) {
+    if (std::isnan(a)) return false;
+    if (std::isnan(b)) return true;
+    if (a == b) return std::signbit(a) && !std::signbit(b);
+    return a < b;
+  }
+  // :568-707 enforce_ES_subcell_volume!: one direction of one element.  `lidx(i)` maps the 0-based dvdf index to
+  // the L_local index of the same subcell face.
+  // `ysum`: the reference accumulates the y estimate with si outer, sj inner (:641-646), not in index order.
+  template <class F>
+  void es_volume_greedy(const double *dv, int n, F lidx, int d, int64_t k, int s, double sBpsi, double sdvfL, double epsk, bool ysum = false) {
+    double sum_poslim = 0.0;
+    if (!ysum) for (int i = 0; i < n; ++i) sum_poslim += Lloc(lidx(i), d, k, s) * dv[i];
+    else
+      for (int si = 0; si < N1D; ++si)
+        for (int sj = 0; sj < N1D - 1; ++sj) { int i = si + sj * N1D; sum_poslim += Lloc(lidx(i), d, k, s) * dv[i]; }
+    const double rhs = rhs_es(sBpsi, sdvfL, epsk);
+    const double est = sum_poslim - rhs;
+    const double tol = jl_max(0.0, sdvfL - sBpsi);
+    if (!(est > tol)) return;
+    std::vector<std::pair<double, int>> order(n);
+    for (int i = 0; i < n; ++i) order[i] = {dv[i], i};
+    std::sort(order.begin(), order.end(), [](const std::pair<double, int> &a, const std::pair<double, int> &b) {
+      // descending: a before b iff isless(b, a) on tuples
+      if (jl_isless(b.first, a.first)) return true;
+      if (jl_isless(a.first, b.first)) return false;
+      return b.second < a.second;
+    });
+    int curr = 0;   // 0-based count of consumed entries (reference curr_idx - 1)
+    double lhs = sum_poslim;
+    while (lhs > rhs + tol && curr < n) {
+      int idx = order[curr].second;
+      if (dv[idx] < cfg.ZEROTOL) break;
+      lhs = lhs - Lloc(lidx(idx), d, k, s) * dv[idx];
+      ++curr;
+    }
+    for (int i = 0; i < curr; ++i) {
+      int idx = order[i].second;
+      double l_new = (i == curr - 1) ? jl_max((rhs + tol - lhs) / dv[idx], 0.0) : 0.0;
+      double &L = Lloc(lidx(idx), d, k, s);
+      L = jl_min(L, l_new);
+    }
+  }
+  void enforce_ES_subcell_volume(int nstage) {
+    const int s = nstage - 1, N1Dp1 = N1D + 1, N1Dm1 = N1D - 1;
+#pragma omp parallel for schedule(static)
+    for (int64_t k = 0; k < K; ++k) {
+      const double epsk = smooth_factor[k + K * (size_t)s];
+      if constexpr (DIM == 1) {
+        es_volume_greedy(&dvdf[0][(size_t)Nq * k], Nq - 1, [&](int i) { return i + 1; }, 0, k, s, sum_Bpsi[k][0], sum_dvfbarL[k][0], epsk);
+      } else {
+        // the x estimate and the y estimate are both formed before either direction is modified (:632-650);
+        // they touch disjoint coefficients, so doing x then y is the same
+        es_volume_greedy(&dvdf[0][(size_t)Nq * k], Nq - N1D, [&](int i) { return (i % N1Dm1 + 1) + (i / N1Dm1) * N1Dp1; }, 0, k, s,
+                         sum_Bpsi[k][0], sum_dvfbarL[k][0], epsk);
+        es_volume_greedy(&dvdf[1][(size_t)Nq * k], Nq - N1D, [&](int i) { return (i % N1D) + (i / N1D + 1) * N1D; }, 1, k, s,
+                         sum_Bpsi[k][1], sum_dvfbarL[k][1], epsk, true);
+      }
+    }
+  }
+  // :718-795 enforce_ES_subcell_interface!(::Dim2, ::GaussCollocation) + solve_l_es_interface! (:797-805).
+  // The reference runs this inside a threaded loop that reads the neighbour's coefficient while the neighbour may be
+  // rewriting it; the restatement is the serial order (k ascending), which is what one Julia thread does.
+  void enforce_ES_subcell_interface(int nstage) {
+    if (cfg.basis != P2DE_BASIS_GAUSS) return;   // Lobatto: interface fluxes coincide (:714-716)
+    if constexpr (DIM == 2) {
+      const int s = nstage - 1, N1Dp1 = N1D + 1;
+      for (int64_t k = 0; k < K; ++k) {
+        auto solve = [&](int d, int idx, int idxP, int64_t kP, int ifq) {
+          int64_t p = mapP[ifq + (size_t)Nfp * k];
+          const Vec &vM = vf_es[ifq + (size_t)Nfp * k], &vP = vf_es[p];
+          Vec dv;
+          for (int c = 0; c < Nc; ++c) dv[c] = vM[c] - vP[c];
+          double dpsi = psif_es[ifq + (size_t)Nfp * k][d] - psif_es[p][d];
+          double dvfH = dot(dv, fstar_H[ifq + (size_t)Nfp * k][d]);
+          double dvfL = dot(dv, fstar_L[ifq + (size_t)Nfp * k][d]);
+          double l = jl_min(Lloc(idx, d, k, s), Lloc(idxP, d, kP, s));
+          Lloc(idx, d, k, s) = bisection([&](double li) { return li * dvfH + (1 - li) * dvfL <= dpsi; }, 0.0, l);
+        };
+        for (int sj = 0; sj < N1D; ++sj)
+          for (int si = 0; si < N1Dp1; si += N1D) {
+            int iface = (si == 0) ? sj : sj + N1D;
+            int64_t p = mapP[iface + (size_t)Nfp * k];
+            int iP = (int)(p % Nfp); int64_t kP = p / Nfp;
+            int sjP = iP % N1D, siP = (iP / N1D == 0) ? 0 : N1D;
+            solve(0, si + sj * N1Dp1, siP + sjP * N1Dp1, kP, iface);
+          }
+        for (int si = 0; si < N1D; ++si)
+          for (int sj = 0; sj < N1Dp1; sj += N1D) {
+            int iface = (sj == 0) ? si + 2 * N1D : si + 3 * N1D;
+            int64_t p = mapP[iface + (size_t)Nfp * k];
+            int iP = (int)(p % Nfp); int64_t kP = p / Nfp;
+            int siP = iP % N1D, sjP = (iP / N1D == 2) ? 0 : N1D;
+            solve(1, si + sj * N1D, siP + sjP * N1D, kP, iface);
+          }
+      }
+    }
+  }
+  void enforce_ES_subcell(int nstage) {  // :458-464
+    if (!bound_has_cell_entropy()) return;
+    initialize_ES_subcell_limiting();
+    enforce_ES_subcell_volume(nstage);
+    enforce_ES_subcell_interface(nstage);
+  }
   // :405-456 symmetrize_limiting_parameters!  (serial: the reference's cross-element writes are an idempotent min)
   void symmetrize(int nstage) {
     int s = nstage - 1, N1Dp1 = N1D + 1;
@@ -1157,8 +1343,7 @@ struct Oracle : OracleBase {
       initialize_TVD_bounds(dt);
       accumulate_f_bar();
       subcell_bound_limiter(dt, nstage);
-      // enforce_ES_subcell!: no-op for Positivity / MinEntropy / TVD bounds (subcell.jl:458-460);
-      // cell-entropy bounds are a later row and rejected in oracle_create.
+      enforce_ES_subcell(nstage);
       symmetrize(nstage);
       apply_subcell(nstage);
     }
@@ -1248,6 +1433,9 @@ struct Oracle : OracleBase {
     FLD(flux) FLD(wavespeed_f) FLD(lambda) FLD(lambdaB) FLD(alpha) FLD(Uf)
     FLD(beta) FLD(rholog) FLD(betalog) FLD(lam) FLD(LFc) FLD(QF1)
     FLD(blending_factor) FLD(smooth_factor) FLD(lbound_s_modified) FLD(s_modified) FLD(lbound_rho) FLD(ubound_rho)
+    if (s == "dvdf_x") return copy_out(dvdf[0], dst, n);          // [Nq (first Nq-N1D used; 1D: Nq-1), K]
+    if (Nd > 1 && s == "dvdf_y") return copy_out(dvdf[Nd - 1], dst, n);
+    FLD(sum_Bpsi) FLD(sum_dvfbarL) FLD(rhoL)
 #undef FLD
     if (s == "uP_L") return copy_out(uP_L, dst, n);
     if (s == "uP_H") return copy_out(uP_H, dst, n);
@@ -1270,10 +1458,10 @@ const char *oracle_last_error() { return g_err.c_str(); }
 void *oracle_create(const p2de_config *cfg, const p2de_operators *ops, const p2de_geometry *geom, const p2de_bcdata *bc) {
   if (!cfg || !ops || !geom || !bc) { g_err = "null argument"; return nullptr; }
   if (cfg->dim != 1 && cfg->dim != 2) { g_err = "dim must be 1 or 2"; return nullptr; }
-  if (cfg->limiter == P2DE_LIMITER_SUBCELL &&
+  if (cfg->limiter == P2DE_LIMITER_SUBCELL && cfg->dim == 1 && cfg->basis == P2DE_BASIS_GAUSS &&
       (cfg->bound == P2DE_BOUND_POS_CELL_ENTROPY || cfg->bound == P2DE_BOUND_POS_RELAXED_CELL_ENTROPY ||
        cfg->bound == P2DE_BOUND_TVD_CELL_ENTROPY || cfg->bound == P2DE_BOUND_TVD_RELAXED_CELL_ENTROPY)) {
-    g_err = "cell-entropy bounds are not restated yet (SURVEY.md §8f-2)";
+    g_err = "cell-entropy bounds with 1D Gauss collocation: the reference has no enforce_ES_subcell_interface! method (subcell.jl:714-718)";
     return nullptr;
   }
   try {

@@ -118,6 +118,9 @@ struct p2de_handle {
   double *VDM_inv = nullptr;                  // [Np, Nq] (Hennemann indicator)
   unsigned long long *smin_bits = nullptr;    // global min of s_modified at t0 (min-entropy bounds)
   int entropy_bound = 0;                      // 0 none, 1 min entropy, 2 relaxed min entropy
+  int tvd = 0;                                // TVD*Bound: needs the low-order rhs of the neighbours (MODE_LOW pre-pass)
+  int cell_entropy = 0;                       // 0 none, 1 cell entropy, 2 relaxed cell entropy
+  double *rhsLpre = nullptr;                  // [K][Nq][4] (+ halo rows) low-order rhs of the pre-pass
   double *Lz = nullptr;       // [K, Ns]
   double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
@@ -424,6 +427,13 @@ int setup_topology(p2de_handle *h, const p2de_bcdata *bc) {
   return 0;
 }
 
+// 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound (Solver.jl:47-63)
+int cell_entropy_of(int bound) {
+  if (bound == P2DE_BOUND_POS_CELL_ENTROPY || bound == P2DE_BOUND_TVD_CELL_ENTROPY) return 1;
+  if (bound == P2DE_BOUND_POS_RELAXED_CELL_ENTROPY || bound == P2DE_BOUND_TVD_RELAXED_CELL_ENTROPY) return 2;
+  return 0;
+}
+
 __global__ void set_dt_kernel(unsigned long long *dt_bits, double v) { *dt_bits = (unsigned long long)__double_as_longlong(v); }
 
 // minimum(s_modified) over all nodes (initialize_s_modified!, subcell.jl:19-35); s_modified > 0
@@ -457,14 +467,16 @@ template <int N1D, int MODE, bool FAST>
 int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
   constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
-  size_t smem = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
+  const size_t base = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
+  const bool sub = !FAST && MODE == MODE_SUBCELL;
+  size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
   if (const char *pad = getenv("P2DE_SMEM_PAD")) smem += (size_t)atoi(pad);   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
   if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, false>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static size_t attr_set = 0;
+  if (smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_set = smem;
   }
   unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
   prof_begin(h, 0);
@@ -475,7 +487,8 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   return 0;
 }
 template <int N1D>
-int launch_stage_n(p2de_handle *h, const StageArgs &A) {
+int launch_stage_n(p2de_handle *h, const StageArgs &A, bool low_prepass) {
+  if (low_prepass) return launch_stage_t<N1D, MODE_LOW, false>(h, A);
   if (h->fast) {
     switch (h->mode) {
       case MODE_SUBCELL: return launch_stage_t<N1D, MODE_SUBCELL, true>(h, A);
@@ -491,12 +504,12 @@ int launch_stage_n(p2de_handle *h, const StageArgs &A) {
     default: return launch_stage_t<N1D, MODE_HIGH, false>(h, A);
   }
 }
-int launch_stage(p2de_handle *h, const StageArgs &A) {
+int launch_stage(p2de_handle *h, const StageArgs &A, bool low_prepass = false) {
   switch (h->N1D) {
-    case 2: return launch_stage_n<2>(h, A);
-    case 3: return launch_stage_n<3>(h, A);
-    case 4: return launch_stage_n<4>(h, A);
-    case 5: return launch_stage_n<5>(h, A);
+    case 2: return launch_stage_n<2>(h, A, low_prepass);
+    case 3: return launch_stage_n<3>(h, A, low_prepass);
+    case 4: return launch_stage_n<4>(h, A, low_prepass);
+    case 5: return launch_stage_n<5>(h, A, low_prepass);
   }
   return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
 }
@@ -581,6 +594,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.gauss = h->gauss ? 1 : 0; A.utf = h->utf;
   A.theta_local = (h->gauss && h->nodewise) ? h->theta_local_dev + (size_t)h->K * h->Nfp * (nstage - 1) : nullptr;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
+  A.tvd = h->tvd; A.rhsLpre = h->rhsLpre; A.cell_entropy = h->cell_entropy; A.bound_beta = h->cfg.bound_beta;
   return A;
 }
 
@@ -792,6 +806,15 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
     if (int rc = exchange_rows(h, h->utf, (size_t)h->cfg.Kx * h->Nfp * 4)) return rc;
   }
   StageArgs A = stage_args(h, Uin, nstage, dt_host, limiter_dt_dev);
+  if (h->tvd) {
+    // TVD bounds (subcell.jl:119-141) need rho + dt rhsL[1] of the stencil nodes ACROSS element faces, i.e. the
+    // neighbours' finished low-order rhs: a low-order pre-pass of the same kernel family writes it for all elements
+    StageArgs P = A;
+    P.rhsU = h->rhsLpre; P.nstage = 2;   // nstage != 1: no CFL reduction in the pre-pass
+    P.rhsH_diag = nullptr; P.rhsL_diag = nullptr; P.Lout = nullptr; P.tvd = 0; P.cell_entropy = 0; P.entropy_bound = 0; P.hennemann = 0;
+    if (int rc = launch_stage(h, P, true)) return rc;
+    if (int rc = exchange_rows(h, h->rhsLpre, (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
+  }
   // stages 2/3 of the FAST subcell path: the limiter's dt is the step's dt, so the stage kernel can
   // already form the SSP combine of the un-corrected rhs and the update kernel only adds corrections
   const bool fuse = h->fast && h->mode == MODE_SUBCELL && Uout && !want_outputs && nstage > 1 &&
@@ -851,9 +874,14 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   else if (cfg->rhs_type == P2DE_RHS_LIMITED_DG) {
     if (cfg->limiter == P2DE_LIMITER_ZHANGSHU) mode = MODE_ZHANGSHU;
     else if (cfg->limiter == P2DE_LIMITER_SUBCELL) {
-      const bool ent = cfg->bound == P2DE_BOUND_POS_MIN_ENTROPY || cfg->bound == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY;
-      if (cfg->bound != P2DE_BOUND_POSITIVITY && !(ent && !d1 && ops->VDM_inv))
-        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "bound %d: PositivityBound (1D/2D) and the two min-entropy bounds (2D) have GPU kernels; cell-entropy / TVD bounds do not (SURVEY.md 8f-2)", cfg->bound);
+      if (cfg->bound < P2DE_BOUND_POSITIVITY || cfg->bound > P2DE_BOUND_TVD_RELAXED_CELL_ENTROPY) return fail(nullptr, P2DE_ERR_ARG, "bound %d", cfg->bound);
+      if (cfg->bound != P2DE_BOUND_POSITIVITY && d1)
+        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "bound %d: only PositivityBound has a 1D kernel (SURVEY.md 8f-2)", cfg->bound);
+      // the smoothness indicator runs for every bound but PositivityBound (shock_capture.jl:4-12) and needs inv(VDM)
+      if (cfg->bound != P2DE_BOUND_POSITIVITY && cfg->bound != P2DE_BOUND_TVD && !ops->VDM_inv)
+        return fail(nullptr, P2DE_ERR_ARG, "bound %d needs ops.VDM_inv", cfg->bound);
+      if (cell_entropy_of(cfg->bound) && cfg->basis == P2DE_BASIS_GAUSS)
+        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "cell-entropy bounds on Gauss nodes (enforce_ES_subcell_interface!, subcell.jl:718-805) have no GPU kernel");
       mode = MODE_SUBCELL;
     } else return fail(nullptr, P2DE_ERR_UNSUPPORTED, "LimitedDG needs ZhangShuLimiter or SubcellLimiter");
   } else return fail(nullptr, P2DE_ERR_ARG, "rhs_type %d", cfg->rhs_type);
@@ -874,8 +902,14 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
                    !cfg->lgl_projection_roundtrip;
     h->fast = mode == MODE_LOW ? low_ok : mode == MODE_HIGH ? high_ok : (low_ok && high_ok);
   }
-  if (mode == MODE_SUBCELL) h->entropy_bound = cfg->bound == P2DE_BOUND_POS_MIN_ENTROPY ? 1 : (cfg->bound == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY ? 2 : 0);
-  if (h->entropy_bound || cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) h->fast = false;   // generic kernel has these features
+  if (mode == MODE_SUBCELL) {
+    const int b = cfg->bound;
+    h->entropy_bound = (b == P2DE_BOUND_POS_MIN_ENTROPY || b == P2DE_BOUND_TVD_MIN_ENTROPY) ? 1
+                     : (b == P2DE_BOUND_POS_RELAXED_MIN_ENTROPY || b == P2DE_BOUND_TVD_RELAXED_MIN_ENTROPY) ? 2 : 0;
+    h->tvd = b >= P2DE_BOUND_TVD ? 1 : 0;
+    h->cell_entropy = cell_entropy_of(b);
+  }
+  if (h->entropy_bound || h->tvd || h->cell_entropy || cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE) h->fast = false;   // generic kernel has these features
   h->gauss = !d1 && cfg->basis == P2DE_BASIS_GAUSS;
   h->nodewise = cfg->proj_limiter == P2DE_PROJLIM_NODEWISE;
   if (h->gauss) h->fast = false;
@@ -929,6 +963,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
       h->direct = !(nd && atoi(nd));
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
+    if (h->tvd && (rc = dev_alloc_halo(h, &h->rhsLpre, nU, rowU))) return bail(rc);
   } else {
     if ((rc = ensure_rhsU(h))) return bail(rc);
   }

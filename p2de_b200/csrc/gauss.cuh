@@ -25,13 +25,7 @@ struct ProjArgs {
   int nodewise;
 };
 
-// v_ufun(::Dim2), compressible_Navier_Stokes.jl:134-144
-P2DE_DEV void v_ufun2(double gamma, double gm1, const Cons2 &U, double v[4]) {
-  double p = pfun2(gm1, U);
-  double s = log(p / pow(U.rho, gamma));                 // sfun :64-68
-  v[0] = (gamma + 1 - s) - gm1 * U.E / p;
-  v[1] = U.m1 * gm1 / p; v[2] = U.m2 * gm1 / p; v[3] = -U.rho * gm1 / p;
-}
+// v_ufun2 (v_ufun(::Dim2), compressible_Navier_Stokes.jl:134-144) lives in kernels2d.cuh
 // u_vfun(::Dim2), :155-163 with s_vfun :93-97 and rhoe_vfun :99-104
 P2DE_DEV Cons2 u_vfun2(double gamma, double gm1, const double v[4]) {
   double q = v[1] * v[1] + v[2] * v[2];

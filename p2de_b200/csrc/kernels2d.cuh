@@ -92,6 +92,11 @@ struct StageArgs {
   // projection-limiting parameters theta_local [K][Nfp] of this stage, both written by gauss_project_kernel
   int gauss;
   const double *utf, *theta_local;
+  // generic kernel, remaining subcell bounds
+  int tvd;                           // TVD*Bound: rho in [min, max] of the low-order update over the low-order stencil
+  const double *rhsLpre;             // [K][Nq][4] low-order rhs of ALL elements (a MODE_LOW pre-pass): the stencil crosses faces
+  int cell_entropy;                  // 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound(beta)
+  double bound_beta;
 };
 
 struct UpdateArgs {
@@ -178,6 +183,12 @@ constexpr int stage_smem_doubles_per_elem() {
   constexpr int Nq = N1D * N1D;
   return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + 6 * Nq + N1D + 4 * Nq + 3 * 2 * N1D;
 }
+// extra shared memory of the TVD / cell-entropy bounds (allocated only when the bound is on): rhoL [S], its ghosts
+// [2][S], and per direction dvdf, dv.f_bar_L and the interior coefficients [2][Nq - N1D] each
+template <int N1D>
+constexpr int stage_smem_extra_doubles_per_elem(bool tvd, bool cell) {
+  return (tvd ? 3 * N1D * N1D : 0) + (cell ? 6 * N1D * (N1D - 1) : 0);
+}
 
 // s_modified_ufun, compressible_Navier_Stokes.jl:80-85
 P2DE_DEV double s_modified(double gamma, const Cons2 &U) { return rhoe2(U) * pow(U.rho, -gamma); }
@@ -196,6 +207,74 @@ __device__ __noinline__ double limiting_param_phi(double gamma, double POSTOL, c
     if (f(x_new)) x_valid = x_new; else x_invalid = x_new;
   }
   return x_valid;
+}
+
+// limiting_param_bound_rho_rhoe, limiter_utils.jl:26-40, with a finite upper density bound (TVD bounds) and
+// Urhoe = Inf; the caller's min(L_local, .) with L_local = 1 is folded in
+__device__ __noinline__ double limiting_param_rho_bounds(double ZEROTOL, const Cons2 &U, double c, const double Pv[4], double Lrho,
+                                                         double Urho, double Lrhoe) {
+  double a, b;
+  quad_coeff_ab(U, Pv, Lrhoe, a, b);
+  double l = 1.0;
+  if (U.rho + Pv[0] < Lrho) l = jl_max((Lrho - U.rho) / Pv[0], 0.0);
+  if (U.rho + Pv[0] > Urho) l = jl_min(l, jl_max((Urho - U.rho) / Pv[0], 0.0));
+  l = jl_min(l, rhoe_quadratic_roots(ZEROTOL, a, b, c));
+  return jl_min(l, 1.0);
+}
+
+// v_ufun(::Dim2), compressible_Navier_Stokes.jl:134-144
+P2DE_DEV void v_ufun2(double gamma, double gm1, const Cons2 &U, double V[4]) {
+  double p = pfun2(gm1, U);
+  double s = log(p / pow(U.rho, gamma));                 // sfun :64-68
+  V[0] = (gamma + 1 - s) - gm1 * U.E / p;
+  V[1] = U.m1 * gm1 / p; V[2] = U.m2 * gm1 / p; V[3] = -U.rho * gm1 / p;
+}
+
+// Base.isless on Float64 (NaN largest, -0.0 < 0.0), for the descending (value, index) order of
+// sort!(dvdf_order_k, rev=true), subcell.jl:607,673,703
+P2DE_DEV bool jl_isless(double a, double b) {
+  if (a != a) return false;
+  if (b != b) return true;
+  if (a == b) return signbit(a) && !signbit(b);
+  return a < b;
+}
+
+// enforce_ES_subcell_volume!, subcell.jl:612-707, one direction of one element, serial.  dv / dvfL / Lc hold the
+// NE = N1D (N1D - 1) interior subcell faces of the direction in the reference's dvdf index order
+// (x: (si - 1) + sj (N1D - 1); y: si + (sj - 1) N1D); `ysum` = the y estimate is accumulated si outer, sj inner (:641-646).
+template <int N1D>
+__device__ __noinline__ void es_volume_greedy(const double *dv, const double *dvfL, double *Lc, bool ysum, double sBpsi,
+                                              int relaxed, double beta, double epsk, double ZEROTOL) {
+  constexpr int NE = N1D * (N1D - 1);
+  double sdvfL = 0.0, sum_poslim = 0.0;
+  for (int i = 0; i < NE; ++i) {
+    const int idx = ysum ? (i / (N1D - 1)) + (i % (N1D - 1)) * N1D : i;
+    sdvfL += dvfL[idx];
+    sum_poslim += Lc[idx] * dv[idx];
+  }
+  const double rhs = relaxed ? (1 - beta * epsk) * (sBpsi - sdvfL) : sBpsi - sdvfL;   // rhs_es :709-716
+  const double tol = jl_max(0.0, sdvfL - sBpsi);
+  if (!(sum_poslim - rhs > tol)) return;
+  unsigned used = 0;          // NE <= 20 entries: selection in descending (value, index) order instead of a sort
+  int taken[NE];
+  int curr = 0;
+  double lhs = sum_poslim;
+  while (lhs > rhs + tol && curr < NE) {
+    int best = -1;
+    for (int i = 0; i < NE; ++i) {
+      if ((used >> i) & 1u) continue;
+      if (best < 0 || jl_isless(dv[best], dv[i]) || (!jl_isless(dv[i], dv[best]) && i > best)) best = i;
+    }
+    if (dv[best] < ZEROTOL) break;
+    used |= 1u << best;
+    lhs = lhs - Lc[best] * dv[best];
+    taken[curr++] = best;
+  }
+  for (int i = 0; i < curr; ++i) {
+    const int idx = taken[i];
+    const double l_new = (i == curr - 1) ? jl_max((rhs + tol - lhs) / dv[idx], 0.0) : 0.0;
+    Lc[idx] = jl_min(Lc[idx], l_new);
+  }
 }
 
 // FAST = default flux configuration (Chandrashekar volume flux, Lax-Friedrichs surface fluxes on
@@ -221,6 +300,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   double *lbnd = smod + S;                        // [S] indicator rho*p, later the lower bound on s_modified
   double *ghst = lbnd + S;                        // [2][S] s_modified across the x / y face of boundary nodes
   double *ered = ghst + 2 * S;                    // [EPB][TPE][3] modal energy partial sums
+  // optional arrays (stage_smem_extra_doubles_per_elem)
+  constexpr int NE = N1D * (N1D - 1);
+  double *rhoLs = ered + EPB * TPE * 3;           // [S] density of the low-order update (TVD bounds)
+  double *ghR = rhoLs + S;                        // [2][S] the same across the x / y face of boundary nodes
+  double *esD = ghR + 2 * S - (A.tvd ? 0 : 3 * S);   // [EPB][2][NE] dvdf (cell-entropy bounds)
+  double *esF = esD + EPB * 2 * NE;               // [EPB][2][NE] dv . f_bar_L
+  double *esL = esF + EPB * 2 * NE;               // [EPB][2][NE] interior coefficients
+  const bool need_ind = A.hennemann || A.entropy_bound == 2 || A.cell_entropy == 2;
 
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
@@ -254,7 +341,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       o[6 * S] = p; o[7 * S] = beta;
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
       if (A.entropy_bound) smod[nbase + node] = s_modified(gamma, U);
-      if (A.hennemann || A.entropy_bound == 2) lbnd[nbase + node] = U.rho * p;   // indicator, shock_capture.jl:82-94
+      if (need_ind) lbnd[nbase + node] = U.rho * p;   // indicator, shock_capture.jl:82-94
     }
   }
   __syncthreads();
@@ -262,7 +349,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   // ---- modal smoothness indicator (shock_capture.jl:47-80), blending factor (:111-132) and
   //      smoothness factor of the relaxed bound (subcell.jl:932-956); per element, every thread
   double blend = A.blend, epsk = A.entropy_bound == 1 ? 1.0 : 0.0;
-  if (A.hennemann || A.entropy_bound == 2) {
+  if (need_ind) {
     double eN = 0.0, eNm1 = 0.0, etot = 0.0;
     if (active)
       for (int m = ln; m < Nq; m += TPE) {
@@ -285,7 +372,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       const double al = 1.0 / (1.0 + exp(-s_factor / TN * (sigma - TN)));
       blend = jl_max(jl_min(1.0 - al, 1.0), 0.5);
     }
-    if (A.entropy_bound == 2) {
+    if (A.entropy_bound == 2 || A.cell_entropy == 2) {
       const double kappa = 1.0, s0 = log10(pow((double)A.N, -4.0)), sk = log10(sigma);
       epsk = sk < s0 - kappa ? 0.0 : (sk > s0 + kappa ? 1.0 : 0.5 - 0.5 * sin(3.141592653589793 * (sk - s0) / (2 * kappa)));
     }
@@ -321,6 +408,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     if (A.entropy_bound) {   // low_order_stencil across the element boundary (limiter_utils.jl:184-231)
       ghst[d * S + nbase + (d == 0 ? 0 + line * N1D : line)] = s_modified(gamma, Unb[0]);
       ghst[d * S + nbase + (d == 0 ? (N1D - 1) + line * N1D : line + (N1D - 1) * N1D)] = s_modified(gamma, Unb[1]);
+    }
+    if (MODE == MODE_SUBCELL && A.tvd) {   // rhoL = rho + dt rhsL[1] of the stencil node across the face (subcell.jl:119-141)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int ae = e ? N1D - 1 : 0;
+        ghR[d * S + nbase + (d == 0 ? ae + line * N1D : line + ae * N1D)] =
+            Unb[e].rho + dtl * A.rhsLpre[(nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4];
+      }
     }
     double fl[N1D][4];                      // nodal flux along d
 #pragma unroll
@@ -579,6 +674,16 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     __syncthreads();
   }
 
+  // ---- density of the low-order update at the element's own nodes (initialize_TVD_bounds!, subcell.jl:119-127)
+  if (MODE == MODE_SUBCELL && A.tvd) {
+    if (active)
+      for (int node = ln; node < Nq; node += TPE) {
+        const double *pl = partsL + (nbase + node) * 8;
+        rhoLs[nbase + node] = nodes[0 * S + nbase + node] + dtl * (pl[0] + pl[4]);
+      }
+    __syncthreads();
+  }
+
   // ---- CFL: dt = min_i CFL * 0.5 * wJ_i / lambda_i, low_order_graph_viscosity.jl:222-281
   if (DO_LOW && A.nstage == 1) {
     double dtloc = INFINITY;
@@ -604,9 +709,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 
-  if (!active && MODE != MODE_ZHANGSHU) return;
+  if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && A.cell_entropy)) return;
 
   if (MODE == MODE_SUBCELL) {
+    if (A.cell_entropy && !active) { __syncthreads(); __syncthreads(); return; }
     // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
     //      limiting coefficients of this line's N1D+1 subcell faces (subcell.jl:248-349)
     double dFv[NF][4];
@@ -617,7 +723,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
       for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + (GH[s - 1][c] - GL[s - 1][c]);
     Cons2 uL[N1D];
-    double Lrho[N1D], Lrhoe[N1D], c0[N1D];
+    double Lrho[N1D], Lrhoe[N1D], c0[N1D], Urho[N1D];
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       int node = d == 0 ? a + line * N1D : line + a * N1D;
@@ -628,6 +734,16 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       uL[a].rho = U[a].rho + dtl * r[0]; uL[a].m1 = U[a].m1 + dtl * r[1];
       uL[a].m2 = U[a].m2 + dtl * r[2]; uL[a].E = U[a].E + dtl * r[3];
       Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
+      Urho[a] = INFINITY;
+      if (A.tvd) {   // stencil min / max of rhoL (subcell.jl:129-141, low_order_stencil limiter_utils.jl:222-231; rho_bound :352-361)
+        const int i = node % N1D, j = node / N1D;
+        double lb = rhoLs[nbase + node], ub = lb, v;
+        v = i > 0 ? rhoLs[nbase + node - 1] : ghR[0 * S + nbase + node]; lb = jl_min(lb, v); ub = jl_max(ub, v);
+        v = i < N1D - 1 ? rhoLs[nbase + node + 1] : ghR[0 * S + nbase + node]; lb = jl_min(lb, v); ub = jl_max(ub, v);
+        v = j > 0 ? rhoLs[nbase + node - N1D] : ghR[1 * S + nbase + node]; lb = jl_min(lb, v); ub = jl_max(ub, v);
+        v = j < N1D - 1 ? rhoLs[nbase + node + N1D] : ghR[1 * S + nbase + node]; lb = jl_min(lb, v); ub = jl_max(ub, v);
+        Lrho[a] = lb; Urho[a] = ub;
+      }
       c0[a] = quad_coeff_c(uL[a], Lrhoe[a]);
       if (d == 0) {
         store4(A.rhsL + (k * Nq + node) * 4, r);
@@ -642,7 +758,8 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         double Pv[4], kk = -4 * dtl * rwJ[s];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        double lp = limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]);
+        double lp = A.tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Urho[s], Lrhoe[s])
+                          : limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]);
         if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s], Pv, lbnd[nbase + (d == 0 ? s + line * N1D : line + s * N1D)], lp);
         l = jl_min(l, lp);
       }
@@ -650,11 +767,50 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         double Pv[4], kk = 4 * dtl * rwJ[s - 1];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        double lp = limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]);
+        double lp = A.tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Urho[s - 1], Lrhoe[s - 1])
+                          : limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]);
         if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s - 1], Pv, lbnd[nbase + (d == 0 ? (s - 1) + line * N1D : line + (s - 1) * N1D)], lp);
         l = jl_min(l, lp);
       }
       lv[s] = jl_min(l, blend);
+    }
+    if (A.cell_entropy) {
+      // enforce_ES_subcell! on the element's interior subcell faces (subcell.jl:462-707; the interface part is a
+      // no-op on Lobatto nodes, :714-716): dvdf = (v_{s-1} - v_s) . (f_bar_H - f_bar_L), dv . f_bar_L per face by the
+      // line threads, the greedy update by one thread per element and direction
+      double vprev[4], vcur[4], fL[4];
+      v_ufun2(gamma, gm1, U[0], vprev);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) fL[c] = BFL[0][c];
+#pragma unroll
+      for (int s = 1; s < N1D; ++s) {
+        v_ufun2(gamma, gm1, U[s], vcur);
+        double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          fL[c] += GL[s - 1][c];
+          const double dv = vprev[c] - vcur[c];
+          a1 += dv * dFv[s][c]; a2 += dv * fL[c];
+          vprev[c] = vcur[c];
+        }
+        const int i = (el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D);
+        esD[i] = a1; esF[i] = a2; esL[i] = lv[s];
+      }
+      __syncthreads();
+      if (line == 0) {
+        double sB = 0.0;   // sum_Bpsi[k][d], subcell.jl:519-528: psi = (gamma - 1) (rho u, rho v) at the face nodes' volume nodes
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          for (int l2 = 0; l2 < N1D; ++l2) {
+            const int ae = e ? N1D - 1 : 0, node = d == 0 ? ae + l2 * N1D : l2 + ae * N1D;
+            sB += T.Bf[d][l2][e] * (gm1 * nodes[(1 + d) * S + nbase + node]);
+          }
+        es_volume_greedy<N1D>(esD + (el * 2 + d) * NE, esF + (el * 2 + d) * NE, esL + (el * 2 + d) * NE, d == 1, sB,
+                              A.cell_entropy == 2, A.bound_beta, epsk, A.ZEROTOL);
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s = 1; s < N1D; ++s) lv[s] = esL[(el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D)];
     }
     double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
 #pragma unroll

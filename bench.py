@@ -254,6 +254,15 @@ def run_ours(args):
         return t_ms
 
     e2e_steps = max(3, min(args.steps, 9))
+    if args.no_e2e:      # kernel A/B runs only (tools/ab_variants.sh): not a bench line the driver reads
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
+                              "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd,
+                              "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
     e2e_loop([st], [stream], [host], 2)
     initial_state(param, rd, ic, host.numpy())
     serial_ms = timed_e2e([st], [stream], [host], e2e_steps)
@@ -391,6 +400,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="S-DMR", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel A/B runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -47,6 +47,16 @@ def run_case(factory, nsteps):
     out = {"U0": U0, "rhsU_stage1": orc.field("rhsU"), "dt_stage1": np.array(dt1)}
     if param.rhs_limiter.code == 2:
         out["L_local_stage1"] = orc.field("L_local")[0]
+        if param.rhs_limiter.bound.code >= 5 and param.equation.dim == 2:
+            # TVD bounds: coefficients of faces with f_bar_H - f_bar_L = rounding noise are 0 or 1 by the sign of that
+            # noise (tests/test_gpu_bounds.py: significant_faces); the mask of the faces that are compared
+            n = param.N + 1
+            sig = []
+            for ax in "xy":
+                fH = orc.field(f"f_bar_H_{ax}").reshape(-1, n * n + n, 4)
+                fL = orc.field(f"f_bar_L_{ax}").reshape(-1, n * n + n, 4)
+                sig.append(np.abs(fH - fL).max(-1) > 1e-10 * np.abs(fH).max())
+            out["L_local_sig_stage1"] = np.stack(sig, axis=1)
     else:
         out["L_stage1"] = orc.field("L")[0]
     orc.set_state(U0)

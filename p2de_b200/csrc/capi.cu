@@ -7,6 +7,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -121,6 +122,7 @@ struct p2de_handle {
   int tvd = 0;                                // TVD*Bound: needs the low-order rhs of the neighbours (MODE_LOW pre-pass)
   int cell_entropy = 0;                       // 0 none, 1 cell entropy, 2 relaxed cell entropy
   double *rhsLpre = nullptr;                  // [K][Nq][4] (+ halo rows) low-order rhs of the pre-pass
+  double *fstar = nullptr;                    // [K][Nfp][2][4] Gauss + cell entropy: normal components of fstar_H, fstar_L
   double *Lz = nullptr;       // [K, Ns]
   double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
@@ -537,26 +539,6 @@ int launch_update_fast(p2de_handle *h, const UpdateArgs &A) {
   return 0;
 }
 template <int N1D>
-int launch_fix_n(p2de_handle *h, const UpdateArgs &A) {
-  constexpr int EPB = 16;
-  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
-  prof_begin(h, 1);
-  interface_fix_kernel<N1D, EPB><<<grid, EPB * 16, 0, h->stream>>>(A, h->topo, tables<N1D>(h));
-  prof_end(h);
-  CU(h, cudaGetLastError());
-  h->launches++;
-  return 0;
-}
-int launch_fix(p2de_handle *h, const UpdateArgs &A) {
-  switch (h->N1D) {
-    case 2: return launch_fix_n<2>(h, A);
-    case 3: return launch_fix_n<3>(h, A);
-    case 4: return launch_fix_n<4>(h, A);
-    case 5: return launch_fix_n<5>(h, A);
-  }
-  return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
-}
-template <int N1D>
 int launch_update_n(p2de_handle *h, const UpdateArgs &A) {
   if (h->mode == MODE_SUBCELL && h->fast) return launch_update_fast<N1D>(h, A);
   if (h->mode == MODE_SUBCELL) return launch_update_t<N1D, MODE_SUBCELL>(h, A);
@@ -570,6 +552,34 @@ int launch_update(p2de_handle *h, const UpdateArgs &A) {
     case 5: return launch_update_n<5>(h, A);
   }
   return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
+}
+
+// Uout = a resW + b (Uin + dt r): the SSP stage combine (SSPRK33.jl:31-39) as a flat, fully coalesced pass
+__global__ void __launch_bounds__(256)
+axpy_update_kernel(double2 *__restrict__ Uout, const double2 *__restrict__ resW, const double2 *__restrict__ Uin,
+                   const double2 *__restrict__ r, long long n2, double a, double b, const double *dt_dev, double dt_host, int use_dt_dev) {
+  const double dt = use_dt_dev ? *dt_dev : dt_host;
+  const bool plain = a == 0.0 && b == 1.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+    const double2 u = Uin[i], q = r[i];
+    double2 o;
+    if (plain) { o.x = u.x + dt * q.x; o.y = u.y + dt * q.y; }
+    else { const double2 w = resW[i]; o.x = a * w.x + b * (u.x + dt * q.x); o.y = a * w.y + b * (u.y + dt * q.y); }
+    Uout[i] = o;
+  }
+}
+int launch_axpy(p2de_handle *h, double *Uout, const double *resW, const double *Uin, const double *r, double a, double b,
+                double dt_host, bool use_dt_dev) {
+  const long long n2 = h->K * h->Nq * 2;
+  const unsigned grid = (unsigned)std::min<long long>((n2 + 255) / 256, 148ll * 8 * 4);
+  prof_begin(h, 1);
+  axpy_update_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<double2 *>(Uout), reinterpret_cast<const double2 *>(resW),
+                                                  reinterpret_cast<const double2 *>(Uin), reinterpret_cast<const double2 *>(r), n2, a, b,
+                                                  reinterpret_cast<const double *>(h->dt_bits), dt_host, use_dt_dev ? 1 : 0);
+  prof_end(h);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
 }
 
 StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_host, bool use_dt_dev) {
@@ -595,6 +605,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.theta_local = (h->gauss && h->nodewise) ? h->theta_local_dev + (size_t)h->K * h->Nfp * (nstage - 1) : nullptr;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   A.tvd = h->tvd; A.rhsLpre = h->rhsLpre; A.cell_entropy = h->cell_entropy; A.bound_beta = h->cfg.bound_beta;
+  A.fstar = h->fstar;
   return A;
 }
 
@@ -820,17 +831,22 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   const bool fuse = h->fast && h->mode == MODE_SUBCELL && Uout && !want_outputs && nstage > 1 &&
                     limiter_dt_dev == update_dt_dev;
   // ... and when the output buffer is not the input buffer it writes the new state itself; the
-  // interface symmetrisation is then a sparse fix-up (interface_fix_kernel)
+  // no second kernel is needed then (sym_free below)
   // (Uout == resW is fine: a node's resW is read by the one thread that then writes that node)
   const bool direct = fuse && Uout != Uin;
   if (fuse) { A.fuse = 1; A.fuse_a = a; A.fuse_b = b; A.fuse_resW = resW; }
   if (direct) A.rpre = Uout;
+  // FAST subcell path: f_bar_H - f_bar_L is exactly zero on interior element faces, so the interface coefficients are 1
+  // on both sides and symmetrize_limiting_parameters! (subcell.jl:418-456) is the identity; what is left after the stage
+  // kernel is at most the SSP combine (stage 1, where dt is only known once the kernel has finished everywhere)
+  const bool sym_free = h->fast && h->mode == MODE_SUBCELL && !want_outputs && (direct || !fuse);
   if (int rc = launch_stage(h, A)) return rc;
   if (h->comm) {
     if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
       NC(h, nccl_api(nullptr)->AllReduce(h->dt_bits, h->dt_bits, 1, ncclDouble, ncclMin, h->comm, h->stream));
-    // E2: un-symmetrised interface coefficients of the neighbouring stripes' boundary rows
-    if (h->mode == MODE_SUBCELL)
+    // E2: un-symmetrised interface coefficients of the neighbouring stripes' boundary rows (FAST path: the interface
+    // coefficients are 1 on both sides of every interior face, so only the L_local output needs them)
+    if (h->mode == MODE_SUBCELL && !sym_free)
       if (int rc = exchange_rows(h, h->lpre, (size_t)h->cfg.Kx * 2 * h->N1D * (h->N1D + 1))) return rc;
   }
   UpdateArgs B{};
@@ -841,7 +857,10 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.Uq_in = Uin; B.resW = resW; B.Uq_out = Uout; B.a = a; B.b = b;
   B.dt_dev = reinterpret_cast<const double *>(h->dt_bits); B.dt_host = dt_host; B.use_dt_dev = update_dt_dev;
   B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0; B.pre_updated = fuse ? 1 : 0;
-  if (direct) return launch_fix(h, B);
+  B.fstar = h->fstar; B.gamma = h->cfg.gamma;
+  if (direct) return 0;   // the stage kernel wrote the new state; nothing to symmetrise on the FAST path
+  if (sym_free && Uout)
+    return launch_axpy(h, Uout, resW, Uin, h->rpre, a, b, dt_host, update_dt_dev);   // pure SSP combine
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
   return 0;
 }
@@ -880,8 +899,6 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
       // the smoothness indicator runs for every bound but PositivityBound (shock_capture.jl:4-12) and needs inv(VDM)
       if (cfg->bound != P2DE_BOUND_POSITIVITY && cfg->bound != P2DE_BOUND_TVD && !ops->VDM_inv)
         return fail(nullptr, P2DE_ERR_ARG, "bound %d needs ops.VDM_inv", cfg->bound);
-      if (cell_entropy_of(cfg->bound) && cfg->basis == P2DE_BASIS_GAUSS)
-        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "cell-entropy bounds on Gauss nodes (enforce_ES_subcell_interface!, subcell.jl:718-805) have no GPU kernel");
       mode = MODE_SUBCELL;
     } else return fail(nullptr, P2DE_ERR_UNSUPPORTED, "LimitedDG needs ZhangShuLimiter or SubcellLimiter");
   } else return fail(nullptr, P2DE_ERR_ARG, "rhs_type %d", cfg->rhs_type);
@@ -958,12 +975,15 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if (mode == MODE_SUBCELL) {
     if ((rc = dev_alloc_halo(h, &h->lpre, (size_t)h->K * 2 * N1D * (N1D + 1), rowL))) return bail(rc);
     if (h->fast) {
-      if ((rc = dev_alloc_halo(h, &h->rpre, nU, rowU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
+      // (no dFend buffer: with exact-zero f_bar_H - f_bar_L on interior element faces the interface symmetrisation
+      //  is the identity on this path, stage_fast.cuh "End faces")
+      if ((rc = dev_alloc_halo(h, &h->rpre, nU, rowU))) return bail(rc);
       const char *nd = getenv("P2DE_NO_DIRECT");   // testing aid: keep the dense update kernel after every stage
       h->direct = !(nd && atoi(nd));
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
     if (h->tvd && (rc = dev_alloc_halo(h, &h->rhsLpre, nU, rowU))) return bail(rc);
+    if (h->cell_entropy && h->gauss && (rc = dev_alloc(h, &h->fstar, (size_t)h->K * h->Nfp * 8))) return bail(rc);
   } else {
     if ((rc = ensure_rhsU(h))) return bail(rc);
   }

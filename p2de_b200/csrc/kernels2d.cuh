@@ -97,6 +97,7 @@ struct StageArgs {
   const double *rhsLpre;             // [K][Nq][4] low-order rhs of ALL elements (a MODE_LOW pre-pass): the stencil crosses faces
   int cell_entropy;                  // 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound(beta)
   double bound_beta;
+  double *fstar;                     // Gauss + cell entropy: [K][Nfp][2][4] normal components of fstar_H, fstar_L (State.jl:11-12)
 };
 
 struct UpdateArgs {
@@ -114,6 +115,10 @@ struct UpdateArgs {
   int rotated;                       // dF of y-lines is stored in the rotated frame (FAST stage kernel)
   int pre_updated;                   // rpre already holds the SSP combine of the un-corrected rhs (StageArgs.fuse)
   double Jq;
+  // Gauss + cell-entropy bounds: enforce_ES_subcell_interface! (subcell.jl:718-805) needs the numerical fluxes of both
+  // sides of a face and the entropy variables / potentials of the face nodes' volume nodes (from Uq_in)
+  const double *fstar;               // [K][Nfp][2][4] or nullptr
+  double gamma;
 };
 
 struct Nbr { long long kP; int fP; int bc; const double *ival; };
@@ -516,6 +521,11 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           cons_arr(Uf, uf); cons_arr(uP, up);
 #pragma unroll
           for (int c = 0; c < 4; ++c) BFL[e][c] = B * (0.5 * (fM[c] + fP[c])) - lamB * (up[c] - uf[c]);
+          if (MODE == MODE_SUBCELL && A.fstar) {   // fstar_L = f* - lf / B (apply_LF_dissipation_to_fstar, rhs_utils.jl:93-102)
+            double *fo = A.fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 1) * 4;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fo[c] = 0.5 * (fM[c] + fP[c]) - (lamB * (up[c] - uf[c])) / B;
+          }
           lamFace[e] = lamB;
           if (proj && A.nstage == 1) {   // lambda_B_CFL(::LaxFriedrichsOnProjectedVal), :287-291
             double alpha = find_alpha(A.POSTOL, U[ae], Uf);
@@ -609,6 +619,11 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           cons_arr(Ut[e], uf); cons_arr(uP, up);
 #pragma unroll
           for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
+          if (MODE == MODE_SUBCELL && A.fstar) {   // fstar_H, flux_differencing.jl:263-270
+            double *fo = A.fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 0) * 4;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) fo[c] = fs[c] - (LFc * (up[c] - uf[c])) / B;
+          }
         }
       }
       if (!FAST && A.gauss) {
@@ -712,10 +727,13 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && A.cell_entropy)) return;
 
   if (MODE == MODE_SUBCELL) {
-    if (A.cell_entropy && !active) { __syncthreads(); __syncthreads(); return; }
     // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
     //      limiting coefficients of this line's N1D+1 subcell faces (subcell.jl:248-349)
+    // (inactive threads of a partial batch only get here with the cell-entropy bounds, whose barriers every thread of
+    //  the CTA has to reach at the same place)
     double dFv[NF][4];
+    double lv[NF];
+    if (active) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) dFv[0][c] = BFH[0][c] - BFL[0][c];
 #pragma unroll
@@ -750,7 +768,6 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
       }
     }
-    double lv[NF];
 #pragma unroll
     for (int s = 0; s < NF; ++s) {
       double l = 1.0;
@@ -774,10 +791,12 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       }
       lv[s] = jl_min(l, blend);
     }
+    }   // active
     if (A.cell_entropy) {
-      // enforce_ES_subcell! on the element's interior subcell faces (subcell.jl:462-707; the interface part is a
-      // no-op on Lobatto nodes, :714-716): dvdf = (v_{s-1} - v_s) . (f_bar_H - f_bar_L), dv . f_bar_L per face by the
-      // line threads, the greedy update by one thread per element and direction
+      // enforce_ES_subcell! on the element's interior subcell faces (subcell.jl:462-707; on Lobatto nodes the interface
+      // part is a no-op, :714-716, on Gauss nodes it is done by update_kernel): dvdf = (v_{s-1} - v_s) . (f_bar_H - f_bar_L),
+      // dv . f_bar_L per face by the line threads, the greedy update by one thread per element and direction
+      if (active) {
       double vprev[4], vcur[4], fL[4];
       v_ufun2(gamma, gm1, U[0], vprev);
 #pragma unroll
@@ -796,8 +815,9 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         const int i = (el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D);
         esD[i] = a1; esF[i] = a2; esL[i] = lv[s];
       }
+      }   // active
       __syncthreads();
-      if (line == 0) {
+      if (active && line == 0) {
         double sB = 0.0;   // sum_Bpsi[k][d], subcell.jl:519-528: psi = (gamma - 1) (rho u, rho v) at the face nodes' volume nodes
 #pragma unroll
         for (int e = 0; e < 2; ++e)
@@ -809,9 +829,12 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
                               A.cell_entropy == 2, A.bound_beta, epsk, A.ZEROTOL);
       }
       __syncthreads();
+      if (active) {
 #pragma unroll
-      for (int s = 1; s < N1D; ++s) lv[s] = esL[(el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D)];
+        for (int s = 1; s < N1D; ++s) lv[s] = esL[(el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D)];
+      }
     }
+    if (!active) return;
     double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);
 #pragma unroll
     for (int s = 0; s < NF; ++s) store4(dst + s * 4, dFv[s]);
@@ -887,6 +910,18 @@ P2DE_DEV int lidx_of_face(int fP) {
   return a + (F == 2 ? 0 : N1D) * N1D;             // y block: si + sj*N1D
 }
 
+// solve_l_es_interface!, subcell.jl:797-805: bisection(l -> l dvfH + (1 - l) dvfL <= dpsi, 0, l0) (nonlinear_solvers.jl:3-20)
+__device__ __noinline__ double es_interface_bisection(double l0, double dvfH, double dvfL, double dpsi) {
+  auto f = [&](double l) { return l * dvfH + (1 - l) * dvfL <= dpsi; };
+  if (f(l0)) return l0;
+  double x_valid = 0.0, x_invalid = l0;
+  for (int iter = 0; iter <= 20; ++iter) {
+    const double x_new = 0.5 * (x_valid + x_invalid);
+    if (f(x_new)) x_valid = x_new; else x_invalid = x_new;
+  }
+  return x_valid;
+}
+
 template <int N1D, int MODE, int EPB>
 __global__ void __launch_bounds__(EPB * 2 * N1D)
 update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ MeshTopo M,
@@ -911,9 +946,34 @@ update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ Mesh
       const int ix = (int)(k % M.Kx), iy = (int)(k / M.Kx);
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        Nbr nb = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
+        const int f = (2 * d + e) * N1D + line;
+        Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
         double lP = A.lpre[(nb.kP * 2 + d) * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
-        lv[e ? N1D : 0] = jl_min(lv[e ? N1D : 0], lP);
+        double lsym = jl_min(lv[e ? N1D : 0], lP);
+        if (A.fstar && nb.kP != k) {
+          // enforce_ES_subcell_interface!(::Dim2, ::GaussCollocation), subcell.jl:718-805: each side replaces its
+          // coefficient by bisection(l -> l dv.f*_H + (1 - l) dv.f*_L <= dpsi, 0, min(l, l_P)) with ITS OWN fluxes and
+          // dv = v_f - v_fP, dpsi = psi_f - psi_fP, then symmetrize takes the minimum.  The reference does this in a
+          // loop over k that reads the partner's coefficient as it is at that moment; in element order the element with
+          // the lower index goes first and the other one starts from its result (B(l) <= l), which is what both
+          // sides evaluate here.
+          const int ae = e ? N1D - 1 : 0, node = d == 0 ? ae + line * N1D : line + ae * N1D;
+          const double gm1 = A.gamma - 1.0;
+          const Cons2 uM = load_cons(A.Uq_in + (k * Nq + node) * 4), uPn = load_cons(A.Uq_in + (nb.kP * Nq + Tc.fq2q[nb.fP]) * 4);
+          double vM[4], vP[4], dv[4];
+          v_ufun2(A.gamma, gm1, uM, vM); v_ufun2(A.gamma, gm1, uPn, vP);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dv[c] = vM[c] - vP[c];
+          const double dpsi = gm1 * (d == 0 ? uM.m1 : uM.m2) - gm1 * (d == 0 ? uPn.m1 : uPn.m2);
+          const double *fm = A.fstar + (k * (4 * N1D) + f) * 8, *fp = A.fstar + (nb.kP * (4 * N1D) + nb.fP) * 8;
+          double hM = 0.0, lM = 0.0, hP = 0.0, lPd = 0.0;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { hM += dv[c] * fm[c]; lM += dv[c] * fm[4 + c]; hP += (-dv[c]) * fp[c]; lPd += (-dv[c]) * fp[4 + c]; }
+          const bool mine_first = k < nb.kP;
+          double l = es_interface_bisection(lsym, mine_first ? hM : hP, mine_first ? lM : lPd, mine_first ? dpsi : -dpsi);
+          lsym = es_interface_bisection(l, mine_first ? hP : hM, mine_first ? lPd : lM, mine_first ? -dpsi : dpsi);
+        }
+        lv[e ? N1D : 0] = lsym;
       }
       if (A.Llocal_out) {
         double *ldst = A.Llocal_out + (k * 2 + d) * (N1D * NF);

@@ -166,12 +166,14 @@ __device__ __noinline__ double limiting_param_pos_slow(double ZEROTOL, double rh
   if (!no_root) l = jl_min(l, rhoe_quadratic_roots(ZEROTOL, a, b, c));
   return jl_min(l, 1.0);
 }
+// common case: density bound inactive and no root in (0, 1]  ->  1 (no min, no division)
+P2DE_DEV bool limiting_param_pos_easy(double rho, double P0, double Lrho, double a, double b, double c) {
+  return !(rho + P0 < Lrho) && (c > 0.0) && (a + b + c > 0.0) && !(a > 0.0 && b < 0.0 && -b < 2.0 * a);
+}
 P2DE_DEV double limiting_param_pos(double ZEROTOL, const Cons2 &U, double c, const double Pv[4], double Lrho, double Lrhoe) {
   double a, b;
   quad_coeff_ab(U, Pv, Lrhoe, a, b);
-  // common case: density bound inactive and no root in (0, 1]  ->  1 (no min, no division)
-  bool easy = !(U.rho + Pv[0] < Lrho) && (c > 0.0) && (a + b + c > 0.0) && !(a > 0.0 && b < 0.0 && -b < 2.0 * a);
-  if (easy) return 1.0;
+  if (limiting_param_pos_easy(U.rho, Pv[0], Lrho, a, b, c)) return 1.0;
   return limiting_param_pos_slow(ZEROTOL, U.rho, Pv[0], Lrho, a, b, c);
 }
 

@@ -163,6 +163,18 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
   const double *Ubase = A.Uq + kb * (Nq * 4);             // this batch's states; 32-bit offsets from here on
 
+#ifdef P2DE_EXP_PREFETCH
+  {
+    // pull the states of the batch P2DE_EXP_PREFETCH CTAs ahead into L2 (it starts on some SM about when this one ends)
+    const long long kp = kb + (long long)P2DE_EXP_PREFETCH * EPB;
+    constexpr int LINES = EPB * Nq * 32 / 128;
+    if (kp + EPB <= M.K) {
+      if (tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Uq + kp * (Nq * 4) + tid * 16));
+      else if (MODE == MODE_SUBCELL && A.fuse && tid < 2 * LINES)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
+    }
+  }
+#endif
   // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a
   // lane-serialised constant-bank access)
   {
@@ -312,6 +324,14 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       double BFH[2][4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) dF0[c] = 0.0;
+      if (MODE == MODE_SUBCELL) {
+        // G = wJ (rhsxyH - rhsxyL) starts as Q0F1 - (BF_H - BF_L): the volume part of -GL; the surface terms
+        // cancel identically on interior faces (identity projection) and leave the LF term on inflow/outflow faces
+#pragma unroll
+        for (int a = 0; a < N1D; ++a)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) G[a][c] = -GL[a][c];
+      }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ae = e ? N1D - 1 : 0;
@@ -333,7 +353,8 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
           double lf = lamB * (up[c] - uf[c]);
           GL[ae][c] -= bfs - lf;                         // - BF_L
-          BFH[e][c] = nb[e].bc ? bfs : bfs - lf;         // BF_H (LFc = 0 on inflow/outflow faces)
+          if (MODE == MODE_SUBCELL) { if (nb[e].bc) G[ae][c] -= lf; }
+          else BFH[e][c] = nb[e].bc ? bfs : bfs - lf;    // BF_H (LFc = 0 on inflow/outflow faces)
           if (e == 0 && nb[e].bc) dF0[c] = lf;           // BF_H - BF_L on the seed face
         }
         lamFace[e] = lamB;
@@ -347,13 +368,14 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           if (A.nstage == 1)   // this direction's share of lambda_i (:222-281): its two volume pairs and its face
             lamp[d * S + pos[a]] = ((a > 0 ? lamPair[a - 1] : 0.0) + lamPair[a]) + (a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0));
         }
-        // G starts as -wJ rhsxyL - BF_H; the volume pairs below add the rest of wJ rhsxyH.
-        // (MODE_SUBCELL keeps only the difference; the other modes keep wJ rhsxyH by itself.)
+        // the other modes keep wJ rhsxyH by itself: G starts as -BF_H, the volume pairs below add the rest
+        if (MODE != MODE_SUBCELL) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          double bh = a == 0 ? BFH[0][c] : 0.0;
-          if (a == N1D - 1) bh += BFH[1][c];
-          G[a][c] = (MODE == MODE_SUBCELL ? -GL[a][c] : 0.0) - bh;
+          for (int c = 0; c < 4; ++c) {
+            double bh = a == 0 ? BFH[0][c] : 0.0;
+            if (a == N1D - 1) bh += BFH[1][c];
+            G[a][c] = -bh;
+          }
         }
       }
     }
@@ -372,7 +394,11 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         fS_rot(A.half_inv_gm1, q[i], q[j], F);
         double Sv = T.SHt[d][i][j][line];
 #pragma unroll
+#ifdef P2DE_EXP_FMA
+        for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }
+#else
         for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+#endif
       });
     }
 #pragma unroll
@@ -424,6 +450,16 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     for (int s = 1; s < NF; ++s)
 #pragma unroll
       for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + G[s - 1][c];
+    // End faces.  f_bar_H - f_bar_L on an element face is BF_H - BF_L there, which with the identity projection is
+    // exactly zero unless the face carries an inflow/outflow condition (the seed dF0 above; at the far end the prefix
+    // sum returns to it up to rounding, ~1e-16 |flux|).  The exact zero is used: the face's P is then zero, its
+    // coefficient is 1 from both sides without evaluating limiting_param, and the interface symmetrisation
+    // (subcell.jl:418-456) is the identity (boundary faces are their own partners), so no second kernel is needed.
+    const bool bc0 = nb[0].bc != 0, bc1 = nb[1].bc != 0;
+    if (!bc1) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) dFv[N1D][c] = 0.0;
+    }
     // node by node: u^L = Uq + dt rhsL (subcell.jl:269), its bounds, and the two subcell faces
     // next to it (P = -/+ 4 dt (fH - fL) / wJ, subcell.jl:300,312,328,340)
     double lv[NF];
@@ -461,8 +497,19 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 #ifdef P2DE_EXP_NOLIM
       lv[a] = jl_min(lv[a], Pm[0] + c0 + Lrho); lv[a + 1] = jl_min(lv[a + 1], Pp[1] + Lrhoe);
 #else
-      lv[a] = jl_min(lv[a], limiting_param_pos(A.ZEROTOL, uL, c0, Pm, Lrho, Lrhoe));
-      lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos(A.ZEROTOL, uL, c0, Pp, Lrho, Lrhoe));
+      // (lv <= 1 throughout, so the common result 1.0 of limiting_param_pos needs no min)
+      if (a > 0 || bc0) {
+        double qa, qb;
+        quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
+        if (!limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0))
+          lv[a] = jl_min(lv[a], limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pm[0], Lrho, qa, qb, c0));
+      }
+      if (a < N1D - 1 || bc1) {
+        double qa, qb;
+        quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
+        if (!limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0))
+          lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pp[0], Lrho, qa, qb, c0));
+      }
 #endif
     }
 #pragma unroll
@@ -477,9 +524,10 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (lv[a + 1] * dFv[a + 1][2] - lv[a] * dFv[a][2]) * rwJ[a],
                                                     m1.y + (lv[a + 1] * dFv[a + 1][3] - lv[a] * dFv[a][3]) * rwJ[a]);
     }
-    // end-face dF (rotated frame) for the interface correction in update_kernel_fast
-    store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
-    store4(A.dFend + (k * (4 * N1D) + (2 * d + 1) * N1D + line) * 4, dFv[N1D]);
+    if (A.dFend) {   // end-face dF (rotated frame); only kept for diagnostics, nothing reads it on the product path
+      store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
+      store4(A.dFend + (k * (4 * N1D) + (2 * d + 1) * N1D + line) * 4, dFv[N1D]);
+    }
 #pragma unroll
     for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
     }   // active
@@ -667,81 +715,6 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
       }
       store4(A.Uq_out + off, un);
     }
-  }
-}
-
-// Stages 2 and 3 of the FAST subcell path write a*resW + b*(Uq + dt*rhs_uncorrected) straight into
-// the next state buffer (StageArgs.fuse with rpre = that buffer), so what is left of the interface
-// symmetrisation (subcell.jl:418-456) is a SPARSE fix-up: only where the neighbour's coefficient is
-// smaller than this element's own, b*dt*(l_sym - l)*dF_end/wJ is added to the node on the element
-// boundary.  On interior faces f_H - f_L is rounding noise (identity LGL projection), so both sides
-// almost always return 1 and this kernel reads the interface coefficients and exits.
-// 16 threads per element, one per face node (N1D = 5: strided).  Same arithmetic, in the same
-// order, as update_kernel_fast's pre_updated branch.
-template <int N1D, int EPB>
-__global__ void __launch_bounds__(EPB * 16)
-interface_fix_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ MeshTopo M,
-                     const __grid_constant__ Tables2D<N1D> Tc) {
-  constexpr int Nq = N1D * N1D, Nfp = 4 * N1D, NF = N1D + 1, NL = 2 * N1D * NF, TPE = 16;
-  __shared__ double corr[EPB * Nfp * 4];
-  const int tid = threadIdx.x, el = tid / TPE, tl = tid % TPE;
-  const long long k = (long long)blockIdx.x * EPB + el;
-  const bool active = k < M.K;
-  int any = 0;
-  // batch strictly inside a structured mesh (CTA-uniform): the partner of face node f is k -+ 1 / k -+ Kx
-  bool interior = false;
-  const long long kb = (long long)blockIdx.x * EPB;
-  if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {
-    const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
-    interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
-  }
-  if (active) {
-    int ix = 0, iy = 0;
-    if (!interior) {
-      if (M.K < 0x7fffffffll) { iy = (int)((unsigned)k / (unsigned)M.Kx); ix = (int)((unsigned)k - (unsigned)iy * (unsigned)M.Kx); }
-      else { ix = (int)(k % M.Kx); iy = (int)(k / M.Kx); }
-    }
-    const double *lbase = A.lpre + kb * NL;
-    for (int f = tl; f < Nfp; f += TPE) {
-      const int F = f / N1D, line = f % N1D, d = F >> 1, e = F & 1;
-      const int s = e ? N1D : 0;
-      const int lidx = d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D);
-      const double lv = lbase[el * NL + lidx];
-      double lP;
-      if (interior) {
-        const int sP = e ? 0 : N1D;   // the partner's opposite end face
-        const int dk = d == 0 ? (e ? 1 : -1) : (e ? M.Kx : -M.Kx);
-        lP = lbase[(long long)(el + dk) * NL + d * (N1D * NF) + (d == 0 ? sP + line * NF : line + sP * N1D)];
-      } else {
-        Nbr nb = neighbor<N1D>(M, k, ix, iy, f);
-        lP = A.lpre[nb.kP * NL + d * (N1D * NF) + lidx_of_face<N1D>(nb.fP)];
-      }
-      const double lsym = jl_min(lv, lP);
-      double *c = corr + (el * Nfp + f) * 4;
-      if (lsym != lv) {   // the neighbour limits this face harder than this element did
-        const double w = (e ? (lsym - lv) : -(lsym - lv)) * Tc.rwJ[Tc.fq2q[f]];
-        Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
-        c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
-        any = 1;
-      } else { c[0] = 0.0; c[1] = 0.0; c[2] = 0.0; c[3] = 0.0; }
-    }
-  }
-  if (!__syncthreads_or(any)) return;
-  if (!active) return;
-  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
-  const double bd = A.b * dt;
-  const double *cb = corr + el * Nfp * 4;
-  for (int node = tl; node < Nq; node += TPE) {
-    const int i = node % N1D, j = node / N1D;
-    if (i != 0 && i != N1D - 1 && j != 0 && j != N1D - 1) continue;
-    const long long off = (k * Nq + node) * 4;
-    Cons2 rp = load_cons(A.Uq_out + off);
-    double un[4] = {rp.rho, rp.m1, rp.m2, rp.E};
-    if (i == 0) { const double *c = cb + (0 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
-    if (i == N1D - 1) { const double *c = cb + (1 * N1D + j) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
-    if (j == 0) { const double *c = cb + (2 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
-    if (j == N1D - 1) { const double *c = cb + (3 * N1D + i) * 4; un[0] += bd * c[0]; un[1] += bd * c[1]; un[2] += bd * c[2]; un[3] += bd * c[3]; }
-    store4(A.Uq_out + off, un);
   }
 }
 

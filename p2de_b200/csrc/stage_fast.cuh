@@ -21,6 +21,9 @@ namespace p2de {
 #ifndef P2DE_FAST_MIN_BLOCKS
 #define P2DE_FAST_MIN_BLOCKS 4
 #endif
+#ifndef P2DE_FAST_PREFETCH
+#define P2DE_FAST_PREFETCH 1
+#endif
 #ifndef P2DE_FAST_MIN_BLOCKS5
 #define P2DE_FAST_MIN_BLOCKS5 3   // N=4 (N1D=5): 168 registers, no spills
 #endif
@@ -137,10 +140,12 @@ constexpr int fast_smem_doubles_per_elem() {
 }
 
 
-template <int N1D, int MODE, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
-stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
-                  const __grid_constant__ Tables2D<N1D> Tc) {
+// INTERIOR = the batch lies strictly inside a structured mesh (CTA-uniform, decided by the kernel below): the neighbours
+// are k -+ 1 / k -+ Kx and no face carries a boundary condition, so the boundary-condition branches, the seed
+// f_bar_H - f_bar_L of the prefix sums and the two end-face limiter evaluations of every line vanish at compile time
+// (fewer live registers: the generic version spills the boundary flags across the whole kernel).
+template <int N1D, int MODE, int EPB, bool INTERIOR>
+__device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
   constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;
@@ -158,15 +163,17 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
   const long long kb = (long long)blockIdx.x * EPB;      // first element of this CTA's batch
   const long long k = kb + el;
-  const bool active = k < M.K;
-  const bool full = kb + EPB <= M.K;                      // no partial batch: skip the per-element guards
+  const bool active = INTERIOR || k < M.K;
+  const bool full = INTERIOR || kb + EPB <= M.K;          // no partial batch: skip the per-element guards
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
   const double *Ubase = A.Uq + kb * (Nq * 4);             // this batch's states; 32-bit offsets from here on
 
-#ifdef P2DE_EXP_PREFETCH
-  {
-    // pull the states of the batch P2DE_EXP_PREFETCH CTAs ahead into L2 (it starts on some SM about when this one ends)
-    const long long kp = kb + (long long)P2DE_EXP_PREFETCH * EPB;
+  if (P2DE_FAST_PREFETCH) {
+    // pull the states of the batch one full wave of resident CTAs ahead into L2: that batch starts on some SM about
+    // when this one ends, and its first instruction is a wait on exactly these lines (measured: -2.7 % on S-DMR;
+    // a persistent-CTA loop over batches was measured too and loses 13 % to the spills of its loop-carried state)
+    constexpr int AHEAD = 148 * (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS);
+    const long long kp = kb + (long long)AHEAD * EPB;
     constexpr int LINES = EPB * Nq * 32 / 128;
     if (kp + EPB <= M.K) {
       if (tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Uq + kp * (Nq * 4) + tid * 16));
@@ -174,7 +181,6 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
     }
   }
-#endif
   // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a
   // lane-serialised constant-bank access)
   {
@@ -192,12 +198,7 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     // Structured mesh, batch strictly inside the domain (the common case, CTA-uniform): the neighbours
     // are k -+ 1 / k -+ Kx, no boundary condition, and the partner face node follows from the LGL face
     // map that p2de_create verified (build_tables: fq2q).
-    bool interior = false;
-    if (!M.mapP32 && full && M.K < 0x7fffffffll) {
-      const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
-      interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
-    }
-    if (interior) {
+    if (INTERIOR) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         nb[e].bc = 0; nb[e].ival = nullptr; nb[e].kP = 0; nb[e].fP = 0;
@@ -340,8 +341,9 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
         double wsP = wavespeed_rot(gamma, gm1, rinvP, Unb[e].mn, Unb[e].E);
         double lamB = 0.5 * nn * fmax(ws[ae], wsP);
         ConsR uP = Unb[e];
-        if (nb[e].bc) {
-          if (nb[e].bc == 1) { const double *p = nb[e].ival; uP.rho = p[0]; uP.mn = p[1 + d]; uP.mt = p[2 - d]; uP.E = p[3]; }
+        const int bce = INTERIOR ? 0 : nb[e].bc;
+        if (bce) {
+          if (bce == 1) { const double *p = nb[e].ival; uP.rho = p[0]; uP.mn = p[1 + d]; uP.mt = p[2 - d]; uP.E = p[3]; }
           else uP = U[ae];
           rinvP = rcp_fast(uP.rho);
         }
@@ -353,9 +355,9 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
           double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
           double lf = lamB * (up[c] - uf[c]);
           GL[ae][c] -= bfs - lf;                         // - BF_L
-          if (MODE == MODE_SUBCELL) { if (nb[e].bc) G[ae][c] -= lf; }
-          else BFH[e][c] = nb[e].bc ? bfs : bfs - lf;    // BF_H (LFc = 0 on inflow/outflow faces)
-          if (e == 0 && nb[e].bc) dF0[c] = lf;           // BF_H - BF_L on the seed face
+          if (MODE == MODE_SUBCELL) { if (bce) G[ae][c] -= lf; }
+          else BFH[e][c] = bce ? bfs : bfs - lf;         // BF_H (LFc = 0 on inflow/outflow faces)
+          if (e == 0 && bce) dF0[c] = lf;                // BF_H - BF_L on the seed face
         }
         lamFace[e] = lamB;
       }
@@ -445,17 +447,17 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
     //      this line's N1D+1 subcell faces (subcell.jl:248-349)
     double dFv[NF][4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) dFv[0][c] = dF0[c];
+    for (int c = 0; c < 4; ++c) dFv[0][c] = INTERIOR ? 0.0 : dF0[c];
 #pragma unroll
     for (int s = 1; s < NF; ++s)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) dFv[s][c] = dFv[s - 1][c] + G[s - 1][c];
+      for (int c = 0; c < 4; ++c) dFv[s][c] = (INTERIOR && s == 1) ? G[0][c] : dFv[s - 1][c] + G[s - 1][c];
     // End faces.  f_bar_H - f_bar_L on an element face is BF_H - BF_L there, which with the identity projection is
     // exactly zero unless the face carries an inflow/outflow condition (the seed dF0 above; at the far end the prefix
     // sum returns to it up to rounding, ~1e-16 |flux|).  The exact zero is used: the face's P is then zero, its
     // coefficient is 1 from both sides without evaluating limiting_param, and the interface symmetrisation
     // (subcell.jl:418-456) is the identity (boundary faces are their own partners), so no second kernel is needed.
-    const bool bc0 = nb[0].bc != 0, bc1 = nb[1].bc != 0;
+    const bool bc0 = !INTERIOR && nb[0].bc != 0, bc1 = !INTERIOR && nb[1].bc != 0;
     if (!bc1) {
 #pragma unroll
       for (int c = 0; c < 4; ++c) dFv[N1D][c] = 0.0;
@@ -519,10 +521,15 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-      tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + (lv[a + 1] * dFv[a + 1][0] - lv[a] * dFv[a][0]) * rwJ[a],
-                                                    m0.y + (lv[a + 1] * dFv[a + 1][1] - lv[a] * dFv[a][1]) * rwJ[a]);
-      tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (lv[a + 1] * dFv[a + 1][2] - lv[a] * dFv[a][2]) * rwJ[a],
-                                                    m1.y + (lv[a + 1] * dFv[a + 1][3] - lv[a] * dFv[a][3]) * rwJ[a]);
+      // (INTERIOR: dF is exactly zero on the two end faces, the products are dropped at compile time)
+      double hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        hi[c] = (INTERIOR && a == N1D - 1) ? 0.0 : lv[a + 1] * dFv[a + 1][c];
+        lo[c] = (INTERIOR && a == 0) ? 0.0 : lv[a] * dFv[a][c];
+      }
+      tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + (hi[0] - lo[0]) * rwJ[a], m0.y + (hi[1] - lo[1]) * rwJ[a]);
+      tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (hi[2] - lo[2]) * rwJ[a], m1.y + (hi[3] - lo[3]) * rwJ[a]);
     }
     if (A.dFend) {   // end-face dF (rotated frame); only kept for diagnostics, nothing reads it on the product path
       store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
@@ -630,6 +637,20 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       if (A.rhsH_diag && DO_HIGH) store4(A.rhsH_diag + (k * Nq + node) * 4, rH[a]);
     }
   }
+}
+
+template <int N1D, int MODE, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
+stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                  const __grid_constant__ Tables2D<N1D> Tc) {
+  const long long kb = (long long)blockIdx.x * EPB;
+  bool interior = false;
+  if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {
+    const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
+    interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
+  }
+  if (interior) stage_fast_impl<N1D, MODE, EPB, true>(A, M, Tc);
+  else stage_fast_impl<N1D, MODE, EPB, false>(A, M, Tc);
 }
 
 // update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation

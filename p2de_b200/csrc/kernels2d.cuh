@@ -32,22 +32,26 @@ enum { MODE_SUBCELL = 0, MODE_ZHANGSHU = 1, MODE_LOW = 2, MODE_HIGH = 3 };
 
 template <int N1D>
 struct Tables2D {
-  double SH[2][N1D][N1D][N1D];  // physical hybridized S: [d][line][a][b] = GJ_dd * Srsh_db[d][node(a), node(b)]
-  double SHt[2][N1D][N1D][N1D]; // the same as [d][a][b][line]: bank-conflict free when the lanes of a warp differ in `line`
+  // ---- the part stage_kernel_fast uses comes first: it copies only these FAST_BYTES to shared memory
+  double SHt[2][N1D][N1D][N1D]; // physical hybridized S as [d][a][b][line] = GJ_dd * Srsh_db[d][node(a), node(b)]: bank-conflict free when the lanes of a warp differ in `line`
   double S0[2][N1D][N1D];       // physical low-order S0 of pair (a+1, a): [d][line][a]
   double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
   double wq[N1D * N1D];
-  double rwJ[N1D * N1D];        // 1 / (Jq * wq)
-  double rwJl[2][N1D][N1D];     // the same per grid line: [d][line][a]
+  double rwJl[2][N1D][N1D];     // 1 / (Jq * wq) per grid line: [d][line][a]
   // shared-memory positions used by stage_kernel_fast (see node_pos there), as look-up tables:
   int posl[2][4][N1D][N1D];     // [d][el & 3][line][a]: node_pos(el, .) - el * Nq of the a-th node of a line
   int posn[4][N1D * N1D];       // [el & 3][node]: the same for a flat node index
+  // ---- generic kernels only
+  double SH[2][N1D][N1D][N1D];  // the same S as [d][line][a][b]
+  double rwJ[N1D * N1D];        // 1 / (Jq * wq)
   double minv[N1D * N1D];       // MinvVhT[i, i]
   double minvf[4 * N1D];        // MinvVfT[fq2q[f], f]
   int fq2q[4 * N1D];            // 0-based
   // Gauss collocation (face nodes are not volume nodes): per line and line end e
   double VfL[2][N1D][2][N1D];   // Vf[f, node(a)]: extrapolation weights of the line's nodes to its end face node
   double SHf[2][N1D][2][N1D];   // physical hybridized S, face row x volume column: GJ_dd * Srsh_db[d][Nq + f, node(a)]
+  static constexpr int FAST_BYTES = (int)(sizeof(double) * (2 * N1D * N1D * N1D + 2 * N1D * N1D + 2 * N1D * 2 + N1D * N1D + 2 * N1D * N1D) +
+                                          sizeof(int) * (2 * 4 * N1D * N1D + 4 * N1D * N1D));
 };
 
 struct MeshTopo {

@@ -181,12 +181,16 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
     }
   }
-  // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a
-  // lane-serialised constant-bank access)
-  {
-    const double2 *src = reinterpret_cast<const double2 *>(A.tab_dev);
-    double2 *dst = reinterpret_cast<double2 *>(sm);
-    for (int i = tid; i < TBL / 2; i += NT) dst[i] = src[i];
+  // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a lane-serialised
+  // constant-bank access).  Only the loads are issued here; the stores to shared memory come after the state loads
+  // below have been issued too, so that the two round trips overlap instead of following each other.
+  static_assert(Tables2D<N1D>::FAST_BYTES + 8 <= (int)sizeof(Tables2D<N1D>), "the copy is rounded up to 16-byte words");
+  constexpr int TF2 = (Tables2D<N1D>::FAST_BYTES + 15) / 16, NTL = (TF2 + NT - 1) / NT;
+  double2 treg[NTL];
+#pragma unroll
+  for (int it = 0; it < NTL; ++it) {
+    const int i = tid + it * NT;
+    if (i < TF2) treg[it] = reinterpret_cast<const double2 *>(A.tab_dev)[i];
   }
   const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   // ---- the two neighbour face nodes of this line: issue the loads now (one 32-byte node each, two
@@ -235,6 +239,11 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
     }
+  }
+#pragma unroll
+  for (int it = 0; it < NTL; ++it) {
+    const int i = tid + it * NT;
+    if (i < TF2) reinterpret_cast<double2 *>(sm)[i] = treg[it];
   }
   __syncthreads();   // tables are in shared memory
 #pragma unroll

@@ -480,9 +480,14 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
   }
-  unsigned grid = (unsigned)((h->K + EPB - 1) / EPB);
+  dim3 grid((unsigned)((h->K + EPB - 1) / EPB));
+  StageArgs A2 = A;
+  if (FAST && !h->topo.mapP32 && h->cfg.Kx % EPB == 0 && h->cfg.Ky <= 65535) {
+    A2.rowblocks = h->cfg.Kx / EPB;
+    grid = dim3((unsigned)A2.rowblocks, (unsigned)h->cfg.Ky);
+  }
   prof_begin(h, 0);
-  kern<<<grid, EPB * TPE, smem, h->stream>>>(A, h->topo, tables<N1D>(h));
+  kern<<<grid, EPB * TPE, smem, h->stream>>>(A2, h->topo, tables<N1D>(h));
   prof_end(h);
   CU(h, cudaGetLastError());
   h->launches++;

@@ -21,6 +21,9 @@ namespace p2de {
 #ifndef P2DE_FAST_MIN_BLOCKS
 #define P2DE_FAST_MIN_BLOCKS 4
 #endif
+#ifndef P2DE_FAST_LIMITER_TWO_PASS
+#define P2DE_FAST_LIMITER_TWO_PASS 1
+#endif
 #ifndef P2DE_FAST_PREFETCH
 #define P2DE_FAST_PREFETCH 1
 #endif
@@ -145,7 +148,7 @@ constexpr int fast_smem_doubles_per_elem() {
 // f_bar_H - f_bar_L of the prefix sums and the two end-face limiter evaluations of every line vanish at compile time
 // (fewer live registers: the generic version spills the boundary flags across the whole kernel).
 template <int N1D, int MODE, int EPB, bool INTERIOR>
-__device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc) {
+__device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc, const long long kb) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
   constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;
@@ -161,8 +164,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
 
   const int tid = threadIdx.x;
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
-  const long long kb = (long long)blockIdx.x * EPB;      // first element of this CTA's batch
-  const long long k = kb + el;
+  const long long k = kb + el;                            // kb = first element of this CTA's batch
   const bool active = INTERIOR || k < M.K;
   const bool full = INTERIOR || kb + EPB <= M.K;          // no partial batch: skip the per-element guards
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
@@ -476,6 +478,52 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     double lv[NF];
 #pragma unroll
     for (int s = 0; s < NF; ++s) lv[s] = 1.0;
+    // First pass, branch-free: does ANY of this line's evaluations leave the common case "coefficient 1"
+    // (limiting_param_pos_easy)?  One divergent region per line instead of one per evaluation, and the common case
+    // runs as a single basic block in which the independent checks interleave.
+    bool all_easy = true;
+    if (!P2DE_FAST_LIMITER_TWO_PASS) all_easy = false;
+    else {
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        const double *o = nodes + pos[a];
+        double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
+        double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
+        double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
+        Cons2 uL;
+        uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
+        uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
+        const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
+        const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
+        const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
+        const double kk = 4 * dtl * rwJ[a];
+        double Pm[4], Pp[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
+        if (a > 0 || bc0) {
+          double qa, qb;
+          quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
+          all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0);
+        }
+        if (a < N1D - 1 || bc1) {
+          double qa, qb;
+          quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
+          all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0);
+        }
+        if (d == 0 && A.rhsL_diag) {
+          const int node = a + line * N1D;
+          double r[4] = {r0, r1, r2, r3};
+          store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+        }
+        if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
+          const int node = d == 0 ? a + line * N1D : line + a * N1D;
+          double *hd = A.rhsH_diag + (k * Nq + node) * 4;
+          atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
+          atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
+        }
+      }
+    }
+    if (!all_easy) {
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       const double *o = nodes + pos[a];
@@ -490,6 +538,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
       const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
       const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
+      if (!P2DE_FAST_LIMITER_TWO_PASS) {
       if (d == 0 && A.rhsL_diag) {
         const int node = a + line * N1D;
         double r[4] = {r0, r1, r2, r3};
@@ -500,6 +549,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         double *hd = A.rhsH_diag + (k * Nq + node) * 4;
         atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
         atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
+      }
       }
       const double kk = 4 * dtl * rwJ[a];
       double Pm[4], Pp[4];
@@ -523,10 +573,21 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       }
 #endif
     }
-#pragma unroll
-    for (int s = 0; s < NF; ++s) lv[s] = jl_min(lv[s], A.blend);
+    }   // !all_easy
+    // (update_blending_factor! = 1 without shock capturing, shock_capture.jl:111-114: the FAST path has none, so the
+    //  min with A.blend is the identity)
     // this line's share of the un-symmetrised limited rhs (subcell.jl:841-924 with the line's own
     // coefficients): t_d = rhsxyL_d + (l_{a+1} dF_{a+1} - l_a dF_a) / wJ, in the line's rotated frame
+    if (all_easy) {
+      // every coefficient of the line is 1: l_{a+1} dF_{a+1} - l_a dF_a is the prefix sum's own increment G[a],
+      // i.e. the share is rhsxyH_d
+#pragma unroll
+      for (int a = 0; a < N1D; ++a) {
+        double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
+        tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + G[a][0] * rwJ[a], m0.y + G[a][1] * rwJ[a]);
+        tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + G[a][2] * rwJ[a], m1.y + G[a][3] * rwJ[a]);
+      }
+    } else {
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
       double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
@@ -540,10 +601,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + (hi[0] - lo[0]) * rwJ[a], m0.y + (hi[1] - lo[1]) * rwJ[a]);
       tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (hi[2] - lo[2]) * rwJ[a], m1.y + (hi[3] - lo[3]) * rwJ[a]);
     }
-    if (A.dFend) {   // end-face dF (rotated frame); only kept for diagnostics, nothing reads it on the product path
-      store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
-      store4(A.dFend + (k * (4 * N1D) + (2 * d + 1) * N1D + line) * 4, dFv[N1D]);
-    }
+    }   // !all_easy
 #pragma unroll
     for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
     }   // active
@@ -652,14 +710,20 @@ template <int N1D, int MODE, int EPB>
 __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
 stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
                   const __grid_constant__ Tables2D<N1D> Tc) {
-  const long long kb = (long long)blockIdx.x * EPB;
+  long long kb;
   bool interior = false;
-  if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {
-    const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
-    interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
+  if (A.rowblocks) {   // structured mesh with Kx a multiple of EPB: 2D grid (batch in row, element row), no division
+    kb = ((long long)blockIdx.y * A.rowblocks + blockIdx.x) * EPB;
+    interior = blockIdx.x > 0u && blockIdx.x + 1u < (unsigned)A.rowblocks && blockIdx.y > 0u && blockIdx.y + 1u < gridDim.y;
+  } else {
+    kb = (long long)blockIdx.x * EPB;
+    if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {
+      const unsigned iy0 = (unsigned)kb / (unsigned)M.Kx, ix0 = (unsigned)kb - iy0 * (unsigned)M.Kx;
+      interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
+    }
   }
-  if (interior) stage_fast_impl<N1D, MODE, EPB, true>(A, M, Tc);
-  else stage_fast_impl<N1D, MODE, EPB, false>(A, M, Tc);
+  if (interior) stage_fast_impl<N1D, MODE, EPB, true>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE, EPB, false>(A, M, Tc, kb);
 }
 
 // update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation

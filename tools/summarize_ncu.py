@@ -1,0 +1,91 @@
+#!/usr/bin/env python
+"""Turns gpurun_out/prof_stage.ncu-rep + gpurun_out/launches.csv (tools/gpu_ncu.sh) into the tracked summaries:
+
+    profiles/r1_ncu_full_raw_S-DMR.csv          ncu --page raw --csv of the capture
+    profiles/r1_ncu_details_excerpt.txt         selected lines of --page details
+    profiles/r1_launches_bench_steps2_warmup1.csv   launch list (gpu__time_duration.sum per launch)
+    profiles/r1_traffic.json                    DRAM bytes / FP64 instruction counts per launch (read by bench.py)
+
+Runs on the CPU box (ncu -i needs no GPU)."""
+import csv
+import io
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REP = os.path.join(ROOT, "gpurun_out", "prof_stage.ncu-rep")
+PROF = os.path.join(ROOT, "profiles")
+NODES = 4096 * 1024 * 16     # S-DMR: DOF-updates per stage
+
+
+def ncu(*args):
+    return subprocess.run(["ncu", "-i", REP, *args], capture_output=True, text=True, check=True).stdout
+
+
+def main():
+    raw = ncu("--page", "raw", "--csv")
+    with open(os.path.join(PROF, "r1_ncu_full_raw_S-DMR.csv"), "w") as f:
+        f.write(raw)
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, data = rows[0], rows[2:]
+    col = {n: i for i, n in enumerate(hdr)}
+
+    def val(r, name):
+        return float(r[col[name]].replace(",", ""))
+
+    names = ["stage_kernel_fast_stage1", "axpy_update_kernel_stage1", "stage_kernel_fast_stage2", "stage_kernel_fast_stage3"]
+    out = {}
+    total = 0.0
+    for r, nm in zip(data, names):
+        kn = r[col["Kernel Name"]]
+        assert nm.split("_stage")[0].split("_kernel")[0] in kn, (nm, kn)
+        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
+        unit_r, unit_w = rows[1][col["dram__bytes_read.sum"]], rows[1][col["dram__bytes_write.sum"]]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd *= scale[unit_r]; wr *= scale[unit_w]
+        dur = val(r, "gpu__time_duration.sum")
+        dur_ms = dur * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6}[rows[1][col["gpu__time_duration.sum"]]]
+        out[nm] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "duration_ms_under_ncu": round(dur_ms, 4),
+                   "registers_per_thread": int(val(r, "launch__registers_per_thread")),
+                   "fp64_pipe_cycles_active_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") if "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active" in col else None,
+                   "issue_slots_busy_pct": val(r, "sm__inst_issued.avg.pct_of_peak_sustained_active") if "sm__inst_issued.avg.pct_of_peak_sustained_active" in col else None,
+                   "dram_throughput_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") if "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed" in col else None,
+                   "warps_active_per_sm": 4 * val(r, "smsp__warps_active.avg.per_cycle_active") if "smsp__warps_active.avg.per_cycle_active" in col else None}
+        total += rd + wr
+    r2 = data[2]
+    f = {k: val(r2, f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum") / NODES for k in ("dfma", "dmul", "dadd")}
+    out["per_step_total_bytes"] = total
+    out["per_stage_total_bytes"] = total / 3
+    out["fp64"] = {"_comment": "stage kernel of stage 2: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on per DOF-update (67.1 M nodes)",
+                   "dfma_per_dof_update": round(f["dfma"], 2), "dmul_per_dof_update": round(f["dmul"], 2), "dadd_per_dof_update": round(f["dadd"], 2),
+                   "flops_per_dof_update": round(2 * f["dfma"] + f["dmul"] + f["dadd"], 2),
+                   "lane_ops_per_dof_update": round(f["dfma"] + f["dmul"] + f["dadd"], 2)}
+    js = {"_comment": "Per-launch numbers from ONE ncu --set full --clock-control none capture (profiles/r1_ncu_full_raw_S-DMR.csv, made by "
+                      "tools/gpu_ncu.sh + tools/summarize_ncu.py), workload S-DMR (4096x1024, N=3, subcell), 1 B200: the four hot-path launches of "
+                      "one SSP-RK3 step (stage kernel, stage-1 SSP combine, stage kernel x2 with the combine fused). bench.py reads "
+                      "per_stage_total_bytes and the fp64 block.",
+          "S-DMR": out}
+    with open(os.path.join(PROF, "r1_traffic.json"), "w") as fjs:
+        json.dump(js, fjs, indent=1)
+    det = ncu("--page", "details")
+    keep = ("stage_kernel_fast", "axpy_update_kernel", "Memory Throughput", "DRAM Throughput", "Duration", "L2 Cache Throughput", "Compute (SM) Throughput",
+            "Executed Ipc Active", "Issue Slots Busy", "FP64", "fused", "Block Size", "Grid Size", "Registers Per Thread", "Dynamic Shared Memory Per Block",
+            "Block Limit", "Theoretical Occupancy", "Achieved Occupancy", "Warp Cycles Per Issued", "No Eligible", "Eligible Warps")
+    with open(os.path.join(PROF, "r1_ncu_details_excerpt.txt"), "w") as fd:
+        for line in det.splitlines():
+            if any(k in line for k in keep):
+                fd.write(line.rstrip()[:160] + "\n")
+    src = os.path.join(ROOT, "gpurun_out", "launches.csv")
+    if os.path.exists(src):
+        with open(src) as fi, open(os.path.join(PROF, "r1_launches_bench_steps2_warmup1.csv"), "w") as fo:
+            for line in fi:
+                if line.startswith('"'):
+                    fo.write(line)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -623,23 +623,65 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     }
     __syncthreads();
     double *out = A.rpre + kb * (Nq * 4);
+    if (NIT > 2) {   // N1D = 5: node by node (three nodes' worth of staging registers spills)
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) {
+        const int n = tid + it * NT;
+        const int e2 = n / Nq, node = n % Nq;
+        if (n < S && (full || kb + e2 < M.K)) {
+          const int p2 = e2 * Nq + T.posn[e2 & 3][node];
+          double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
+          double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
+          if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
+            r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
+            r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
+            r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
+            r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
+          }
+          store4(out + n * 4, r);
+        }
+      }
+    } else {
+    // all shared-memory loads of this thread's NIT nodes first, then the arithmetic and the stores (the loads of
+    // one node used to wait behind the stores of the previous one)
+    int p2v[NIT];
+    bool okv[NIT];
+    double2 xv[NIT][4];
+    double uo[NIT][4];
 #pragma unroll
     for (int it = 0; it < NIT; ++it) {
       const int n = tid + it * NT;
       const int e2 = n / Nq, node = n % Nq;
-      if (n < S && (full || kb + e2 < M.K)) {
-        const int p2 = e2 * Nq + T.posn[e2 & 3][node];
-        double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
+      okv[it] = n < S && (full || kb + e2 < M.K);
+      // swizzled position: arithmetic for N1D = 4 (no dependent table look-up), table otherwise
+      p2v[it] = N1D == 4 ? node_pos<N1D>(e2, node % N1D, node / N1D) : (n < S ? e2 * Nq + T.posn[e2 & 3][node] : 0);
+    }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it)
+      if (okv[it]) {
+        const int p2 = p2v[it];
+        xv[it][0] = tbuf[0 * S + p2]; xv[it][1] = tbuf[1 * S + p2]; xv[it][2] = tbuf[2 * S + p2]; xv[it][3] = tbuf[3 * S + p2];
+        if (A.fuse) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) uo[it][c] = nodes[c * S + p2];
+        }
+      }
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
+      const int n = tid + it * NT;
+      if (okv[it]) {
+        const double2 x0 = xv[it][0], x1 = xv[it][1], y0 = xv[it][2], y1 = xv[it][3];
         double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
         if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
-          r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
-          r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
-          r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
-          r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
+          r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (uo[it][0] + dtl * r[0]);
+          r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (uo[it][1] + dtl * r[1]);
+          r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (uo[it][2] + dtl * r[2]);
+          r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (uo[it][3] + dtl * r[3]);
         }
         store4(out + n * 4, r);
       }
     }
+    }   // NIT <= 2
     double *lout = A.lpre + kb * NL;
     if (full && (EPB * NL) % 2 == 0) {   // 16-byte copies
       const double2 *ls2 = reinterpret_cast<const double2 *>(lstage);

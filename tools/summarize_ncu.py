@@ -55,14 +55,35 @@ def main():
                    "dram_throughput_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") if "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed" in col else None,
                    "warps_active_per_sm": 4 * val(r, "smsp__warps_active.avg.per_cycle_active") if "smsp__warps_active.avg.per_cycle_active" in col else None}
         total += rd + wr
-    r2 = data[2]
-    f = {k: val(r2, f"smsp__sass_thread_inst_executed_op_{k}_pred_on.sum") / NODES for k in ("dfma", "dmul", "dadd")}
+    # FP64 thread-instruction counts of the stage-2 kernel from the source page (the third captured launch)
+    import re
+    srows = list(csv.reader(io.StringIO(ncu("--page", "source", "--csv", "--print-kernel-base", "function"))))
+    kernels, cur = [], None
+    for r in srows:
+        if r and r[0] == "Kernel Name":
+            cur = {"rows": [], "name": r[1]}; kernels.append(cur)
+        elif r and r[0] == "Address":
+            cur["hdr"] = r
+        elif cur is not None and r:
+            cur["rows"].append(r)
+    k2 = [k for k in kernels if "stage_kernel_fast" in k["name"]][2]   # a fused (stage 2 / 3) launch either way
+    ci = {n: i for i, n in enumerate(k2["hdr"])}
+    f = {"dfma": 0.0, "dmul": 0.0, "dadd": 0.0, "dsetp": 0.0, "all": 0.0}
+    for r in k2["rows"]:
+        n = float(r[ci["Predicated-On Thread Instructions Executed"]])
+        f["all"] += n
+        m = re.match(r"\s*(@!?U?P\d+\s+)?([A-Z0-9_]+)", r[ci["Source"]])
+        op = m.group(2).lower() if m else ""
+        if op in f:
+            f[op] += n
+    f = {k: v / NODES for k, v in f.items()}
     out["per_step_total_bytes"] = total
     out["per_stage_total_bytes"] = total / 3
-    out["fp64"] = {"_comment": "stage kernel of stage 2: smsp__sass_thread_inst_executed_op_{dfma,dmul,dadd}_pred_on per DOF-update (67.1 M nodes)",
+    out["fp64"] = {"_comment": "stage kernel of stage 2: predicated-on thread instructions per DOF-update (67.1 M nodes) from the ncu source page",
                    "dfma_per_dof_update": round(f["dfma"], 2), "dmul_per_dof_update": round(f["dmul"], 2), "dadd_per_dof_update": round(f["dadd"], 2),
                    "flops_per_dof_update": round(2 * f["dfma"] + f["dmul"] + f["dadd"], 2),
-                   "lane_ops_per_dof_update": round(f["dfma"] + f["dmul"] + f["dadd"], 2)}
+                   "lane_ops_per_dof_update": round(f["dfma"] + f["dmul"] + f["dadd"], 2),
+                   "dsetp_per_dof_update": round(f["dsetp"], 2), "thread_instructions_per_dof_update": round(f["all"], 1)}
     js = {"_comment": "Per-launch numbers from ONE ncu --set full --clock-control none capture (profiles/r1_ncu_full_raw_S-DMR.csv, made by "
                       "tools/gpu_ncu.sh + tools/summarize_ncu.py), workload S-DMR (4096x1024, N=3, subcell), 1 B200: the four hot-path launches of "
                       "one SSP-RK3 step (stage kernel, stage-1 SSP combine, stage kernel x2 with the combine fused). bench.py reads "

@@ -44,6 +44,9 @@ code(::NoEntropyProjectionLimiter) = 0; code(::NodewiseScaledExtrapolation) = 1
 code(::NoRHSLimiter) = 0; code(::ZhangShuLimiter) = 1; code(::SubcellLimiter) = 2
 code(::PositivityBound) = 0; code(::PositivityAndMinEntropyBound) = 1; code(::PositivityAndRelaxedMinEntropyBound) = 2
 code(::PositivityAndCellEntropyBound) = 3; code(::PositivityAndRelaxedCellEntropyBound) = 4
+code(::TVDBound) = 5; code(::TVDAndMinEntropyBound) = 6; code(::TVDAndRelaxedMinEntropyBound) = 7
+code(::TVDAndCellEntropyBound) = 8; code(::TVDAndRelaxedCellEntropyBound) = 9
+bound_beta(b) = hasproperty(b, :beta) ? Float64(b.beta) : 0.0     # *RelaxedCellEntropyBound(beta), Solver.jl:52-63
 code(::NoShockCapture) = 0; code(::HennemannShockCapture) = 1
 
 "`State` of the reference plus the device handle; `rhs!`/`SSP33!` dispatch on it."
@@ -71,7 +74,8 @@ function B200State(state, solver, state_param; device=-1, keep_diagnostics=false
         sizes.Nq, sizes.Nfp, sizes.Nh, sizes.Np, code(r), code(volf), code(lowf), code(highf),
         code(param.entropyproj_limiter), code(lim), lim isa NoRHSLimiter ? 0 : code(P2DE.bound(lim)), code(sc),
         keep_diagnostics, device, 0, 0,
-        sc isa HennemannShockCapture ? sc.a : 0.5, sc isa HennemannShockCapture ? sc.c : 1.8, 0.0,
+        sc isa HennemannShockCapture ? sc.a : 0.5, sc isa HennemannShockCapture ? sc.c : 1.8,
+        lim isa NoRHSLimiter ? 0.0 : bound_beta(P2DE.bound(lim)),
         P2DE.get_gamma(param.equation), gc.POSTOL, gc.ZEROTOL, lp.zeta, lp.eta, tp.CFL, tp.dt0, tp.t0, tp.T)
     bc = state_param.bcdata
     dense = [Matrix(s) for s in ops.Srs0]

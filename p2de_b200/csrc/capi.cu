@@ -113,6 +113,7 @@ struct p2de_handle {
   // device memory
   double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
   bool direct = false;                // FAST subcell path: stages 2/3 write the state from the stage kernel
+  bool defer = false;                 // ... and stage 2 forms the stage-1 combine on the fly (P2DE_NO_DEFER=1 disables)
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
   double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
@@ -478,7 +479,12 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   static size_t attr_set = 0;
   if (smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (FAST && MODE == MODE_SUBCELL)
+      CU(h, cudaFuncSetAttribute(stage_kernel_fast_defer<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;
+  }
+  if constexpr (FAST && MODE == MODE_SUBCELL) {
+    if (A.defer_add) kern = stage_kernel_fast_defer<N1D, EPB>;
   }
   dim3 grid((unsigned)((h->K + EPB - 1) / EPB));
   StageArgs A2 = A;
@@ -798,7 +804,8 @@ int launch_project(p2de_handle *h, const double *Uin, int nstage) {
 // one stage: stage_kernel + update_kernel.  `Uin` is the stage input; if `Uout` != nullptr the
 // SSP combine Uout = a*resW + b*(Uin + dt*rhsU) is fused into the update kernel.
 int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt_host, bool limiter_dt_dev,
-              bool update_dt_dev, double *Uout, const double *resW, double a, double b, bool want_outputs) {
+              bool update_dt_dev, double *Uout, const double *resW, double a, double b, bool want_outputs,
+              double *Uadd = nullptr, bool combine = true) {
   if (nstage == 1) {
     double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // low_order_graph_viscosity.jl:230
     set_dt_kernel<<<1, 1, 0, h->stream>>>(h->dt_bits, cap);
@@ -815,8 +822,9 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
     h->launches += 2;
     if (h->comm) NC(h, nccl_api(nullptr)->AllReduce(h->smin_bits, h->smin_bits, 1, ncclDouble, ncclMin, h->comm, h->stream));
   }
-  // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above
-  if (int rc = exchange_rows(h, const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
+  // E1: face-state halo (the boundary element rows of Uq) from the stripes below / above; with a deferred combine
+  // (stage input = Uin + dt Uadd) the halo rows of Uin are still those of the previous stage and Uadd's travel instead
+  if (int rc = exchange_rows(h, Uadd ? Uadd : const_cast<double *>(Uin), (size_t)h->cfg.Kx * h->Nq * 4)) return rc;
   if (h->gauss) {   // entropy projection (+ NodewiseScaledExtrapolation) to the face nodes; its halo rows travel like E1
     if (int rc = launch_project(h, Uin, nstage)) return rc;
     if (int rc = exchange_rows(h, h->utf, (size_t)h->cfg.Kx * h->Nfp * 4)) return rc;
@@ -841,6 +849,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   const bool direct = fuse && Uout != Uin;
   if (fuse) { A.fuse = 1; A.fuse_a = a; A.fuse_b = b; A.fuse_resW = resW; }
   if (direct) A.rpre = Uout;
+  A.defer_add = Uadd;
   // FAST subcell path: f_bar_H - f_bar_L is exactly zero on interior element faces, so the interface coefficients are 1
   // on both sides and symmetrize_limiting_parameters! (subcell.jl:418-456) is the identity; what is left after the stage
   // kernel is at most the SSP combine (stage 1, where dt is only known once the kernel has finished everywhere)
@@ -864,8 +873,10 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.Jq = h->Jq; B.rotated = h->fast ? 1 : 0; B.pre_updated = fuse ? 1 : 0;
   B.fstar = h->fstar; B.gamma = h->cfg.gamma;
   if (direct) return 0;   // the stage kernel wrote the new state; nothing to symmetrise on the FAST path
-  if (sym_free && Uout)
-    return launch_axpy(h, Uout, resW, Uin, h->rpre, a, b, dt_host, update_dt_dev);   // pure SSP combine
+  if (sym_free) {
+    if (Uout && combine) return launch_axpy(h, Uout, resW, Uin, h->rpre, a, b, dt_host, update_dt_dev);   // pure SSP combine
+    return 0;             // combine deferred into the next stage's kernel (StageArgs.defer_add)
+  }
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
   return 0;
 }
@@ -985,6 +996,8 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
       if ((rc = dev_alloc_halo(h, &h->rpre, nU, rowU))) return bail(rc);
       const char *nd = getenv("P2DE_NO_DIRECT");   // testing aid: keep the dense update kernel after every stage
       h->direct = !(nd && atoi(nd));
+      const char *nf = getenv("P2DE_NO_DEFER");    // testing / A-B aid: materialise U1 with the axpy kernel
+      h->defer = h->direct && !(nf && atoi(nf));
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
     if (h->tvd && (rc = dev_alloc_halo(h, &h->rhsLpre, nU, rowU))) return bail(rc);
@@ -1095,6 +1108,14 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
     // needs an output buffer other than the stage input: U1 -> Ub (dense update, dt only known after the
     // stage-1 kernel), U2 -> the rpre buffer (free once the stage-1 update has consumed it), U^{n+1} -> over
     // U^n, which stage 3 reads only as its own resW, node by node, by the thread that then writes the node.
+    if (h->defer) {
+      // ... and the stage-1 combine U1 = U^n + dt rhsU is not materialised at all: stage 1 leaves rhsU in the rpre
+      // buffer and the stage-2 kernel forms U1 while loading (same bytes as reading U1 and resW = U^n): 4 launches
+      if (int rc = run_stage(h, Ua, 1, t, cap, false, true, Ub, Ua, 0.0, 1.0, false, nullptr, false)) return rc;
+      if (int rc = run_stage(h, Ua, 2, t, cap, true, true, Ub, Ua, 3.0 / 4.0, 1.0 / 4.0, false, h->rpre)) return rc;
+      if (int rc = run_stage(h, Ub, 3, t, cap, true, true, Ua, Ua, 1.0 / 3.0, 2.0 / 3.0, false)) return rc;
+      return P2DE_OK;
+    }
     if (int rc = run_stage(h, Ua, 1, t, cap, false, true, Ub, Ua, 0.0, 1.0, false)) return rc;
     if (int rc = run_stage(h, Ub, 2, t, cap, true, true, h->rpre, Ua, 3.0 / 4.0, 1.0 / 4.0, false)) return rc;
     if (int rc = run_stage(h, h->rpre, 3, t, cap, true, true, Ua, Ua, 1.0 / 3.0, 2.0 / 3.0, false)) return rc;

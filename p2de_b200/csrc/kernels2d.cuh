@@ -101,6 +101,9 @@ struct StageArgs {
   const double *rhsLpre;             // [K][Nq][4] low-order rhs of ALL elements (a MODE_LOW pre-pass): the stencil crosses faces
   int cell_entropy;                  // 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound(beta)
   double bound_beta;
+  // FAST subcell kernel, stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (the stage-1 SSP combine
+  // U1 = U^n + dt rhsU, SSPRK33.jl:31-33, formed on the fly instead of by a separate pass over the mesh)
+  const double *defer_add;
   int rowblocks;                     // FAST kernel: > 0 = 2D grid (rowblocks x Ky), Kx = rowblocks * EPB; 0 = 1D grid over batches
   double *fstar;                     // Gauss + cell entropy: [K][Nfp][2][4] normal components of fstar_H, fstar_L (State.jl:11-12)
 };

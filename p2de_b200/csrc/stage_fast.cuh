@@ -63,6 +63,14 @@ P2DE_DEV double sqrt_fast(double a) {
   return fma(dd, h, g);
 }
 
+// U + dt * R at one node (the deferred stage-1 combine, StageArgs.defer_add)
+P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pr, double dt) {
+  Cons2 U = load_cons(pu);
+  const Cons2 R = load_cons(pr);
+  U.rho = fma(dt, R.rho, U.rho); U.m1 = fma(dt, R.m1, U.m1); U.m2 = fma(dt, R.m2, U.m2); U.E = fma(dt, R.E, U.E);
+  return U;
+}
+
 // state in the frame of one axis: (rho, normal momentum, tangential momentum, E)
 struct ConsR { double rho, mn, mt, E; };
 struct PrimR { double rho, un, ut, beta, rholog, betalog; };
@@ -147,7 +155,7 @@ constexpr int fast_smem_doubles_per_elem() {
 // are k -+ 1 / k -+ Kx and no face carries a boundary condition, so the boundary-condition branches, the seed
 // f_bar_H - f_bar_L of the prefix sums and the two end-face limiter evaluations of every line vanish at compile time
 // (fewer live registers: the generic version spills the boundary flags across the whole kernel).
-template <int N1D, int MODE, int EPB, bool INTERIOR>
+template <int N1D, int MODE, int EPB, bool INTERIOR, bool DEFER>
 __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc, const long long kb) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
@@ -179,6 +187,8 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     constexpr int LINES = EPB * Nq * 32 / 128;
     if (kp + EPB <= M.K) {
       if (tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Uq + kp * (Nq * 4) + tid * 16));
+      else if (DEFER && tid < 2 * LINES)      // (resW is Uq itself in that stage)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.defer_add + kp * (Nq * 4) + (tid - LINES) * 16));
       else if (MODE == MODE_SUBCELL && A.fuse && tid < 2 * LINES)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
     }
@@ -215,6 +225,8 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         const bool in_batch = d == 0 && (e ? el + 1 < EPB : el > 0);
         nbpos[e] = -1;
         if (in_batch) nbpos[e] = (el + dk) * Nq;   // completed with the swizzle table once the tables are loaded
+        else if (DEFER)
+          UnbC[e] = load_cons_plus(Ubase + ((long long)(el + dk) * Nq + node) * 4, A.defer_add + kb * (Nq * 4) + ((long long)(el + dk) * Nq + node) * 4, dtl);
         else UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
       }
     } else if (active) {
@@ -224,7 +236,8 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
-        UnbC[e] = load_cons(A.Uq + (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4);
+        const long long noff = (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4;
+        UnbC[e] = (DEFER) ? load_cons_plus(A.Uq + noff, A.defer_add + noff, dtl) : load_cons(A.Uq + noff);
       }
     }
   }
@@ -237,8 +250,9 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     const int n = tid + it * NT;
     Uraw[it].rho = 1.0; Uraw[it].m1 = 0.0; Uraw[it].m2 = 0.0; Uraw[it].E = 1.0;
     if (n < S && (full || kb + n / Nq < M.K)) {
-      Uraw[it] = load_cons(Ubase + n * 4);
-      if (MODE == MODE_SUBCELL && A.fuse)   // the flat output phase of this same thread reads resW here: pull it into L2 now
+      Uraw[it] = (DEFER) ? load_cons_plus(Ubase + n * 4, A.defer_add + kb * (Nq * 4) + n * 4, dtl)
+                                                       : load_cons(Ubase + n * 4);
+      if (MODE == MODE_SUBCELL && A.fuse && !DEFER)   // the flat output phase of this same thread reads resW here: pull it into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
     }
   }
@@ -748,12 +762,11 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   }
 }
 
-template <int N1D, int MODE, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
-stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
-                  const __grid_constant__ Tables2D<N1D> Tc) {
+// first element of this CTA's batch and whether the batch lies strictly inside a structured mesh
+template <int EPB>
+P2DE_DEV long long fast_batch(const StageArgs &A, const MeshTopo &M, bool &interior) {
   long long kb;
-  bool interior = false;
+  interior = false;
   if (A.rowblocks) {   // structured mesh with Kx a multiple of EPB: 2D grid (batch in row, element row), no division
     kb = ((long long)blockIdx.y * A.rowblocks + blockIdx.x) * EPB;
     interior = blockIdx.x > 0u && blockIdx.x + 1u < (unsigned)A.rowblocks && blockIdx.y > 0u && blockIdx.y + 1u < gridDim.y;
@@ -764,8 +777,29 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
       interior = ix0 > 0u && ix0 + EPB < (unsigned)M.Kx && iy0 > 0u && iy0 + 1u < (unsigned)M.Ky;
     }
   }
-  if (interior) stage_fast_impl<N1D, MODE, EPB, true>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE, EPB, false>(A, M, Tc, kb);
+  return kb;
+}
+
+template <int N1D, int MODE, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
+stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                  const __grid_constant__ Tables2D<N1D> Tc) {
+  bool interior;
+  const long long kb = fast_batch<EPB>(A, M, interior);
+  if (interior) stage_fast_impl<N1D, MODE, EPB, true, false>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE, EPB, false, false>(A, M, Tc, kb);
+}
+
+// stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (its own kernel: as a fourth and fifth copy of
+// the body inside stage_kernel_fast it made ptxas' allocation for the other copies 3 % slower)
+template <int N1D, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
+stage_kernel_fast_defer(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                        const __grid_constant__ Tables2D<N1D> Tc) {
+  bool interior;
+  const long long kb = fast_batch<EPB>(A, M, interior);
+  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, true>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, true>(A, M, Tc, kb);
 }
 
 // update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation

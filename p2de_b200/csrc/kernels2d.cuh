@@ -181,12 +181,14 @@ P2DE_DEV double find_alpha(double POSTOL, const Cons2 &ui, const Cons2 &ut) {
   double alphaL = 0.0, alphaR = 1.0;
   Cons2 s;
   auto sub = [&](double al) { s.rho = al * ui.rho - ut.rho; s.m1 = al * ui.m1 - ut.m1; s.m2 = al * ui.m2 - ut.m2; s.E = al * ui.E - ut.E; };
+  // (rhoe_ufun with a Newton reciprocal: 51 IEEE divisions per face node otherwise; guarded by rho > POSTOL > 0)
+  auto ok = [&]() { return s.rho > POSTOL && s.E - 0.5 * (s.m1 * s.m1 + s.m2 * s.m2) * rcp_fast(s.rho) > POSTOL; };
   sub(alphaR);
-  while (!(s.rho > POSTOL && rhoe2(s) > POSTOL) && alphaR < 1e300) { alphaR = 2 * alphaR; sub(alphaR); }
+  while (!ok() && alphaR < 1e300) { alphaR = 2 * alphaR; sub(alphaR); }
   for (int it = 0; it < 50; ++it) {
     double alphaM = (alphaL + alphaR) / 2;
     sub(alphaM);
-    if (s.rho > POSTOL && rhoe2(s) > POSTOL) alphaR = alphaM; else alphaL = alphaM;
+    if (ok()) alphaR = alphaM; else alphaL = alphaM;
   }
   return alphaR;
 }
@@ -345,12 +347,17 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
         o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv;
         if (DO_LOW) { o[10 * S] = wavespeed_fast(gamma, gm1, rinv, U.m1, U.E); o[11 * S] = wavespeed_fast(gamma, gm1, rinv, U.m2, U.E); }
+      } else if (A.gauss) {   // fast reciprocal / square root (physics.cuh: "_fd"), see fS_dir_fd
+        double rinv = rcp_fast(U.rho);
+        p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+        o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv;
+        if (DO_LOW) { o[10 * S] = wavespeed_dir_fd(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir_fd(gamma, gm1, U, 1); }
       } else {
         p = pfun2(gm1, U);
         o[4 * S] = U.m1 / U.rho; o[5 * S] = U.m2 / U.rho;
         if (DO_LOW) { o[10 * S] = wavespeed_dir(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir(gamma, gm1, U, 1); }
       }
-      beta = U.rho / (2 * p);
+      beta = (!FAST && A.gauss) ? div_fast(U.rho, 2 * p) : U.rho / (2 * p);
       o[6 * S] = p; o[7 * S] = beta;
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
       if (A.entropy_bound) smod[nbase + node] = s_modified(gamma, U);
@@ -513,8 +520,8 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           bool proj = A.surf_low == P2DE_SURFFLUX_LF_PROJECTED;
           Cons2 Uf = proj ? Ut[e] : U[ae];
           Cons2 UfP = proj ? Utnb[e] : Unb[e];
-          double wsM = proj ? wavespeed_dir(gamma, gm1, Uf, d) : ws[ae];
-          double wsP = wavespeed_dir(gamma, gm1, UfP, d);
+          double wsM = proj ? (A.gauss ? wavespeed_dir_fd(gamma, gm1, Uf, d) : wavespeed_dir(gamma, gm1, Uf, d)) : ws[ae];
+          double wsP = A.gauss ? wavespeed_dir_fd(gamma, gm1, UfP, d) : wavespeed_dir(gamma, gm1, UfP, d);
           double lamB = 0.5 * nn * jl_max(wsM, wsP);
           Cons2 uP = UfP;
           if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
@@ -562,7 +569,9 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
           for (int i = j + 1; i < N1D; ++i) {
             double F[4];
-            if (FAST) fS_fast(A.half_inv_gm1, q[i], q[j], d, F); else fS_dir(gm1, q[i], q[j], d, F);
+            if (FAST) fS_fast(A.half_inv_gm1, q[i], q[j], d, F);
+            else if (A.gauss) fS_dir_fd(gm1, q[i], q[j], d, F);
+            else fS_dir(gm1, q[i], q[j], d, F);
             double Sv = T.SH[d][line][i][j];
 #pragma unroll
             for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; GH[i][c] -= Sf; GH[j][c] += Sf; }
@@ -587,13 +596,13 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         // column j, QF1[i] += S_ij fS(u_i, u_j), QF1[j] -= the same (flux_differencing.jl:164-211)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          Prim2 pf = prim_of(gm1, Ut[e]);
+          Prim2 pf = prim_of_fd(gm1, Ut[e]);
           double ff[4];
           flux_dir(gm1, Ut[e], d, ff);
 #pragma unroll
           for (int a = 0; a < N1D; ++a) {
             double F[4];
-            if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) fS_dir(gm1, pf, q[a], d, F);
+            if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) fS_dir_fd(gm1, pf, q[a], d, F);
             else {
 #pragma unroll
               for (int c = 0; c < 4; ++c) F[c] = 0.5 * (ff[c] + fl[a][c]);
@@ -610,7 +619,8 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         for (int e = 0; e < 2; ++e) {
           const int ae = e ? N1D - 1 : 0;
           double B = T.Bf[d][line][e], nn = fabs(B);
-          double LFc = 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
+          double LFc = A.gauss ? 0.5 * nn * jl_max(wavespeed_dir_fd(gamma, gm1, Ut[e], d), wavespeed_dir_fd(gamma, gm1, Utnb[e], d))
+                               : 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
           Cons2 uP = Utnb[e];
           if (nb[e].bc == 1) { uP = load_cons(nb[e].ival); LFc = 0.0; }
           else if (nb[e].bc == 2) { uP = U[ae]; LFc = 0.0; }

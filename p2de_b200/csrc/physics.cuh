@@ -74,6 +74,43 @@ __device__ __noinline__ Cons2 entropy_roundtrip(double gamma, double gm1, Cons2 
   return W;
 }
 
+// reciprocal: MUFU.RCP64H seed (>= 20 bits) + one third-order step x (1 + e + e^2), e = 1 - a x
+// (error ~ e^3 < 2^-60: three dependent FMAs instead of the four of two Newton steps)
+P2DE_DEV double rcp_fast(double a) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
+  double e = fma(-a, x, 1.0);
+  double t = fma(e, e, e);
+  return fma(x, t, x);
+}
+// n / a with one residual correction (last-bit accurate for normal operands)
+P2DE_DEV double div_fast(double n, double a) {
+  double x = rcp_fast(a);
+  double q = n * x;
+  double r = fma(-a, q, n);
+  return fma(r, x, q);
+}
+// sqrt: MUFU.RSQ64H seed + two coupled Newton steps + residual correction
+P2DE_DEV double sqrt_fast(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  double dd = fma(-g, g, a);
+  return fma(dd, h, g);
+}
+
+// ---- Gauss collocation in the generic kernel: the same reference formulas with div_fast / sqrt_fast instead of the IEEE
+//      division and square-root routines (14 flux-differencing pairs per line x 6 divisions each dominate that kernel)
+P2DE_DEV double logmean_fd(double aL, double aR, double logL, double logR) {
+  double da = aR - aL, aavg = 0.5 * (aR + aL);
+  double f = div_fast(da, aavg), v = f * f;
+  if (fabs(f) < 1e-4) return aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857)));
+  return -div_fast(da, logL - logR);
+}
 // logmean :307-321
 P2DE_DEV double logmean(double aL, double aR, double logL, double logR) {
   double da = aR - aL, aavg = 0.5 * (aR + aL);
@@ -93,6 +130,18 @@ P2DE_DEV void fS_dir(double gm1, const Prim2 &L, const Prim2 &R, int d, double F
   double unorm = L.u * R.u + L.v * R.v;
   double pa = rhoavg / (L.beta + R.beta);
   double f4aux = rholog / (2 * gm1 * betalog) + pa + 0.5 * rholog * unorm;
+  double FxS1 = rholog * uavg, FxS3 = FxS1 * vavg;
+  if (d == 0) { F[0] = FxS1; F[1] = FxS1 * uavg + pa; F[2] = FxS3; F[3] = f4aux * uavg; }
+  else { double FyS1 = rholog * vavg; F[0] = FyS1; F[1] = FxS3; F[2] = FyS1 * vavg + pa; F[3] = f4aux * vavg; }
+}
+
+P2DE_DEV void fS_dir_fd(double gm1, const Prim2 &L, const Prim2 &R, int d, double F[4]) {
+  double rholog = logmean_fd(L.rho, R.rho, L.rholog, R.rholog);
+  double betalog = logmean_fd(L.beta, R.beta, L.betalog, R.betalog);
+  double rhoavg = 0.5 * (L.rho + R.rho), uavg = 0.5 * (L.u + R.u), vavg = 0.5 * (L.v + R.v);
+  double unorm = L.u * R.u + L.v * R.v;
+  double pa = div_fast(rhoavg, L.beta + R.beta);
+  double f4aux = div_fast(rholog, 2 * gm1 * betalog) + pa + 0.5 * rholog * unorm;
   double FxS1 = rholog * uavg, FxS3 = FxS1 * vavg;
   if (d == 0) { F[0] = FxS1; F[1] = FxS1 * uavg + pa; F[2] = FxS3; F[3] = f4aux * uavg; }
   else { double FyS1 = rholog * vavg; F[0] = FyS1; F[1] = FxS3; F[2] = FyS1 * vavg + pa; F[3] = f4aux * vavg; }
@@ -131,6 +180,21 @@ P2DE_DEV Prim2 prim_of(double gm1, const Cons2 &U) {
   q.beta = U.rho / (2 * p);                              // betafun :42-45
   q.rholog = log(U.rho); q.betalog = log(q.beta);
   return q;
+}
+
+P2DE_DEV Prim2 prim_of_fd(double gm1, const Cons2 &U) {
+  Prim2 q;
+  double rinv = rcp_fast(U.rho);
+  double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+  q.rho = U.rho; q.u = U.m1 * rinv; q.v = U.m2 * rinv;
+  q.beta = div_fast(U.rho, 2 * p);
+  q.rholog = log(U.rho); q.betalog = log(q.beta);
+  return q;
+}
+P2DE_DEV double wavespeed_dir_fd(double gamma, double gm1, const Cons2 &U, int d) {
+  double rinv = rcp_fast(U.rho), mn = d == 0 ? U.m1 : U.m2;
+  double p = gm1 * (U.E - 0.5 * (mn * mn) * rinv);
+  return fabs(mn * rinv) + sqrt_fast(gamma * p * rinv);
 }
 
 // rhoe_quadratic_coefficients(::Dim2), src/dg/limiter/limiter_utils.jl:85-90

@@ -34,35 +34,6 @@ namespace p2de {
 // constants of logmean's series branch (:315-317) and its reciprocal: read as constant-bank operands
 __constant__ double kSeries[5] = {-0.2, 0.0512, 0.026038857142857, 0.2, 0.0912};
 
-// reciprocal: MUFU.RCP64H seed (>= 20 bits) + one third-order step x (1 + e + e^2), e = 1 - a x
-// (error ~ e^3 < 2^-60: three dependent FMAs instead of the four of two Newton steps)
-P2DE_DEV double rcp_fast(double a) {
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(a));
-  double e = fma(-a, x, 1.0);
-  double t = fma(e, e, e);
-  return fma(x, t, x);
-}
-// n / a with one residual correction (last-bit accurate for normal operands)
-P2DE_DEV double div_fast(double n, double a) {
-  double x = rcp_fast(a);
-  double q = n * x;
-  double r = fma(-a, q, n);
-  return fma(r, x, q);
-}
-// sqrt: MUFU.RSQ64H seed + two coupled Newton steps + residual correction
-P2DE_DEV double sqrt_fast(double a) {
-  double y;
-  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-  double g = a * y, h = 0.5 * y;
-  double r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  r = fma(-g, h, 0.5);
-  g = fma(g, r, g); h = fma(h, r, h);
-  double dd = fma(-g, g, a);
-  return fma(dd, h, g);
-}
-
 // U + dt * R at one node (the deferred stage-1 combine, StageArgs.defer_add)
 P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pr, double dt) {
   Cons2 U = load_cons(pu);

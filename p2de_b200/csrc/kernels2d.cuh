@@ -331,7 +331,9 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
 
   {
-    const double *src = reinterpret_cast<const double *>(&Tc);
+    // from global memory (same bytes as the kernel parameter): an indexed read of the parameter is a lane-serialised
+    // constant-bank access (6 % of this kernel's stall samples before)
+    const double *src = A.tab_dev;
     for (int i = tid; i < TBLC; i += EPB * TPE) sm[i] = src[i];
   }
   // ---- node phase: primitives, logs, axis wavespeeds of every volume node (once per node)

@@ -25,7 +25,7 @@
 namespace p2de {
 
 #ifndef P2DE_STAGE_MIN_BLOCKS
-#define P2DE_STAGE_MIN_BLOCKS 2
+#define P2DE_STAGE_MIN_BLOCKS 3   // generic kernel: 3 CTAs/SM at 168 registers beat 2 at 255 (S-KH-gauss 6.8 -> 6.1 ms); shared memory allows no fourth
 #endif
 
 enum { MODE_SUBCELL = 0, MODE_ZHANGSHU = 1, MODE_LOW = 2, MODE_HIGH = 3 };

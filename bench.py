@@ -317,8 +317,8 @@ def run_ours(args):
                    "parallelism": f"dp{world} (y-stripes)" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes per stage (stage kernel + update / interface-fix kernel, averaged over the 3 stages of a step) from one ncu --set full capture, profiles/r1_traffic.json",
-                     "kernel": "stage_kernel + update_kernel (one RK stage)", "algorithmic_bytes_per_dof_update": A,
+                     "traffic_note": "DRAM bytes per stage (all hot-path kernels of one SSP-RK3 step / 3) from one ncu --set full capture, profiles/r1_traffic.json (S-DMR only)",
+                     "kernel": "all kernels of one RK stage (FAST path: stage_kernel_fast only; generic path: + projection / update kernels)", "algorithmic_bytes_per_dof_update": A,
                      "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
                      "stage_kernel_share": stage_ms / max(stage_ms + upd_ms + proj_ms, 1e-30),
                      "projection_kernel_ms": (proj_ms / n_proj) if n_proj else None},

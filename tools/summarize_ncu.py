@@ -36,24 +36,35 @@ def main():
     def val(r, name):
         return float(r[col[name]].replace(",", ""))
 
-    names = ["stage_kernel_fast_stage1", "axpy_update_kernel_stage1", "stage_kernel_fast_stage2", "stage_kernel_fast_stage3"]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tscale = {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6}
     out = {}
     total = 0.0
-    for r, nm in zip(data, names):
+    for r in data:
         kn = r[col["Kernel Name"]]
-        assert nm.split("_stage")[0].split("_kernel")[0] in kn, (nm, kn)
-        rd, wr = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum")
-        unit_r, unit_w = rows[1][col["dram__bytes_read.sum"]], rows[1][col["dram__bytes_write.sum"]]
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-        rd *= scale[unit_r]; wr *= scale[unit_w]
-        dur = val(r, "gpu__time_duration.sum")
-        dur_ms = dur * {"ns": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "nsecond": 1e-6}[rows[1][col["gpu__time_duration.sum"]]]
+        rd = val(r, "dram__bytes_read.sum") * scale[rows[1][col["dram__bytes_read.sum"]]]
+        wr = val(r, "dram__bytes_write.sum") * scale[rows[1][col["dram__bytes_write.sum"]]]
+        # the launches of one step: stage 1 (reads Uq only), stage 2 (its own instantiation: forms U1 while loading), stage 3
+        if "axpy_update_kernel" in kn:
+            nm = "axpy_update_kernel_stage1"
+        elif "stage_kernel_fast_defer" in kn:
+            nm = "stage_kernel_fast_defer_stage2"
+        elif "stage_kernel_fast" in kn:
+            nm = "stage_kernel_fast_stage1" if rd < 3.0e9 else "stage_kernel_fast_stage3"
+        else:
+            continue
+        if nm in out:
+            continue
+        dur_ms = val(r, "gpu__time_duration.sum") * tscale[rows[1][col["gpu__time_duration.sum"]]]
+
+        def opt(name, f=1.0):
+            return f * val(r, name) if name in col else None
         out[nm] = {"dram_read_bytes": rd, "dram_write_bytes": wr, "duration_ms_under_ncu": round(dur_ms, 4),
                    "registers_per_thread": int(val(r, "launch__registers_per_thread")),
-                   "fp64_pipe_cycles_active_pct": val(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") if "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active" in col else None,
-                   "issue_slots_busy_pct": val(r, "sm__inst_issued.avg.pct_of_peak_sustained_active") if "sm__inst_issued.avg.pct_of_peak_sustained_active" in col else None,
-                   "dram_throughput_pct": val(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") if "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed" in col else None,
-                   "warps_active_per_sm": 4 * val(r, "smsp__warps_active.avg.per_cycle_active") if "smsp__warps_active.avg.per_cycle_active" in col else None}
+                   "fp64_pipe_cycles_active_pct": opt("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                   "issue_slots_busy_pct": opt("sm__inst_issued.avg.pct_of_peak_sustained_active"),
+                   "dram_throughput_pct": opt("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                   "warps_active_per_sm": opt("smsp__warps_active.avg.per_cycle_active", 4.0)}
         total += rd + wr
     # FP64 thread-instruction counts of the stage-2 kernel from the source page (the third captured launch)
     import re
@@ -66,7 +77,10 @@ def main():
             cur["hdr"] = r
         elif cur is not None and r:
             cur["rows"].append(r)
-    k2 = [k for k in kernels if "stage_kernel_fast" in k["name"]][2]   # a fused (stage 2 / 3) launch either way
+    k2 = [k for k in kernels if "stage_kernel_fast" in k["name"] and "defer" not in k["name"]][0]
+    for kk in kernels:      # prefer a stage-3 launch (plain instantiation, SSP combine fused): the one with resW traffic
+        if "stage_kernel_fast" in kk["name"] and "defer" not in kk["name"]:
+            k2 = kk
     ci = {n: i for i, n in enumerate(k2["hdr"])}
     f = {"dfma": 0.0, "dmul": 0.0, "dadd": 0.0, "dsetp": 0.0, "all": 0.0}
     for r in k2["rows"]:
@@ -79,14 +93,14 @@ def main():
     f = {k: v / NODES for k, v in f.items()}
     out["per_step_total_bytes"] = total
     out["per_stage_total_bytes"] = total / 3
-    out["fp64"] = {"_comment": "stage kernel of stage 2: predicated-on thread instructions per DOF-update (67.1 M nodes) from the ncu source page",
+    out["fp64"] = {"_comment": "stage kernel (last captured launch of the plain instantiation): predicated-on thread instructions per DOF-update (67.1 M nodes) from the ncu source page",
                    "dfma_per_dof_update": round(f["dfma"], 2), "dmul_per_dof_update": round(f["dmul"], 2), "dadd_per_dof_update": round(f["dadd"], 2),
                    "flops_per_dof_update": round(2 * f["dfma"] + f["dmul"] + f["dadd"], 2),
                    "lane_ops_per_dof_update": round(f["dfma"] + f["dmul"] + f["dadd"], 2),
                    "dsetp_per_dof_update": round(f["dsetp"], 2), "thread_instructions_per_dof_update": round(f["all"], 1)}
     js = {"_comment": "Per-launch numbers from ONE ncu --set full --clock-control none capture (profiles/r1_ncu_full_raw_S-DMR.csv, made by "
                       "tools/gpu_ncu.sh + tools/summarize_ncu.py), workload S-DMR (4096x1024, N=3, subcell), 1 B200: the four hot-path launches of "
-                      "one SSP-RK3 step (stage kernel, stage-1 SSP combine, stage kernel x2 with the combine fused). bench.py reads "
+                      "one SSP-RK3 step (stage kernel; stage kernel forming the stage-1 combine while loading; stage kernel). bench.py reads "
                       "per_stage_total_bytes and the fp64 block.",
           "S-DMR": out}
     with open(os.path.join(PROF, "r1_traffic.json"), "w") as fjs:

@@ -475,10 +475,21 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
   if (const char *pad = getenv("P2DE_SMEM_PAD")) smem += (size_t)atoi(pad);   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
-  if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, false>;
+  if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, 0>;
+  // the shipped-examples configuration on Gauss nodes has its options compiled in (kernels2d.cuh: CFG = 1)
+  const bool default_gauss = !FAST && MODE == MODE_SUBCELL && A.gauss && !A.roundtrip && A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR &&
+                             A.surf_low == P2DE_SURFFLUX_LF_PROJECTED && A.surf_high == P2DE_SURFFLUX_LF_PROJECTED && !A.hennemann &&
+                             !A.entropy_bound && !A.tvd && !A.cell_entropy && !A.fstar;
+  if constexpr (!FAST && MODE == MODE_SUBCELL) {
+    if (default_gauss) kern = stage_kernel<N1D, MODE, EPB, 1>;
+  }
   static size_t attr_set = 0;
   if (smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if constexpr (!FAST && MODE == MODE_SUBCELL) {
+      CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     if constexpr (FAST && MODE == MODE_SUBCELL)
       CU(h, cudaFuncSetAttribute(stage_kernel_fast_defer<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = smem;

@@ -295,11 +295,23 @@ __device__ __noinline__ void es_volume_greedy(const double *dv, const double *dv
 // FAST = default flux configuration (Chandrashekar volume flux, Lax-Friedrichs surface fluxes on
 // nodal/projected values, identity LGL projection): hoisted reciprocals, merged low/high surface
 // flux, three-division two-point flux.  !FAST = every other option, reference operation order.
-template <int N1D, int MODE, int EPB, bool FAST>
+// CFG = 0: every option is a run-time value of StageArgs.  CFG = 1: the configuration of the reference's shipped 2D
+// examples (examples/2D/kelvin-helmholtz.jl:44-55: Gauss collocation, Chandrashekar volume flux, Lax-Friedrichs on projected
+// values for both surface fluxes, PositivityBound, no shock capturing) with the options fixed at compile time: the same
+// arithmetic, but the branches and the code of the other options do not exist (the run-time version of that
+// configuration no longer fits the instruction cache: 18 % instruction-fetch stalls).
+template <int N1D, int MODE, int EPB, int CFG>
 __global__ void __launch_bounds__(EPB * 2 * N1D, P2DE_STAGE_MIN_BLOCKS)
 stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
              const __grid_constant__ Tables2D<N1D> Tc) {
   constexpr int Nq = N1D * N1D, TPE = 2 * N1D, NF = N1D + 1, NFLD = 12;
+  constexpr bool FAST = false;   // (the default Lobatto configuration has its own kernel, stage_fast.cuh)
+  constexpr bool DG = CFG == 1;
+  const int o_gauss = DG ? 1 : A.gauss, o_roundtrip = DG ? 0 : A.roundtrip, o_vol_flux = DG ? P2DE_VOLFLUX_CHANDRASHEKAR : A.vol_flux;
+  const int o_surf_low = DG ? P2DE_SURFFLUX_LF_PROJECTED : A.surf_low, o_surf_high = DG ? P2DE_SURFFLUX_LF_PROJECTED : A.surf_high;
+  const int o_hennemann = DG ? 0 : A.hennemann, o_entropy_bound = DG ? 0 : A.entropy_bound, o_tvd = DG ? 0 : A.tvd;
+  const int o_cell_entropy = DG ? 0 : A.cell_entropy;
+  double *const o_fstar = DG ? nullptr : A.fstar;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
   constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;          // doubles to copy
   constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;   // keeps what follows 16-byte aligned
@@ -319,10 +331,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   constexpr int NE = N1D * (N1D - 1);
   double *rhoLs = ered + EPB * TPE * 3;           // [S] density of the low-order update (TVD bounds)
   double *ghR = rhoLs + S;                        // [2][S] the same across the x / y face of boundary nodes
-  double *esD = ghR + 2 * S - (A.tvd ? 0 : 3 * S);   // [EPB][2][NE] dvdf (cell-entropy bounds)
+  double *esD = ghR + 2 * S - (o_tvd ? 0 : 3 * S);   // [EPB][2][NE] dvdf (cell-entropy bounds)
   double *esF = esD + EPB * 2 * NE;               // [EPB][2][NE] dv . f_bar_L
   double *esL = esF + EPB * 2 * NE;               // [EPB][2][NE] interior coefficients
-  const bool need_ind = A.hennemann || A.entropy_bound == 2 || A.cell_entropy == 2;
+  const bool need_ind = o_hennemann || o_entropy_bound == 2 || o_cell_entropy == 2;
 
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
@@ -349,7 +361,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
         o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv;
         if (DO_LOW) { o[10 * S] = wavespeed_fast(gamma, gm1, rinv, U.m1, U.E); o[11 * S] = wavespeed_fast(gamma, gm1, rinv, U.m2, U.E); }
-      } else if (A.gauss) {   // fast reciprocal / square root (physics.cuh: "_fd"), see fS_dir_fd
+      } else if (o_gauss) {   // fast reciprocal / square root (physics.cuh: "_fd"), see fS_dir_fd
         double rinv = rcp_fast(U.rho);
         p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
         o[4 * S] = U.m1 * rinv; o[5 * S] = U.m2 * rinv;
@@ -359,10 +371,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         o[4 * S] = U.m1 / U.rho; o[5 * S] = U.m2 / U.rho;
         if (DO_LOW) { o[10 * S] = wavespeed_dir(gamma, gm1, U, 0); o[11 * S] = wavespeed_dir(gamma, gm1, U, 1); }
       }
-      beta = (!FAST && A.gauss) ? div_fast(U.rho, 2 * p) : U.rho / (2 * p);
+      beta = (!FAST && o_gauss) ? div_fast(U.rho, 2 * p) : U.rho / (2 * p);
       o[6 * S] = p; o[7 * S] = beta;
       if (DO_HIGH) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
-      if (A.entropy_bound) smod[nbase + node] = s_modified(gamma, U);
+      if (o_entropy_bound) smod[nbase + node] = s_modified(gamma, U);
       if (need_ind) lbnd[nbase + node] = U.rho * p;   // indicator, shock_capture.jl:82-94
     }
   }
@@ -370,7 +382,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 
   // ---- modal smoothness indicator (shock_capture.jl:47-80), blending factor (:111-132) and
   //      smoothness factor of the relaxed bound (subcell.jl:932-956); per element, every thread
-  double blend = A.blend, epsk = A.entropy_bound == 1 ? 1.0 : 0.0;
+  double blend = A.blend, epsk = o_entropy_bound == 1 ? 1.0 : 0.0;
   if (need_ind) {
     double eN = 0.0, eNm1 = 0.0, etot = 0.0;
     if (active)
@@ -388,13 +400,13 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     eN = eNm1 = etot = 0.0;
     for (int t2 = 0; t2 < TPE; ++t2) { eN += ered[(el * TPE + t2) * 3]; eNm1 += ered[(el * TPE + t2) * 3 + 1]; etot += ered[(el * TPE + t2) * 3 + 2]; }
     const double sigma = jl_max(eN / etot, eNm1 / etot);
-    if (A.hennemann) {
+    if (o_hennemann) {
       const double TN = A.hen_a * pow(10.0, -A.hen_c * pow((double)(A.N + 1), 0.25));
       const double s_factor = log((1 - 0.0001) / 0.0001);
       const double al = 1.0 / (1.0 + exp(-s_factor / TN * (sigma - TN)));
       blend = jl_max(jl_min(1.0 - al, 1.0), 0.5);
     }
-    if (A.entropy_bound == 2 || A.cell_entropy == 2) {
+    if (o_entropy_bound == 2 || o_cell_entropy == 2) {
       const double kappa = 1.0, s0 = log10(pow((double)A.N, -4.0)), sk = log10(sigma);
       epsk = sk < s0 - kappa ? 0.0 : (sk > s0 + kappa ? 1.0 : 0.5 - 0.5 * sin(3.141592653589793 * (sk - s0) / (2 * kappa)));
     }
@@ -427,11 +439,11 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
       Unb[e] = load_cons(A.Uq + (nb[e].kP * Nq + T.fq2q[nb[e].fP]) * 4);
     }
-    if (A.entropy_bound) {   // low_order_stencil across the element boundary (limiter_utils.jl:184-231)
+    if (o_entropy_bound) {   // low_order_stencil across the element boundary (limiter_utils.jl:184-231)
       ghst[d * S + nbase + (d == 0 ? 0 + line * N1D : line)] = s_modified(gamma, Unb[0]);
       ghst[d * S + nbase + (d == 0 ? (N1D - 1) + line * N1D : line + (N1D - 1) * N1D)] = s_modified(gamma, Unb[1]);
     }
-    if (MODE == MODE_SUBCELL && A.tvd) {   // rhoL = rho + dt rhsL[1] of the stencil node across the face (subcell.jl:119-141)
+    if (MODE == MODE_SUBCELL && o_tvd) {   // rhoL = rho + dt rhsL[1] of the stencil node across the face (subcell.jl:119-141)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ae = e ? N1D - 1 : 0;
@@ -482,10 +494,10 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       for (int e = 0; e < 2; ++e) {
         Ut[e] = U[e ? N1D - 1 : 0];
         Utnb[e] = Unb[e];
-        if (A.gauss) {   // rhs.jl:113-133: u(v_tilde) at the face nodes, mine and my neighbour's
+        if (o_gauss) {   // rhs.jl:113-133: u(v_tilde) at the face nodes, mine and my neighbour's
           Ut[e] = load_cons(A.utf + (k * (4 * N1D) + (2 * d + e) * N1D + line) * 4);
           Utnb[e] = load_cons(A.utf + (nb[e].kP * (4 * N1D) + nb[e].fP) * 4);
-        } else if (A.roundtrip) {
+        } else if (o_roundtrip) {
           Ut[e] = entropy_roundtrip(gamma, gm1, Ut[e]);
           Utnb[e] = entropy_roundtrip(gamma, gm1, Utnb[e]);
         }
@@ -519,11 +531,11 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         for (int e = 0; e < 2; ++e) {
           const int ae = e ? N1D - 1 : 0;
           double B = T.Bf[d][line][e], nn = fabs(B);
-          bool proj = A.surf_low == P2DE_SURFFLUX_LF_PROJECTED;
+          bool proj = o_surf_low == P2DE_SURFFLUX_LF_PROJECTED;
           Cons2 Uf = proj ? Ut[e] : U[ae];
           Cons2 UfP = proj ? Utnb[e] : Unb[e];
-          double wsM = proj ? (A.gauss ? wavespeed_dir_fd(gamma, gm1, Uf, d) : wavespeed_dir(gamma, gm1, Uf, d)) : ws[ae];
-          double wsP = A.gauss ? wavespeed_dir_fd(gamma, gm1, UfP, d) : wavespeed_dir(gamma, gm1, UfP, d);
+          double wsM = proj ? (o_gauss ? wavespeed_dir_fd(gamma, gm1, Uf, d) : wavespeed_dir(gamma, gm1, Uf, d)) : ws[ae];
+          double wsP = o_gauss ? wavespeed_dir_fd(gamma, gm1, UfP, d) : wavespeed_dir(gamma, gm1, UfP, d);
           double lamB = 0.5 * nn * jl_max(wsM, wsP);
           Cons2 uP = UfP;
           if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
@@ -538,8 +550,8 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           cons_arr(Uf, uf); cons_arr(uP, up);
 #pragma unroll
           for (int c = 0; c < 4; ++c) BFL[e][c] = B * (0.5 * (fM[c] + fP[c])) - lamB * (up[c] - uf[c]);
-          if (MODE == MODE_SUBCELL && A.fstar) {   // fstar_L = f* - lf / B (apply_LF_dissipation_to_fstar, rhs_utils.jl:93-102)
-            double *fo = A.fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 1) * 4;
+          if (MODE == MODE_SUBCELL && o_fstar) {   // fstar_L = f* - lf / B (apply_LF_dissipation_to_fstar, rhs_utils.jl:93-102)
+            double *fo = o_fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 1) * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c) fo[c] = 0.5 * (fM[c] + fP[c]) - (lamB * (up[c] - uf[c])) / B;
           }
@@ -565,14 +577,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         q[a].rho = U[a].rho; q[a].u = uu[a]; q[a].v = vv[a];
         q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
       }
-      if (FAST || A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
+      if (FAST || o_vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) {
 #pragma unroll
         for (int j = 0; j < N1D; ++j)
 #pragma unroll
           for (int i = j + 1; i < N1D; ++i) {
             double F[4];
             if (FAST) fS_fast(A.half_inv_gm1, q[i], q[j], d, F);
-            else if (A.gauss) fS_dir_fd(gm1, q[i], q[j], d, F);
+            else if (o_gauss) fS_dir_fd(gm1, q[i], q[j], d, F);
             else fS_dir(gm1, q[i], q[j], d, F);
             double Sv = T.SH[d][line][i][j];
 #pragma unroll
@@ -593,7 +605,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       for (int e = 0; e < 2; ++e)
 #pragma unroll
         for (int c = 0; c < 4; ++c) GHf[e][c] = 0.0;
-      if (!FAST && A.gauss) {
+      if (!FAST && o_gauss) {
         // hybridized face-volume pairs of Srsh_db = [Q - Q^T, E^T B; -B E, 0] (init.jl:148-155): face row i > volume
         // column j, QF1[i] += S_ij fS(u_i, u_j), QF1[j] -= the same (flux_differencing.jl:164-211)
 #pragma unroll
@@ -604,7 +616,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
           for (int a = 0; a < N1D; ++a) {
             double F[4];
-            if (A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) fS_dir_fd(gm1, pf, q[a], d, F);
+            if (o_vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR) fS_dir_fd(gm1, pf, q[a], d, F);
             else {
 #pragma unroll
               for (int c = 0; c < 4; ++c) F[c] = 0.5 * (ff[c] + fl[a][c]);
@@ -621,13 +633,13 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         for (int e = 0; e < 2; ++e) {
           const int ae = e ? N1D - 1 : 0;
           double B = T.Bf[d][line][e], nn = fabs(B);
-          double LFc = A.gauss ? 0.5 * nn * jl_max(wavespeed_dir_fd(gamma, gm1, Ut[e], d), wavespeed_dir_fd(gamma, gm1, Utnb[e], d))
+          double LFc = o_gauss ? 0.5 * nn * jl_max(wavespeed_dir_fd(gamma, gm1, Ut[e], d), wavespeed_dir_fd(gamma, gm1, Utnb[e], d))
                                : 0.5 * nn * jl_max(wavespeed_dir(gamma, gm1, Ut[e], d), wavespeed_dir(gamma, gm1, Utnb[e], d));
           Cons2 uP = Utnb[e];
           if (nb[e].bc == 1) { uP = load_cons(nb[e].ival); LFc = 0.0; }
           else if (nb[e].bc == 2) { uP = U[ae]; LFc = 0.0; }
           double fs[4];
-          if (A.surf_high == P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED) {
+          if (o_surf_high == P2DE_SURFFLUX_CHANDRASHEKAR_PROJECTED) {
             fS_dir(gm1, prim_of(gm1, Ut[e]), prim_of(gm1, uP), d, fs);
           } else {
             double fM[4], fP[4];
@@ -639,14 +651,14 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           cons_arr(Ut[e], uf); cons_arr(uP, up);
 #pragma unroll
           for (int c = 0; c < 4; ++c) BFH[e][c] = B * fs[c] - LFc * (up[c] - uf[c]);
-          if (MODE == MODE_SUBCELL && A.fstar) {   // fstar_H, flux_differencing.jl:263-270
-            double *fo = A.fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 0) * 4;
+          if (MODE == MODE_SUBCELL && o_fstar) {   // fstar_H, flux_differencing.jl:263-270
+            double *fo = o_fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 0) * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c) fo[c] = fs[c] - (LFc * (up[c] - uf[c])) / B;
           }
         }
       }
-      if (!FAST && A.gauss) {
+      if (!FAST && o_gauss) {
         // assemble_rhs! (flux_differencing.jl:274-361): M^-1 Vh^T = (1/wq) [I Vf_new^T], Vf_new = theta Vf + (1 - theta) Vf_low
         // per face node (:288-319); the 1/(wq J) factor is applied below with rwJ
 #pragma unroll
@@ -695,7 +707,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 
   // ---- lower bound on s_modified: stencil minimum relaxed towards the global minimum
   //      (initialize_lower_bound!, subcell.jl:55-75)
-  if (A.entropy_bound) {
+  if (o_entropy_bound) {
     if (active)
       for (int node = ln; node < Nq; node += TPE) {
         const int i = node % N1D, j = node / N1D;
@@ -710,7 +722,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   }
 
   // ---- density of the low-order update at the element's own nodes (initialize_TVD_bounds!, subcell.jl:119-127)
-  if (MODE == MODE_SUBCELL && A.tvd) {
+  if (MODE == MODE_SUBCELL && o_tvd) {
     if (active)
       for (int node = ln; node < Nq; node += TPE) {
         const double *pl = partsL + (nbase + node) * 8;
@@ -744,7 +756,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 
-  if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && A.cell_entropy)) return;
+  if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && o_cell_entropy)) return;
 
   if (MODE == MODE_SUBCELL) {
     // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
@@ -773,7 +785,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       uL[a].m2 = U[a].m2 + dtl * r[2]; uL[a].E = U[a].E + dtl * r[3];
       Lrho[a] = A.zeta * uL[a].rho; Lrhoe[a] = A.zeta * rhoe2(uL[a]);
       Urho[a] = INFINITY;
-      if (A.tvd) {   // stencil min / max of rhoL (subcell.jl:129-141, low_order_stencil limiter_utils.jl:222-231; rho_bound :352-361)
+      if (o_tvd) {   // stencil min / max of rhoL (subcell.jl:129-141, low_order_stencil limiter_utils.jl:222-231; rho_bound :352-361)
         const int i = node % N1D, j = node / N1D;
         double lb = rhoLs[nbase + node], ub = lb, v;
         v = i > 0 ? rhoLs[nbase + node - 1] : ghR[0 * S + nbase + node]; lb = jl_min(lb, v); ub = jl_max(ub, v);
@@ -795,24 +807,24 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         double Pv[4], kk = -4 * dtl * rwJ[s];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        double lp = A.tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Urho[s], Lrhoe[s])
+        double lp = o_tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Urho[s], Lrhoe[s])
                           : limiting_param_pos(A.ZEROTOL, uL[s], c0[s], Pv, Lrho[s], Lrhoe[s]);
-        if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s], Pv, lbnd[nbase + (d == 0 ? s + line * N1D : line + s * N1D)], lp);
+        if (o_entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s], Pv, lbnd[nbase + (d == 0 ? s + line * N1D : line + s * N1D)], lp);
         l = jl_min(l, lp);
       }
       if (s >= 1) {    // node to the left/bottom: P = +4 dt (fH - fL) / wJ (subcell.jl:312,340)
         double Pv[4], kk = 4 * dtl * rwJ[s - 1];
 #pragma unroll
         for (int c = 0; c < 4; ++c) Pv[c] = kk * dFv[s][c];
-        double lp = A.tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Urho[s - 1], Lrhoe[s - 1])
+        double lp = o_tvd ? limiting_param_rho_bounds(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Urho[s - 1], Lrhoe[s - 1])
                           : limiting_param_pos(A.ZEROTOL, uL[s - 1], c0[s - 1], Pv, Lrho[s - 1], Lrhoe[s - 1]);
-        if (A.entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s - 1], Pv, lbnd[nbase + (d == 0 ? (s - 1) + line * N1D : line + (s - 1) * N1D)], lp);
+        if (o_entropy_bound) lp = limiting_param_phi(gamma, A.POSTOL, uL[s - 1], Pv, lbnd[nbase + (d == 0 ? (s - 1) + line * N1D : line + (s - 1) * N1D)], lp);
         l = jl_min(l, lp);
       }
       lv[s] = jl_min(l, blend);
     }
     }   // active
-    if (A.cell_entropy) {
+    if (o_cell_entropy) {
       // enforce_ES_subcell! on the element's interior subcell faces (subcell.jl:462-707; on Lobatto nodes the interface
       // part is a no-op, :714-716, on Gauss nodes it is done by update_kernel): dvdf = (v_{s-1} - v_s) . (f_bar_H - f_bar_L),
       // dv . f_bar_L per face by the line threads, the greedy update by one thread per element and direction
@@ -846,7 +858,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
             sB += T.Bf[d][l2][e] * (gm1 * nodes[(1 + d) * S + nbase + node]);
           }
         es_volume_greedy<N1D>(esD + (el * 2 + d) * NE, esF + (el * 2 + d) * NE, esL + (el * 2 + d) * NE, d == 1, sB,
-                              A.cell_entropy == 2, A.bound_beta, epsk, A.ZEROTOL);
+                              o_cell_entropy == 2, A.bound_beta, epsk, A.ZEROTOL);
       }
       __syncthreads();
       if (active) {

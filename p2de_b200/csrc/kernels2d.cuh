@@ -541,15 +541,21 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           if (nb[e].bc == 1) uP = load_cons(nb[e].ival);
           else if (nb[e].bc == 2) uP = U[ae];
           double fM[4], fP[4], uf[4], up[4];
-          if (proj) flux_dir(gm1, Uf, d, fM);
+          if (proj) { if (o_gauss) flux_dir_fd(gm1, Uf, d, fM); else flux_dir(gm1, Uf, d, fM); }
           else {
 #pragma unroll
             for (int c = 0; c < 4; ++c) fM[c] = fl[ae][c];
           }
-          flux_dir(gm1, uP, d, fP);
+          if (o_gauss) flux_dir_fd(gm1, uP, d, fP); else flux_dir(gm1, uP, d, fP);
           cons_arr(Uf, uf); cons_arr(uP, up);
 #pragma unroll
           for (int c = 0; c < 4; ++c) BFL[e][c] = B * (0.5 * (fM[c] + fP[c])) - lamB * (up[c] - uf[c]);
+          if (DG) {
+            // both surface fluxes are Lax-Friedrichs on the projected values: BF_H (flux_differencing.jl:223-272) is the
+            // same expression on the same data, except that LFc = 0 on inflow/outflow faces (:116-151)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) BFH[e][c] = nb[e].bc ? B * (0.5 * (fM[c] + fP[c])) : BFL[e][c];
+          }
           if (MODE == MODE_SUBCELL && o_fstar) {   // fstar_L = f* - lf / B (apply_LF_dissipation_to_fstar, rhs_utils.jl:93-102)
             double *fo = o_fstar + ((k * (4 * N1D) + (2 * d + e) * N1D + line) * 2 + 1) * 4;
 #pragma unroll
@@ -627,7 +633,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
           }
         }
       }
-      if (!FAST) {
+      if (!FAST && !(DG && DO_LOW)) {
         // surface, flux_differencing.jl:90-151,223-272
 #pragma unroll
         for (int e = 0; e < 2; ++e) {

@@ -191,6 +191,11 @@ P2DE_DEV Prim2 prim_of_fd(double gm1, const Cons2 &U) {
   q.rholog = log(U.rho); q.betalog = log(q.beta);
   return q;
 }
+P2DE_DEV void flux_dir_fd(double gm1, const Cons2 &U, int d, double f[4]) {
+  double rinv = rcp_fast(U.rho);
+  double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+  flux_dir(U, U.m1 * rinv, U.m2 * rinv, p, d, f);
+}
 P2DE_DEV double wavespeed_dir_fd(double gamma, double gm1, const Cons2 &U, int d) {
   double rinv = rcp_fast(U.rho), mn = d == 0 ? U.m1 : U.m2;
   double p = gm1 * (U.E - 0.5 * (mn * mn) * rinv);

@@ -37,6 +37,30 @@ P2DE_DEV Cons2 u_vfun2(double gamma, double gm1, const double v[4]) {
   return W;
 }
 
+// The same two maps with the powers folded into one logarithm / one exponential
+//   s = log(p / rho^gamma) = log p - gamma log rho,
+//   rhoe(v) = ((gamma-1) / (-v4)^gamma)^(1/(gamma-1)) exp(-s/(gamma-1)) = exp((log(gamma-1) - gamma log(-v4) - s) / (gamma-1))
+// and Newton reciprocals: a few 1e-16 relative away from the reference's evaluation order (pow is ~2 ulp itself),
+// at a third of its cost; the projection kernel is nothing but these two functions.
+P2DE_DEV void v_ufun2_fd(double gamma, double gm1, const Cons2 &U, double v[4]) {
+  const double rinv = rcp_fast(U.rho);
+  const double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
+  const double s = log(p) - gamma * log(U.rho);
+  const double g = gm1 * rcp_fast(p);
+  v[0] = (gamma + 1 - s) - g * U.E;
+  v[1] = U.m1 * g; v[2] = U.m2 * g; v[3] = -U.rho * g;
+}
+P2DE_DEV Cons2 u_vfun2_fd(double gamma, double gm1, double log_gm1, const double v[4]) {
+  const double q = v[1] * v[1] + v[2] * v[2];
+  const double h = 0.5 * q * rcp_fast(v[3]);          // q / (2 v4)
+  const double sv = gamma - v[0] + h;
+  const double rhoeV = exp((log_gm1 - gamma * log(-v[3]) - sv) * rcp_fast(gm1));
+  Cons2 W;
+  W.rho = -rhoeV * v[3]; W.m1 = rhoeV * v[1]; W.m2 = rhoeV * v[2];
+  W.E = rhoeV * (1 - h);
+  return W;
+}
+
 template <int N1D, int EPB>
 __global__ void __launch_bounds__(EPB * 2 * N1D)
 gauss_project_kernel(const __grid_constant__ ProjArgs A, const __grid_constant__ MeshTopo M,
@@ -47,12 +71,12 @@ gauss_project_kernel(const __grid_constant__ ProjArgs A, const __grid_constant__
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
   const bool active = k < M.K;
-  const double gamma = A.gamma, gm1 = A.gamma - 1.0;
+  const double gamma = A.gamma, gm1 = A.gamma - 1.0, log_gm1 = log(gm1);
   if (active)
     for (int node = ln; node < Nq; node += TPE) {
       Cons2 U = load_cons(A.Uq + (k * Nq + node) * 4);
       double v[4];
-      v_ufun2(gamma, gm1, U, v);
+      v_ufun2_fd(gamma, gm1, U, v);
       double *pu = su + (el * Nq + node) * 4, *pv = sv + (el * Nq + node) * 4;
       pu[0] = U.rho; pu[1] = U.m1; pu[2] = U.m2; pu[3] = U.E;
       pv[0] = v[0]; pv[1] = v[1]; pv[2] = v[2]; pv[3] = v[3];
@@ -86,27 +110,31 @@ gauss_project_kernel(const __grid_constant__ ProjArgs A, const __grid_constant__
         }
       };
       // update_and_check_bound_limited_entropyproj_var_on_face_node! :100-130, check_bound_on_face_node :84-98
-      auto ok = [&](double th) {
+      // (returns u(v_tilde_f(theta)) too: the accepted theta's state is the kernel's output)
+      auto ok = [&](double th, Cons2 &ut) {
         double vt[4];
         vtilde(th, vt);
+        ut = u_vfun2_fd(gamma, gm1, log_gm1, vt);
         if (!(vt[3] < -A.POSTOL)) return false;
-        Cons2 ut = u_vfun2(gamma, gm1, vt);
         const double rhoe = rhoe2(ut);
         return vt[3] < jl_min(A.zeta * VUf[3], -A.POSTOL) && ut.rho > jl_max((1 - A.eta) * Uf[0], A.POSTOL) &&
                ut.rho < (1 + A.eta) * Uf[0] && rhoe > jl_max((1 - A.eta) * rhoef, A.POSTOL) && rhoe < (1 + A.eta) * rhoef;
       };
       double th = 1.0;
-      if (A.nodewise && !ok(1.0)) {   // bisection(f, 0.0, 1.0), nonlinear_solvers.jl:3-20
+      Cons2 ut;
+      const bool ok1 = ok(1.0, ut);           // NoEntropyProjectionLimiter: theta = 1 whatever the test says
+      if (A.nodewise && !ok1) {   // bisection(f, 0.0, 1.0), nonlinear_solvers.jl:3-20
         double xv = 0.0, xi = 1.0;
+        Cons2 tmp;
         for (int it = 0; it <= 20; ++it) {
           const double xn = 0.5 * (xv + xi);
-          if (ok(xn)) xv = xn; else xi = xn;
+          if (ok(xn, tmp)) xv = xn; else xi = xn;
         }
         th = xv;
+        double vt[4];
+        vtilde(th, vt);
+        ut = u_vfun2_fd(gamma, gm1, log_gm1, vt);
       }
-      double vt[4];
-      vtilde(th, vt);
-      Cons2 ut = u_vfun2(gamma, gm1, vt);
       double r[4] = {ut.rho, ut.m1, ut.m2, ut.E};
       store4(A.utf + (k * Nfp + f) * 4, r);
       if (A.theta_local) A.theta_local[k * Nfp + f] = th;

@@ -120,6 +120,7 @@ struct p2de_handle {
   double *VDM_inv = nullptr;                  // [Np, Nq] (Hennemann indicator)
   unsigned long long *smin_bits = nullptr;    // global min of s_modified at t0 (min-entropy bounds)
   int entropy_bound = 0;                      // 0 none, 1 min entropy, 2 relaxed min entropy
+  bool slim = false;                          // generic kernel in its compile-time Gauss configuration: FAST-family scratch
   int tvd = 0;                                // TVD*Bound: needs the low-order rhs of the neighbours (MODE_LOW pre-pass)
   int cell_entropy = 0;                       // 0 none, 1 cell entropy, 2 relaxed cell entropy
   double *rhsLpre = nullptr;                  // [K][Nq][4] (+ halo rows) low-order rhs of the pre-pass
@@ -477,9 +478,7 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
   if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, 0>;
   // the shipped-examples configuration on Gauss nodes has its options compiled in (kernels2d.cuh: CFG = 1)
-  const bool default_gauss = !FAST && MODE == MODE_SUBCELL && A.gauss && !A.roundtrip && A.vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR &&
-                             A.surf_low == P2DE_SURFFLUX_LF_PROJECTED && A.surf_high == P2DE_SURFFLUX_LF_PROJECTED && !A.hennemann &&
-                             !A.entropy_bound && !A.tvd && !A.cell_entropy && !A.fstar;
+  const bool default_gauss = !FAST && MODE == MODE_SUBCELL && h->slim;
   if constexpr (!FAST && MODE == MODE_SUBCELL) {
     if (default_gauss) kern = stage_kernel<N1D, MODE, EPB, 1>;
   }
@@ -562,7 +561,7 @@ int launch_update_fast(p2de_handle *h, const UpdateArgs &A) {
 }
 template <int N1D>
 int launch_update_n(p2de_handle *h, const UpdateArgs &A) {
-  if (h->mode == MODE_SUBCELL && h->fast) return launch_update_fast<N1D>(h, A);
+  if (h->mode == MODE_SUBCELL && (h->fast || h->slim)) return launch_update_fast<N1D>(h, A);
   if (h->mode == MODE_SUBCELL) return launch_update_t<N1D, MODE_SUBCELL>(h, A);
   return launch_update_t<N1D, MODE_LOW>(h, A);
 }
@@ -957,6 +956,9 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   h->gauss = !d1 && cfg->basis == P2DE_BASIS_GAUSS;
   h->nodewise = cfg->proj_limiter == P2DE_PROJLIM_NODEWISE;
   if (h->gauss) h->fast = false;
+  h->slim = h->gauss && mode == MODE_SUBCELL && !cfg->lgl_projection_roundtrip && cfg->vol_flux == P2DE_VOLFLUX_CHANDRASHEKAR &&
+            cfg->surf_flux_low == P2DE_SURFFLUX_LF_PROJECTED && cfg->surf_flux_high == P2DE_SURFFLUX_LF_PROJECTED &&
+            cfg->shockcapture == P2DE_SHOCKCAPTURE_NONE && cfg->bound == P2DE_BOUND_POSITIVITY;
   h->N1D = N1D; h->Nq = cfg->Nq; h->Nfp = cfg->Nfp; h->Nc = d1 ? 3 : 4; h->Nd = d1 ? 1 : 2; h->K = cfg->K; h->mode = mode;
   h->dim = cfg->dim;
   h->nLloc = d1 ? 2 * N1D : 2 * N1D * (N1D + 1);   // State.jl:21: zeros(Nq + N1D, Nd, K, Ns); 1D uses the first Nq+1
@@ -1009,6 +1011,8 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
       h->direct = !(nd && atoi(nd));
       const char *nf = getenv("P2DE_NO_DEFER");    // testing / A-B aid: materialise U1 with the axpy kernel
       h->defer = h->direct && !(nf && atoi(nf));
+    } else if (h->slim) {
+      if ((rc = dev_alloc(h, &h->rpre, nU)) || (rc = dev_alloc(h, &h->dFend, (size_t)h->K * h->Nfp * 4))) return bail(rc);
     } else if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)h->K * 2 * N1D * (N1D + 1) * 4)))
       return bail(rc);
     if (h->tvd && (rc = dev_alloc_halo(h, &h->rhsLpre, nU, rowU))) return bail(rc);

@@ -201,8 +201,8 @@ constexpr int stage_smem_doubles_per_elem() {
 // extra shared memory of the TVD / cell-entropy bounds (allocated only when the bound is on): rhoL [S], its ghosts
 // [2][S], and per direction dvdf, dv.f_bar_L and the interior coefficients [2][Nq - N1D] each
 template <int N1D>
-constexpr int stage_smem_extra_doubles_per_elem(bool tvd, bool cell) {
-  return (tvd ? 3 * N1D * N1D : 0) + (cell ? 6 * N1D * (N1D - 1) : 0);
+constexpr int stage_smem_extra_doubles_per_elem(bool tvd, bool cell, bool slim = false) {
+  return (tvd ? 3 * N1D * N1D : 0) + (cell ? 6 * N1D * (N1D - 1) : 0) + (slim ? 8 * N1D * N1D : 0);
 }
 
 // s_modified_ufun, compressible_Navier_Stokes.jl:80-85
@@ -335,6 +335,12 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   double *esF = esD + EPB * 2 * NE;               // [EPB][2][NE] dv . f_bar_L
   double *esL = esF + EPB * 2 * NE;               // [EPB][2][NE] interior coefficients
   const bool need_ind = o_hennemann || o_entropy_bound == 2 || o_cell_entropy == 2;
+  // CFG = 1 writes the slim scratch of the FAST family (un-symmetrised limited rhs + end-face dF, consumed by
+  // update_kernel_fast) instead of rhsL + every subcell face's dF: 84 instead of 132 B/node out, 84 instead of 196 B/node
+  // into the update kernel.  (No TVD / cell-entropy arrays in that configuration: the shares take their place.)
+  constexpr bool SLIM = DG && MODE == MODE_SUBCELL;
+  double *shr = nodes + 4 * S;                    // [S][2][4] the two directions' shares of the limited rhs: node fields 4..11 are
+                                                  // only read in the line phase, two barriers earlier (no extra shared memory)
 
   const int tid = threadIdx.x, el = tid / TPE, ln = tid % TPE, d = ln / N1D, line = ln % N1D;
   const long long k = (long long)blockIdx.x * EPB + el;
@@ -762,7 +768,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
     if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
   }
 
-  if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && o_cell_entropy)) return;
+  if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && (o_cell_entropy || SLIM))) return;
 
   if (MODE == MODE_SUBCELL) {
     // ---- subcell limiter, element-local part: f_bar prefix sums (subcell.jl:163-206) and the
@@ -802,7 +808,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
       }
       c0[a] = quad_coeff_c(uL[a], Lrhoe[a]);
       if (d == 0) {
-        store4(A.rhsL + (k * Nq + node) * 4, r);
+        if (!SLIM) store4(A.rhsL + (k * Nq + node) * 4, r);
         if (A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + node) * 4, r);
       }
     }
@@ -871,6 +877,43 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
 #pragma unroll
         for (int s = 1; s < N1D; ++s) lv[s] = esL[(el * 2 + d) * NE + (d == 0 ? (s - 1) + line * (N1D - 1) : line + (s - 1) * N1D)];
       }
+    }
+    if (SLIM) {
+      if (active) {
+        // this line's share of the un-symmetrised limited rhs: rhsxyL_d + (l_{a+1} dF_{a+1} - l_a dF_a) / wJ (subcell.jl:841-924)
+#pragma unroll
+        for (int a = 0; a < N1D; ++a) {
+          const int node = d == 0 ? a + line * N1D : line + a * N1D;
+          double t[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) t[c] = GL[a][c] * rwJ[a] + (lv[a + 1] * dFv[a + 1][c] - lv[a] * dFv[a][c]) * rwJ[a];
+          store4(shr + ((nbase + node) * 2 + d) * 4, t);
+        }
+        store4(A.dFend + (k * (4 * N1D) + (2 * d + 0) * N1D + line) * 4, dFv[0]);
+        store4(A.dFend + (k * (4 * N1D) + (2 * d + 1) * N1D + line) * 4, dFv[N1D]);
+        double *ldst = A.lpre + (k * 2 + d) * (N1D * NF);
+#pragma unroll
+        for (int s = 0; s < NF; ++s) ldst[d == 0 ? s + line * NF : line + s * N1D] = lv[s];
+        if (A.rhsH_diag) {
+#pragma unroll
+          for (int a = 0; a < N1D; ++a) {
+            int node = d == 0 ? a + line * N1D : line + a * N1D;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) atomicAdd(A.rhsH_diag + (k * Nq + node) * 4 + c, GH[a][c] * rwJ[a]);
+          }
+        }
+      }
+      __syncthreads();
+      if (active && d == 0) {
+#pragma unroll
+        for (int a = 0; a < N1D; ++a) {
+          const int node = a + line * N1D;
+          const double *x = shr + (nbase + node) * 8;
+          double r[4] = {x[0] + x[4], x[1] + x[5], x[2] + x[6], x[3] + x[7]};
+          store4(A.rpre + (k * Nq + node) * 4, r);
+        }
+      }
+      return;
     }
     if (!active) return;
     double *dst = A.dF + ((k * 2 + d) * N1D + line) * (NF * 4);

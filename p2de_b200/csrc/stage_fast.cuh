@@ -806,7 +806,8 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
       if (lsym != lv) {   // the neighbour limits this face harder than this element did
         const double w = (e ? (lsym - lv) : -(lsym - lv)) * s_rwJ[s_fq2q[f]];
         Cons2 t = load_cons(A.dFend + (k * Nfp + f) * 4);    // rotated frame of axis d
-        c[0] = w * t.rho; c[1 + d] = w * t.m1; c[2 - d] = w * t.m2; c[3] = w * t.E;
+        const int dd = A.rotated ? d : 0;                    // (the generic stage kernel's dFend is not rotated)
+        c[0] = w * t.rho; c[1 + dd] = w * t.m1; c[2 - dd] = w * t.m2; c[3] = w * t.E;
       } else { c[0] = 0.0; c[1] = 0.0; c[2] = 0.0; c[3] = 0.0; }   // dFend is not even read
       if (A.Llocal_out) A.Llocal_out[k * NL + lidx] = lsym;
     }

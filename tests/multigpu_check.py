@@ -15,7 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as P  # noqa: E402
-from p2de_b200 import SubcellLimiter, ZhangShuLimiter  # noqa: E402
+from p2de_b200 import (ESLimitedLowOrderPos, GaussCollocation, LaxFriedrichsOnProjectedVal,  # noqa: E402
+                       NodewiseScaledExtrapolation, SubcellLimiter, ZhangShuLimiter)
 from p2de_b200.api import State  # noqa: E402
 from p2de_b200.partition import local_bcdata, local_param, stripe_rows  # noqa: E402
 from p2de_b200.types import Solver  # noqa: E402
@@ -32,7 +33,11 @@ def main():
              ("kh-periodic-zhangshu", P.kelvin_helmholtz(N=3, K=(8, 8), limiter=ZhangShuLimiter()), (True, True)),
              # wide enough for batches strictly inside the mesh: on one GPU the rows next to the cut run the kernel's
              # compile-time INTERIOR version, in the stripes its general version (same arithmetic, different instantiation)
-             ("dmr-wide-subcell", P.dmr(N=3, K=(64, 8)), (False, False))]
+             ("dmr-wide-subcell", P.dmr(N=3, K=(64, 8)), (False, False)),
+             # the shipped-examples configuration (Gauss + NodewiseScaledExtrapolation): projected face states and the
+             # un-symmetrised coefficients travel with the halo rows
+             ("kh-gauss-nodewise-subcell", P.kelvin_helmholtz(N=2, K=(8, 8), basis=GaussCollocation(), entropyproj_limiter=NodewiseScaledExtrapolation(),
+                                                           rhs=ESLimitedLowOrderPos(LaxFriedrichsOnProjectedVal(), LaxFriedrichsOnProjectedVal())), (True, True))]
     for name, problem, periodic in cases:
         param, rd, md, dd, bc, U0 = P.setup(problem)
         Kx, Ky = param.K

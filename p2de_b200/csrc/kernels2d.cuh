@@ -19,6 +19,11 @@
 // its line without talking to anyone; x- and y-lines meet through shared memory only for
 // rhsL = rhs_x + rhs_y (needed for u^L), the CFL sum and the final rhsU.
 // Direction is data, not control flow: both kinds of lines run the same instruction stream.
+//
+// stage_kernel here is the GENERIC variant: every option of the reference (flux choices, Gauss collocation with the
+// projected face states of gauss.cuh, Hennemann shock capturing, all ten subcell bounds) as run-time values of
+// StageArgs, in the reference's operation order; CFG = 1 instantiates it with the options of the reference's shipped 2D
+// examples fixed at compile time.  The default Lobatto configuration has its own kernel (stage_fast.cuh).
 #pragma once
 #include "physics.cuh"
 

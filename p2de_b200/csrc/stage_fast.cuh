@@ -11,7 +11,13 @@
 //     lets ptxas interleave the independent node-pair chains (operands are positive normals);
 //   * with the identity LGL projection the low- and high-order surface fluxes coincide, so an
 //     interior face contributes nothing to f_H - f_L; only inflow/outflow faces do;
-//   * phases are ordered so that at most one 4-node accumulator set is live at a time.
+//   * phases are ordered so that at most one 4-node accumulator set is live at a time;
+//   * that exact zero also makes the interface coefficients 1 on both sides of every interior face, so the
+//     limiter's symmetrisation is the identity and no second kernel follows (see "End faces" below);
+//   * the body is compiled per CTA kind: INTERIOR batches (strictly inside a structured mesh) have no
+//     boundary-condition code at all; DEFER (its own kernel) forms the stage-1 SSP combine while loading;
+//   * an L2 prefetch of the batch one wave of resident CTAs ahead, table loads overlapped with the state loads,
+//     a branch-free first pass of the limiter over the whole line (profiles/README.md has each step's measurement).
 #pragma once
 #include <type_traits>
 #include "kernels2d.cuh"

@@ -110,3 +110,34 @@ def test_new_bounds_keep_conservation_and_symmetric_interfaces(bound):
     Ly = L[:, :, 1, :].reshape(Ky, Kx, N1D + 1, N1D)
     assert np.array_equal(Lx[:, :, :, N1D], np.roll(Lx[:, :, :, 0], -1, axis=1))
     assert np.array_equal(Ly[:, :, N1D, :], np.roll(Ly[:, :, 0, :], -1, axis=0))
+
+
+# ---- 1D (subcell.jl:37-53,93-118,466-500,568-610: the Dim1 methods of the same bounds; no GPU kernel yet) ------------------
+@pytest.mark.parametrize("bound", [TVDBound(), TVDAndMinEntropyBound()], ids=lambda b: type(b).__name__)
+@pytest.mark.parametrize("problem", ["shu-osher", "wave"])
+def test_1d_tvd_bounds_hold_for_the_limited_update(bound, problem):
+    prob = P.shu_osher(N=3, K=64, limiter=SubcellLimiter(bound=bound)) if problem == "shu-osher" else \
+        P.density_wave_1d(N=3, K=16, limiter=SubcellLimiter(bound=bound))
+    param, dd, orc, U0, dt = one_rhs(prob)
+    rho_new = (U0 + dt * orc.field("rhsU"))[:, :, 0]
+    lb = orc.field("lbound_rho").reshape(rho_new.shape)
+    ub = orc.field("ubound_rho").reshape(rho_new.shape)
+    assert (rho_new >= lb - 1e-13).all() and (rho_new <= ub + 1e-13).all()
+    assert (orc.field("L_local")[0][:, 0, :param.N + 2] < 1).any()
+
+
+@pytest.mark.parametrize("bound", [PositivityAndCellEntropyBound(), PositivityAndRelaxedCellEntropyBound(beta=0.5)],
+                         ids=lambda b: type(b).__name__)
+def test_1d_cell_entropy_inequality_holds_after_enforcement(bound):
+    param, dd, orc, U0, dt = one_rhs(P.density_wave_1d(N=3, K=16, limiter=SubcellLimiter(bound=bound)))
+    N1D = param.N + 1
+    L = orc.field("L_local")[0][:, 0, :N1D + 1]
+    dv = orc.field("dvdf_x").reshape(-1, N1D)[:, :N1D - 1]
+    sB = orc.field("sum_Bpsi").reshape(-1)
+    sL = orc.field("sum_dvfbarL").reshape(-1)
+    eps = orc.field("smooth_factor").reshape(3, -1)[0]
+    rhs = (1 - 0.5 * eps if "Relaxed" in type(bound).__name__ else 1.0) * (sB - sL)
+    tol = np.maximum(0.0, sL - sB)
+    lhs = (L[:, 1:N1D] * dv).sum(1)
+    assert (lhs - rhs - tol <= 1e-12 * (np.abs(L[:, 1:N1D] * dv).sum(1) + np.abs(rhs) + 1e-300)).all()
+    assert (L < 1).any() and (L >= 0).all()

@@ -1265,6 +1265,8 @@ int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8
   if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, P2DE_ERR_ARG, "rank %d of %d", rank, nranks);
   if (h->topo.mapP32 || h->dim == 1) return fail(h, P2DE_ERR_UNSUPPORTED, "multi-GPU needs the structured 2D mesh path (y-stripes)");
   if (h->comm) return fail(h, P2DE_ERR_STATE, "communicator already initialised");
+  if (h->fstar && nranks > 1)   // the interface bisection reads the neighbour's fstar_H / fstar_L, which have no halo rows
+    return fail(h, P2DE_ERR_UNSUPPORTED, "cell-entropy bounds on Gauss nodes are single-GPU in this build");
   h->rank = rank; h->nranks = nranks;
   if (nranks == 1) return P2DE_OK;
   std::string why;

@@ -74,7 +74,9 @@ def main():
                 same = np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max() and np.allclose(dts, dts2, rtol=1e-14, atol=0)
             print(f"[multigpu_check] {name}: world={world} bitwise_equal={same} max|diff|={np.abs(got - ref).max():.3e} dt={dts[-1]:.6e}")
             ok = ok and same
+            full.close()
         dist.barrier()
+        st.close()          # ncclCommDestroy: one library communicator per case, not five alive at once
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

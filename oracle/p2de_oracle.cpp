@@ -23,6 +23,11 @@
 //   D3  Julia `min`/`max` propagate NaN; jl_min/jl_max below do the same.
 //   D4  NodewiseScaledExtrapolation (filter.jl) is broken at HEAD by argument shadowing; restated from
 //       the evident intent (see compute_entropyproj_limiting_param).
+//   D5  enforce_ES_subcell_interface! (subcell.jl:718-805, Gauss nodes) reads the partner element's coefficient inside
+//       a threaded loop over elements while the partner may be rewriting it; restated in element order (what one
+//       Julia thread does).  NOT changed: its inequality l dv.f*_H + (1-l) dv.f*_L <= dpsi uses dv = v_f - v_fP and
+//       dpsi = psi_f - psi_fP from the point of view of BOTH sides of a face, i.e. with opposite signs, so wherever the
+//       two states differ one side fails for every l and the coefficient ends at 0 (tests/test_gpu_bounds.py).
 #include <algorithm>
 #include <array>
 #include <cmath>

@@ -474,7 +474,8 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   const size_t base = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
   const bool sub = !FAST && MODE == MODE_SUBCELL;
   size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
-  if (const char *pad = getenv("P2DE_SMEM_PAD")) smem += (size_t)atoi(pad);   // profiling aid: lowers the number of resident CTAs
+  static const size_t smem_pad = [] { const char *pad = getenv("P2DE_SMEM_PAD"); return pad ? (size_t)atoi(pad) : (size_t)0; }();
+  smem += smem_pad;   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
   if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, 0>;
   // the shipped-examples configuration on Gauss nodes has its options compiled in (kernels2d.cuh: CFG = 1)

@@ -141,3 +141,49 @@ def test_1d_cell_entropy_inequality_holds_after_enforcement(bound):
     lhs = (L[:, 1:N1D] * dv).sum(1)
     assert (lhs - rhs - tol <= 1e-12 * (np.abs(L[:, 1:N1D] * dv).sum(1) + np.abs(rhs) + 1e-300)).all()
     assert (L < 1).any() and (L >= 0).all()
+
+
+# ---- x <-> y symmetry: the y-direction code of every bound against its x-direction code ------------------------------------
+def _transpose_problem(problem):
+    """The same flow with the roles of x and y exchanged: K = (Ky, Kx), data(x, y) = swap_uv(data0(y, x))."""
+    param, ic, bc = problem
+    import dataclasses
+    pT = dataclasses.replace(param, K=(param.K[1], param.K[0]), xL=(param.xL[1], param.xL[0]), xR=(param.xR[1], param.xR[0]))
+
+    def icT(prm, x, y):
+        U = ic(param, y, x)
+        return (U[0], U[2], U[1], U[3])
+    return pT, icT, bc
+
+
+@pytest.mark.parametrize("bound", [PositivityBound(), TVDBound(), PositivityAndCellEntropyBound(),
+                                   TVDAndRelaxedCellEntropyBound(beta=0.5), TVDAndMinEntropyBound()], ids=lambda b: type(b).__name__)
+def test_bounds_are_symmetric_under_exchange_of_x_and_y(bound):
+    prob = P.wave2d(N=3, K=(5, 4), limiter=SubcellLimiter(bound=bound))
+    param, dd, orc, U0, dt = one_rhs(prob)
+    paramT, ddT, orcT, U0T, _ = one_rhs(_transpose_problem(prob))
+    n = param.N + 1
+    Kx, Ky = param.K
+
+    def to_T(F):   # [K, Nq, 4] of the original -> layout of the transposed problem
+        G = F.reshape(Ky, Kx, n, n, 4).transpose(1, 0, 3, 2, 4)        # element (iy, ix) -> (ix, iy); node (j, i) -> (i, j)
+        return G[..., [0, 2, 1, 3]].reshape(Kx * Ky, n * n, 4)
+    assert np.abs(to_T(U0) - U0T).max() < 1e-14
+    for f in ("rhsL", "rhsH", "rhsU"):
+        a, b = to_T(orc.field(f)), orcT.field(f)
+        assert np.abs(a - b).max() < 1e-11 * np.abs(b).max(), f
+    L, LT = orc.field("L_local")[0].reshape(Ky, Kx, 2, -1), orcT.field("L_local")[0].reshape(Kx, Ky, 2, -1)
+    Lx = L[:, :, 0, :].reshape(Ky, Kx, n, n + 1)          # [iy, ix, sj, si]
+    Ly = L[:, :, 1, :].reshape(Ky, Kx, n + 1, n)          # [iy, ix, sj, si]
+    LTx = LT[:, :, 0, :].reshape(Kx, Ky, n, n + 1)
+    LTy = LT[:, :, 1, :].reshape(Kx, Ky, n + 1, n)
+    # the original's x faces (si, sj) are the transposed problem's y faces (si' = sj, sj' = si) and vice versa; faces whose
+    # f_bar_H - f_bar_L is rounding noise are excluded (TVD coefficients there are 0 or 1 by the sign of the noise)
+    def sig(o, ax, shape):
+        fH = o.field(f"f_bar_H_{ax}").reshape(-1, n * n + n, 4); fL = o.field(f"f_bar_L_{ax}").reshape(-1, n * n + n, 4)
+        return (np.abs(fH - fL).max(-1) > 1e-10 * np.abs(fH).max()).reshape(shape)
+    sx = sig(orc, "x", (Ky, Kx, n, n + 1))
+    sy = sig(orc, "y", (Ky, Kx, n + 1, n))
+    dx = (Lx.transpose(1, 0, 3, 2) - LTy) * sx.transpose(1, 0, 3, 2)
+    dy = (Ly.transpose(1, 0, 3, 2) - LTx) * sy.transpose(1, 0, 3, 2)
+    assert np.abs(dx).max() < 1e-9 and np.abs(dy).max() < 1e-9

@@ -39,7 +39,7 @@ def test_stripes_tile_the_mesh_and_bc_lists_are_renumbered():
     assert nI == len(bc.mapI) and nO == len(bc.mapO)
 
 
-def _gloo_worker(rank, world, port, q):
+def _gloo_worker(rank, world, port, q, periodic=True):
     """Two ranks exchange their boundary element rows the way the library does over NCCL and
     check that the halo row equals the neighbour's owned row of the global array; the CFL dt is
     min-all-reduced."""
@@ -53,14 +53,19 @@ def _gloo_worker(rank, world, port, q):
     iy0, iy1 = stripe_rows(Ky, rank, world)
     mine = U[iy0 * Kx:iy1 * Kx]
     bottom, top = halo_rows(mine, Kx)
-    lo, hi = (rank - 1) % world, (rank + 1) % world             # periodic in y
+    lo, hi = (rank - 1) % world, (rank + 1) % world             # p2de_comm_init: rank_lo, rank_hi
+    has_lo, has_hi = periodic or rank > 0, periodic or rank < world - 1
     ghost_lo, ghost_hi = torch.empty(Kx, Nq, 4, dtype=torch.float64), torch.empty(Kx, Nq, 4, dtype=torch.float64)
-    reqs = [dist.isend(torch.from_numpy(np.ascontiguousarray(top)), hi), dist.isend(torch.from_numpy(np.ascontiguousarray(bottom)), lo),
-            dist.irecv(ghost_lo, lo), dist.irecv(ghost_hi, hi)]      # same issue order as exchange_rows (capi.cu)
+    reqs = []                                                   # same issue order as exchange_rows (capi.cu)
+    if has_hi: reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(top)), hi))
+    if has_lo: reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(bottom)), lo))
+    if has_lo: reqs.append(dist.irecv(ghost_lo, lo))
+    if has_hi: reqs.append(dist.irecv(ghost_hi, hi))
     for r in reqs:
         r.wait()
-    ok = np.array_equal(ghost_lo.numpy(), U[((iy0 - 1) % Ky) * Kx:((iy0 - 1) % Ky + 1) * Kx])
-    ok &= np.array_equal(ghost_hi.numpy(), U[(iy1 % Ky) * Kx:(iy1 % Ky + 1) * Kx])
+    ok = True
+    if has_lo: ok &= np.array_equal(ghost_lo.numpy(), U[((iy0 - 1) % Ky) * Kx:((iy0 - 1) % Ky + 1) * Kx])
+    if has_hi: ok &= np.array_equal(ghost_hi.numpy(), U[(iy1 % Ky) * Kx:(iy1 % Ky + 1) * Kx])
     dt = torch.tensor([0.1 * (rank + 1)], dtype=torch.float64)
     dist.all_reduce(dt, op=dist.ReduceOp.MIN)
     ok &= float(dt) == 0.1
@@ -68,16 +73,20 @@ def _gloo_worker(rank, world, port, q):
     q.put((rank, bool(ok)))
 
 
-def test_halo_exchange_order_and_dt_allreduce_gloo_world2():
+@pytest.mark.parametrize("world,periodic", [(2, True), (2, False), (4, True), (4, False)],
+                         ids=["world2-periodic", "world2-open", "world4-periodic", "world4-open"])
+def test_halo_exchange_order_and_dt_allreduce_gloo(world, periodic):
+    """world 2, periodic: both neighbours are the same rank; world 4: distinct neighbours, and with open ends the first and
+    last stripe have one neighbour only (the cases of has_lo / has_hi in p2de_comm_init)."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 400)
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 400) + 7 * world + int(periodic)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, q, periodic)) for r in range(world)]
     [p.start() for p in procs]
-    res = sorted(q.get(timeout=120) for _ in procs)
+    res = sorted(q.get(timeout=180) for _ in procs)
     [p.join(timeout=60) for p in procs]
-    assert res == [(0, True), (1, True)]
+    assert res == [(r, True) for r in range(world)]
 
 
 @pytest.mark.gpu

@@ -43,7 +43,7 @@ WORKLOADS = {
     "S-KH-gauss": dict(problem="kelvin_helmholtz", N=3, K=(2048, 512), gauss=True,
                        note="Kelvin-Helmholtz, N=3 Gauss + NodewiseScaledExtrapolation, 2048x512 per GPU, periodic (generic kernels)"),
 }
-CPU_SAMPLE_K = (512, 128)    # bounded sample of the same workload for the CPU arm (39 kB of state per element)
+CPU_SAMPLE_K = (1024, 256)   # bounded sample of the same workload for the CPU arm: 4.2 M nodes, ~0.5 s per step on 16 cores
 
 
 def peaks():
@@ -342,7 +342,7 @@ def run_ours(args):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.workload, steps=2, warmup=1)
+            out["cpu_baseline"] = cpu_baseline(args.workload, steps=6, warmup=1)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
@@ -350,29 +350,36 @@ def run_ours(args):
 
 
 def cpu_baseline(workload, steps, warmup):
-    """The oracle (C++/OpenMP restatement of the reference's CPU algorithm) on all host cores,
-    on a bounded sample of the same workload."""
+    """The oracle (C++/OpenMP restatement of the reference's CPU algorithm) on all host cores, on a bounded sample of
+    the same workload: built here with -O3 -march=native -ffp-contract=off, threads pinned (OMP_PROC_BIND=close, set in
+    main() before the OpenMP runtime loads), per-phase wall time under the reference's TimerOutputs labels."""
     import problems as P
-    from oracle.oracle import Oracle, lib as oracle_lib
+    from oracle import oracle as O
+    flags = O.use_native_build()
     K = CPU_SAMPLE_K
     param, ic, bcf = build_problem(workload, K)
     param_, rd, md, dd, bc, U0 = P.setup((param, ic, bcf))
-    cores = os.cpu_count() or 1
-    orc = Oracle(param, dd, bc, threads=cores)
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc = O.Oracle(param, dd, bc, threads=cores)
     orc.set_state(U0)
     t = param.timestepping_param.t0
     for _ in range(warmup):
         t += orc.ssp33_step(t)
+    orc.phase_times(reset=True)
     t0 = time.perf_counter()
     for _ in range(steps):
         t += orc.ssp33_step(t)
     el = time.perf_counter() - t0
+    phases = orc.phase_times()
     sz = dd.sizes
     v = 3.0 * sz.K * sz.Nq * steps / el
-    return {"value": v, "unit": UNIT, "cores": int(oracle_lib().oracle_max_threads()), "kind": "port",
+    return {"value": v, "unit": UNIT, "cores": int(O.lib().oracle_max_threads()), "kind": "port",
             "sample": f"{workload} data on a {K[0]}x{K[1]} mesh (N={param.N}, {sz.K * sz.Nq} nodes), {steps} SSP-RK3 steps after {warmup} warm-up; "
                       "C++/OpenMP restatement of the reference's CPU algorithm (Julia is not installed on this image)",
-            "ms_per_step": el / steps * 1e3}
+            "same_config": False, "build": flags, "omp_proc_bind": os.environ.get("OMP_PROC_BIND"),
+            "ms_per_step": el / steps * 1e3,
+            # seconds per SSP-RK3 step under the reference's TimerOutputs labels (rhs.jl:6-51, limiter.jl:9-51, SSPRK33.jl:29)
+            "phase_ms_per_step": {k: round(1e3 * x / steps, 3) for k, x in phases.items()}}
 
 
 def run_reference(args):
@@ -402,6 +409,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel A/B runs)")
     args = ap.parse_args()
+    os.environ.setdefault("OMP_PROC_BIND", "close")     # CPU arm: pinned threads (read when libgomp loads)
+    os.environ.setdefault("OMP_PLACES", "cores")
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -222,6 +222,22 @@ int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8
 int32_t p2de_profile(p2de_handle *h, int32_t enable);
 int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, int64_t *launches);
 
+/* Debug / evidence counters of the 2D FAST stage kernel (tests assert that the compile-time INTERIOR and deferred-
+ * combine instantiations the benchmark times really ran; bench.py reports how much data-dependent work a workload
+ * skips).  enable != 0 starts counting from zero, 0 stops; `out` (may be NULL) receives the current values:       */
+enum {
+  P2DE_DBG_CTA_GENERAL = 0,    /* CTAs that ran the general instantiation (boundary conditions, partial batches) */
+  P2DE_DBG_CTA_INTERIOR = 1,   /* CTAs that ran the INTERIOR instantiation                                        */
+  P2DE_DBG_CTA_DEFER = 2,      /* CTAs (of either kind) that formed the stage-1 SSP combine while loading         */
+  P2DE_DBG_ELEM_LOGS = 3,      /* elements whose log(rho), log(beta) were evaluated (logmean off its series branch possible) */
+  P2DE_DBG_ELEM = 4,           /* elements processed                                                              */
+  P2DE_DBG_LINES = 5,          /* grid lines that ran the subcell limiter                                         */
+  P2DE_DBG_LINES_NOT_EASY = 6, /* ... of which some coefficient needed the exact evaluation                       */
+  P2DE_DBG_LIMITER_SLOW = 7,   /* evaluations that solved the quadratic (limiter_utils.jl:52-76)                  */
+  P2DE_DBG_COUNT = 8
+};
+int32_t p2de_debug_counters(p2de_handle *h, int32_t enable, uint64_t out[P2DE_DBG_COUNT]);
+
 /* Number of kernels this handle has launched so far (bench.py reports it).            */
 int64_t p2de_kernel_launch_count(const p2de_handle *h);
 /* Device pointer of Uq (for zero-copy wrapping by the host, e.g. torch.from_dlpack).  */

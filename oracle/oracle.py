@@ -17,23 +17,42 @@ sys.path.insert(0, os.path.dirname(_HERE))
 from p2de_b200.abi import BCDataC, Config, GeometryC, OperatorsC, PackedProblem  # noqa: E402
 
 _LIB = None
+_NATIVE = False
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "libp2de_oracle.so")
+def build(force: bool = False, native: bool = False) -> str:
+    """`native`: the -O3 -march=native build for bench.py's CPU arm, compiled on the machine that runs it
+    (oracle/Makefile); otherwise the portable -O2 build the tests check against."""
+    so = os.path.join(_HERE, "libp2de_oracle_native.so" if native else "libp2de_oracle.so")
     src = os.path.join(_HERE, "p2de_oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "p2de_b200.h")
     stale = (not os.path.exists(so)) or any(
         os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr))
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["native"] if native else []) + (["-B"] if force else []))
     return so
+
+
+def use_native_build():
+    """bench.py's CPU arm: load the -O3 -march=native build (must be called before the first Oracle is made).
+    Falls back to the portable build if it cannot be compiled here; returns the flags actually in use."""
+    global _NATIVE
+    assert _LIB is None, "use_native_build() must precede the first use of the oracle"
+    try:
+        build(native=True)
+        _NATIVE = True
+        return "-O3 -march=native -ffp-contract=off -fopenmp"
+    except Exception:
+        _NATIVE = False
+        return "-O2 -ffp-contract=off -fopenmp"
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        L = C.CDLL(build(native=_NATIVE))
+        L.oracle_phase_times.restype = C.c_int64
+        L.oracle_phase_times.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32]
         L.oracle_create.restype = C.c_void_p
         L.oracle_create.argtypes = [C.POINTER(Config), C.POINTER(OperatorsC), C.POINTER(GeometryC), C.POINTER(BCDataC)]
         L.oracle_destroy.argtypes = [C.c_void_p]
@@ -98,6 +117,17 @@ class Oracle:
 
     def reduce(self, what):
         return self.L.oracle_reduce(self.h, what)
+
+    def phase_times(self, reset=False):
+        """Seconds per phase under the reference's TimerOutputs labels, in first-use order."""
+        n = self.L.oracle_phase_times(self.h, None, 0, 0)
+        buf = C.create_string_buffer(int(n))
+        self.L.oracle_phase_times(self.h, buf, n, int(reset))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            k, v = line.split("\t")
+            out[k] = float(v)
+        return out
 
     def field(self, name, shape=None):
         n = self.L.oracle_get_field(self.h, name.encode(), None, 0)

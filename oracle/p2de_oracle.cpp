@@ -188,7 +188,25 @@ double bisection(F f, double x_valid, double x_invalid) {
   return x_valid;
 }
 
+// Wall-clock per phase, under the reference's TimerOutputs labels (rhs.jl:6-51, limiter.jl:9-51,
+// SSPRK33.jl:29): what `@timeit_debug timer "..."` would report.  Read with oracle_phase_times.
+struct PhaseTimers {
+  std::vector<std::pair<std::string, double>> acc;
+  double &slot(const char *name) {
+    for (auto &p : acc) if (p.first == name) return p.second;
+    acc.emplace_back(name, 0.0);
+    return acc.back().second;
+  }
+  void clear() { acc.clear(); }
+};
+struct PhaseScope {
+  double &dst; double t0;
+  PhaseScope(PhaseTimers &T, const char *name) : dst(T.slot(name)), t0(omp_get_wtime()) {}
+  ~PhaseScope() { dst += omp_get_wtime() - t0; }
+};
+
 struct OracleBase {
+  PhaseTimers timers;
   virtual ~OracleBase() {}
   virtual void set_state(const double *U) = 0;
   virtual void get_state(double *U) = 0;
@@ -1337,20 +1355,20 @@ struct Oracle : OracleBase {
   // ------------------------------------------------------------------ limiter.jl:8-56
   void apply_rhs_limiter(double t, double dt, int nstage) {
     if (cfg.limiter == P2DE_LIMITER_ZHANGSHU) {
-      initialize_smoothness_indicator();
-      update_blending_factor(nstage);
-      apply_zhang_shu(dt, nstage);
+      { PhaseScope ps(timers, "Initialize smoothness indicator"); initialize_smoothness_indicator(); }
+      { PhaseScope ps(timers, "calculate blending factor"); update_blending_factor(nstage); }
+      { PhaseScope ps(timers, "Apply Zhang-Shu limiter"); apply_zhang_shu(dt, nstage); }
     } else if (cfg.limiter == P2DE_LIMITER_SUBCELL) {
-      initialize_smoothness_indicator();
-      update_blending_factor(nstage);
-      update_smoothness_factor(nstage);
-      initialize_entropy_bounds(t, nstage);
-      initialize_TVD_bounds(dt);
-      accumulate_f_bar();
-      subcell_bound_limiter(dt, nstage);
-      enforce_ES_subcell(nstage);
-      symmetrize(nstage);
-      apply_subcell(nstage);
+      { PhaseScope ps(timers, "Initialize smoothness indicator"); initialize_smoothness_indicator(); }
+      { PhaseScope ps(timers, "calculate blending factor"); update_blending_factor(nstage); }
+      { PhaseScope ps(timers, "calculate smoothness factor"); update_smoothness_factor(nstage); }
+      { PhaseScope ps(timers, "Precompute bounds on modified s"); initialize_entropy_bounds(t, nstage); }
+      { PhaseScope ps(timers, "Precompute TVD bounds"); initialize_TVD_bounds(dt); }
+      { PhaseScope ps(timers, "Accumulate low and high order subcell fluxes"); accumulate_f_bar(); }
+      { PhaseScope ps(timers, "Find subcell limiting parameters"); subcell_bound_limiter(dt, nstage); }
+      { PhaseScope ps(timers, "Find subcell limiting parameters for entropy stability"); enforce_ES_subcell(nstage); }
+      { PhaseScope ps(timers, "Symmetrize subcell limiting parameters"); symmetrize(nstage); }
+      { PhaseScope ps(timers, "Apply subcell limiter, accumulate limited rhs"); apply_subcell(nstage); }
     }
   }
   void apply_limiter_only(double t, double dt, int nstage) override { apply_rhs_limiter(t, dt, nstage); }
@@ -1358,21 +1376,29 @@ struct Oracle : OracleBase {
   // ------------------------------------------------------------------ rhs.jl:5-55
   double rhs(double t, double dt_in, int nstage) override {
     double dt = dt_in;
-    if (cfg.proj_limiter == P2DE_PROJLIM_NODEWISE) compute_entropyproj_limiting_param(nstage);   // init_rhs! :15-19
+    PhaseScope all(timers, "rhs calculation");
+    if (cfg.proj_limiter == P2DE_PROJLIM_NODEWISE) {   // init_rhs! :15-19
+      PhaseScope ps(timers, "compute entropy projection limiting parameters");
+      compute_entropyproj_limiting_param(nstage);
+    }
     switch (cfg.rhs_type) {
-      case P2DE_RHS_LOW_ORDER_POSITIVITY:
+      case P2DE_RHS_LOW_ORDER_POSITIVITY: {
+        PhaseScope ps(timers, "low order positivity");
         dt = rhs_low_graph_visc(t, dt_in, nstage, true);
         rhsU = rhsL;
         break;
-      case P2DE_RHS_FLUX_DIFF:
+      }
+      case P2DE_RHS_FLUX_DIFF: {
+        PhaseScope ps(timers, "high order ESDG");
         rhs_fluxdiff(nstage, true);
         rhsU = rhsH;
         break;
+      }
       default:
-        entropy_projection(nstage);
-        dt = rhs_low_graph_visc(t, dt_in, nstage, false);
-        rhs_fluxdiff(nstage, false);
-        apply_rhs_limiter(t, dt_in, nstage);  // NB: the limiter sees the caller's dt (rhs.jl:46,52)
+        { PhaseScope ps(timers, "entropy projection"); entropy_projection(nstage); }
+        { PhaseScope ps(timers, "low order positivity"); dt = rhs_low_graph_visc(t, dt_in, nstage, false); }
+        { PhaseScope ps(timers, "high order ESDG"); rhs_fluxdiff(nstage, false); }
+        { PhaseScope ps(timers, "apply positivity limiter"); apply_rhs_limiter(t, dt_in, nstage); }  // NB: the limiter sees the caller's dt (rhs.jl:46,52)
         break;
     }
     return dt;
@@ -1380,6 +1406,7 @@ struct Oracle : OracleBase {
 
   // timestepping/SSPRK33.jl:28-40 (one iteration of the while loop)
   double ssp33_step(double t) override {
+    PhaseScope all(timers, "SSP stages");
     double dt = jl_min(cfg.CFL * cfg.dt0, cfg.T - t);
     resW = Uq;
     dt = rhs(t, dt, 1);
@@ -1481,6 +1508,16 @@ double oracle_rhs(void *h, double t, double dt, int32_t nstage) { return static_
 double oracle_ssp33_step(void *h, double t) { return static_cast<OracleBase *>(h)->ssp33_step(t); }
 int64_t oracle_get_field(void *h, const char *name, double *dst, int64_t n) { return static_cast<OracleBase *>(h)->get_field(name, dst, n); }
 double oracle_reduce(void *h, int32_t what) { return static_cast<OracleBase *>(h)->reduce(what); }
+// phase times as "label\tseconds\n" lines into buf (returns the length needed); reset != 0 clears them afterwards
+int64_t oracle_phase_times(void *h, char *buf, int64_t n, int32_t reset) {
+  auto *o = static_cast<OracleBase *>(h);
+  std::string out;
+  char num[64];
+  for (auto &p : o->timers.acc) { snprintf(num, sizeof num, "%.9g", p.second); out += p.first + "\t" + num + "\n"; }
+  if (buf && n > 0) { size_t m = std::min<size_t>(out.size(), (size_t)n - 1); std::memcpy(buf, out.data(), m); buf[m] = 0; }
+  if (reset) o->timers.clear();
+  return (int64_t)out.size() + 1;
+}
 void oracle_set_threads(int32_t n) {
 #ifdef _OPENMP
   omp_set_num_threads(n);

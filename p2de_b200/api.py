@@ -175,6 +175,14 @@ class State:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _lib.check(self.L, self.h, self.L.p2de_comm_init(self.h, rank, nranks, buf))
 
+    DBG_NAMES = ("cta_general", "cta_interior", "cta_defer", "elem_logs", "elem", "lines", "lines_not_easy", "limiter_slow")
+
+    def debug_counters(self, enable: bool = True) -> dict:
+        """p2de_debug_counters: current values (since counting was enabled), then start (enable) / stop counting."""
+        buf = (C.c_uint64 * len(self.DBG_NAMES))()
+        _lib.check(self.L, self.h, self.L.p2de_debug_counters(self.h, int(enable), buf))
+        return dict(zip(self.DBG_NAMES, (int(v) for v in buf)))
+
     def kernel_launch_count(self) -> int:
         return int(self.L.p2de_kernel_launch_count(self.h))
 

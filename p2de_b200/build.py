@@ -10,6 +10,8 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libp2de_b200.so")
 SOURCES = ["capi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-split-compile", "0",   # the kernels of the one translation unit are compiled in parallel (same code, 2.5x faster build)
+              "-diag-suppress", "177",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 
 
@@ -31,8 +33,10 @@ def _stale() -> bool:
 def build_extension(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return SO
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", SO] + [os.path.join(CSRC, s) for s in SOURCES]
+    extra = os.environ.get("P2DE_NVCC_EXTRA", "").split()   # A/B builds: -D switches of the kernel headers
+    so = os.environ.get("P2DE_B200_LIB", SO) if extra else SO
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", so] + [os.path.join(CSRC, s) for s in SOURCES]
     env = dict(os.environ)
     env.pop("CXX", None), env.pop("CC", None)
     res = subprocess.run(cmd, cwd=CSRC, env=env, capture_output=True, text=True)
@@ -40,7 +44,7 @@ def build_extension(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)
-    return SO
+    return so
 
 
 if __name__ == "__main__":

@@ -129,6 +129,7 @@ struct p2de_handle {
   double *Llocal = nullptr;   // [Nq+N1D, Nd, K, Ns]
   double *rhsH_diag = nullptr, *rhsL_diag = nullptr;
   unsigned long long *dt_bits = nullptr;
+  unsigned long long *dbg = nullptr, *dbg_buf = nullptr;   // p2de_debug_counters: dbg = dbg_buf while counting
   double *partial = nullptr;  // reduction scratch
   double *tab_dev = nullptr;  // device copy of the Tables2D<N1D> struct (coalesced load into shared memory)
   int *mapP32 = nullptr, *bcflag = nullptr;
@@ -164,6 +165,19 @@ int fail(p2de_handle *h, int code, const char *fmt, ...) {
     cudaError_t e_ = (call);                                                                     \
     if (e_ != cudaSuccess) return fail(h, P2DE_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
   } while (0)
+
+// every entry point runs on the handle's device whatever the caller's current device is, and restores the caller's
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard &) = delete;
+  DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define DEV(h) DeviceGuard dev_guard_((h)->device)
 
 template <class T>
 int dev_alloc(p2de_handle *h, T **p, size_t n) {
@@ -438,7 +452,10 @@ int cell_entropy_of(int bound) {
   return 0;
 }
 
-__global__ void set_dt_kernel(unsigned long long *dt_bits, double v) { *dt_bits = (unsigned long long)__double_as_longlong(v); }
+__global__ void set_dt_kernel(unsigned long long *dt_bits, double v, int with_flag) {
+  dt_bits[0] = (unsigned long long)__double_as_longlong(v);
+  if (with_flag) dt_bits[1] = (unsigned long long)__double_as_longlong(1.0);   // "every candidate was a positive number" (dt_publish)
+}
 
 // minimum(s_modified) over all nodes (initialize_s_modified!, subcell.jl:19-35); s_modified > 0
 __global__ void smin_kernel(const double *U, long long n_nodes, double gamma, unsigned long long *out_bits) {
@@ -483,7 +500,9 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   if constexpr (!FAST && MODE == MODE_SUBCELL) {
     if (default_gauss) kern = stage_kernel<N1D, MODE, EPB, 1>;
   }
-  static size_t attr_set = 0;
+  // (the attribute is per device and per function: one slot per device for this instantiation)
+  static size_t attr_set_dev[64] = {};
+  size_t &attr_set = attr_set_dev[h->device & 63];
   if (smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if constexpr (!FAST && MODE == MODE_SUBCELL) {
@@ -580,7 +599,7 @@ int launch_update(p2de_handle *h, const UpdateArgs &A) {
 __global__ void __launch_bounds__(256)
 axpy_update_kernel(double2 *__restrict__ Uout, const double2 *__restrict__ resW, const double2 *__restrict__ Uin,
                    const double2 *__restrict__ r, long long n2, double a, double b, const double *dt_dev, double dt_host, int use_dt_dev) {
-  const double dt = use_dt_dev ? *dt_dev : dt_host;
+  const double dt = use_dt_dev ? dt_read(dt_dev) : dt_host;
   const bool plain = a == 0.0 && b == 1.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const double2 u = Uin[i], q = r[i];
@@ -628,6 +647,7 @@ StageArgs stage_args(p2de_handle *h, const double *Uq, int nstage, double dt_hos
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   A.tvd = h->tvd; A.rhsLpre = h->rhsLpre; A.cell_entropy = h->cell_entropy; A.bound_beta = h->cfg.bound_beta;
   A.fstar = h->fstar;
+  A.dbg = h->dbg;
   return A;
 }
 
@@ -770,7 +790,7 @@ int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *ge
   h->topo.K = K; h->topo.Kx = (int)K; h->topo.Ky = 1;
   const size_t nU = (size_t)K * Nq * 3;
   if ((rc = dev_alloc(h, &h->U[0], nU)) || (rc = dev_alloc(h, &h->U[1], nU)) || (rc = dev_alloc(h, &h->rhsU, nU)) ||
-      (rc = dev_alloc(h, &h->Lz, (size_t)K * h->Ns)) || (rc = dev_alloc(h, &h->dt_bits, 1)) ||
+      (rc = dev_alloc(h, &h->Lz, (size_t)K * h->Ns)) || (rc = dev_alloc(h, &h->dt_bits, 2)) ||
       (rc = dev_alloc(h, &h->partial, 1024 + (size_t)Nq)))
     return rc;
   CU(h, cudaMemset(h->Lz, 0, (size_t)K * h->Ns * sizeof(double)));
@@ -819,7 +839,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
               double *Uadd = nullptr, bool combine = true) {
   if (nstage == 1) {
     double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // low_order_graph_viscosity.jl:230
-    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->dt_bits, cap);
+    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->dt_bits, cap, 1);
     CU(h, cudaGetLastError());
     h->launches++;
   }
@@ -827,7 +847,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   if (h->rhsH_diag && h->mode == MODE_SUBCELL)
     CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * h->Nc * sizeof(double), h->stream));
   if (h->entropy_bound && nstage == 1 && t == h->cfg.t0) {   // subcell.jl:32-34: global minimum of the initial condition
-    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->smin_bits, INFINITY);
+    set_dt_kernel<<<1, 1, 0, h->stream>>>(h->smin_bits, INFINITY, 0);
     smin_kernel<<<1024, 256, 0, h->stream>>>(Uin, h->K * h->Nq, h->cfg.gamma, h->smin_bits);
     CU(h, cudaGetLastError());
     h->launches += 2;
@@ -865,10 +885,13 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   // on both sides and symmetrize_limiting_parameters! (subcell.jl:418-456) is the identity; what is left after the stage
   // kernel is at most the SSP combine (stage 1, where dt is only known once the kernel has finished everywhere)
   const bool sym_free = h->fast && h->mode == MODE_SUBCELL && !want_outputs && (direct || !fuse);
+  // ... and the stage kernel's coefficients are final: when L_local is kept (State.jl:21; allocated by keep_diagnostics or
+  // by the first p2de_rhs) each stage writes them straight into its own slot L_local[:, :, :, nstage], as SSP33! leaves them
+  if (sym_free && h->Llocal) A.lpre = h->Llocal + (size_t)h->nLloc * h->K * (nstage - 1);
   if (int rc = launch_stage(h, A)) return rc;
   if (h->comm) {
     if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
-      NC(h, nccl_api(nullptr)->AllReduce(h->dt_bits, h->dt_bits, 1, ncclDouble, ncclMin, h->comm, h->stream));
+      NC(h, nccl_api(nullptr)->AllReduce(h->dt_bits, h->dt_bits, 2, ncclDouble, ncclMin, h->comm, h->stream));
     // E2: un-symmetrised interface coefficients of the neighbouring stripes' boundary rows (FAST path: the interface
     // coefficients are 1 on both sides of every interior face, so only the L_local output needs them)
     if (h->mode == MODE_SUBCELL && !sym_free)
@@ -938,6 +961,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0)
     return fail(nullptr, P2DE_ERR_CUDA, "no CUDA device (%s): libp2de_b200 has no CPU fallback", cudaGetErrorString(e));
+  struct RestoreDevice { int prev = -1; RestoreDevice() { cudaGetDevice(&prev); } ~RestoreDevice() { if (prev >= 0) cudaSetDevice(prev); } } restore_device;
   p2de_handle *h = new p2de_handle();
   h->cfg = *cfg;
   {
@@ -1024,6 +1048,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
   if ((rc = dev_alloc(h, &h->Lz, (size_t)h->K * h->Ns))) return bail(rc);
   if (cudaMemset(h->Lz, 0, (size_t)h->K * h->Ns * sizeof(double)) != cudaSuccess) return bail(fail(h, P2DE_ERR_CUDA, "memset"));
   if (cfg->keep_diagnostics) {
+    if (mode == MODE_SUBCELL && (rc = ensure_Llocal(h))) return bail(rc);   // L_local[:, :, :, 1:3] current after every step
     if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return bail(rc);
     cudaMemset(h->rhsH_diag, 0, nU * sizeof(double)); cudaMemset(h->rhsL_diag, 0, nU * sizeof(double));
   }
@@ -1036,7 +1061,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if (!h->nodewise) cudaMemset(h->theta_local_dev, 0, nth * sizeof(double));   // NoEntropyProjectionLimiter never writes theta_local
   }
   if (h->gauss && (rc = dev_alloc_halo(h, &h->utf, (size_t)h->K * h->Nfp * 4, (size_t)cfg->Kx * h->Nfp * 4))) return bail(rc);
-  if ((rc = dev_alloc(h, &h->dt_bits, 1)) || (rc = dev_alloc(h, &h->smin_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
+  if ((rc = dev_alloc(h, &h->dt_bits, 2)) || (rc = dev_alloc(h, &h->smin_bits, 1)) || (rc = dev_alloc(h, &h->partial, 1024 + (size_t)h->Nq))) return bail(rc);
   cudaMemset(h->smin_bits, 0, sizeof(unsigned long long));   // s_modified_min starts at 0.0 (State.jl:180)
   if (ops->VDM_inv) {
     if ((rc = dev_alloc(h, &h->VDM_inv, (size_t)h->Nq * h->Nq))) return bail(rc);
@@ -1055,7 +1080,7 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
 
 int32_t p2de_destroy(p2de_handle *h) {
   if (!h) return P2DE_OK;
-  cudaSetDevice(h->device);
+  DEV(h);
   if (h->comm) { if (const NcclApi *n = nccl_api(nullptr)) n->CommDestroy(h->comm); }
   prof_clear(h);
   for (void *p : h->owned) cudaFree(p);
@@ -1071,12 +1096,14 @@ int32_t p2de_set_stream(p2de_handle *h, void *cuda_stream) {
 
 int32_t p2de_synchronize(p2de_handle *h) {
   if (!h) return P2DE_ERR_ARG;
+  DEV(h);
   CU(h, cudaStreamSynchronize(h->stream));
   return P2DE_OK;
 }
 
 int32_t p2de_set_state_async(p2de_handle *h, const double *Uq_host) {
   if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
+  DEV(h);
   CU(h, cudaMemcpyAsync(h->U[h->cur], Uq_host, (size_t)h->K * h->Nq * h->Nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->have_state = true;
   return P2DE_OK;
@@ -1087,6 +1114,7 @@ int32_t p2de_set_state(p2de_handle *h, const double *Uq_host) {
 }
 int32_t p2de_get_state_async(p2de_handle *h, double *Uq_host) {
   if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
+  DEV(h);
   if (!h->have_state) return fail(h, P2DE_ERR_STATE, "get_state before set_state");
   CU(h, cudaMemcpyAsync(Uq_host, h->U[h->cur], (size_t)h->K * h->Nq * h->Nc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   return P2DE_OK;
@@ -1098,28 +1126,34 @@ int32_t p2de_get_state(p2de_handle *h, double *Uq_host) {
 
 int32_t p2de_rhs(p2de_handle *h, double t, double dt, int32_t nstage, double *dt_out) {
   if (!h) return P2DE_ERR_ARG;
+  DEV(h);
   if (!h->have_state) return fail(h, P2DE_ERR_STATE, "rhs before set_state");
   if (nstage < 1 || nstage > h->Ns) return fail(h, P2DE_ERR_ARG, "nstage %d outside 1..%d", nstage, h->Ns);
   if (int rc = ensure_rhsU(h)) return rc;
   if (h->mode == MODE_SUBCELL) if (int rc = ensure_Llocal(h)) return rc;
   if (int rc = run_stage(h, h->U[h->cur], nstage, t, dt, false, false, nullptr, nullptr, 0, 0, true)) return rc;
-  double dtr = dt;
+  double dtr[2] = {dt, 1.0};
   if (nstage == 1 && h->mode != MODE_HIGH) {
-    CU(h, cudaMemcpyAsync(&dtr, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaMemcpyAsync(dtr, h->dt_bits, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   }
   CU(h, cudaStreamSynchronize(h->stream));
-  if (dt_out) *dt_out = dtr;
+  if (dt_out) *dt_out = dtr[1] == 1.0 ? dtr[0] : std::numeric_limits<double>::quiet_NaN();   // dt_publish: a NaN candidate was seen
   return P2DE_OK;
 }
 
 int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
   if (!h) return P2DE_ERR_ARG;
+  DEV(h);
   if (!h->have_state) return fail(h, P2DE_ERR_STATE, "ssp33_step before set_state");
-  const bool outs = h->Llocal != nullptr;   // keep L_local current only if someone asked for it before
+  // L_local[:, :, :, 1:3] of the step (SSPRK33.jl:31-39 leaves all three stages' coefficients behind): kept current once the
+  // buffer exists.  On the FAST path that costs nothing (run_stage: the stage kernel writes its coefficients into the stage's
+  // slot, same 4-launch schedule); on the generic path the update kernel that runs anyway writes them.
+  const bool fast_direct = h->direct && h->fast && h->mode == MODE_SUBCELL && h->dim == 2;
+  const bool outs = h->Llocal != nullptr && !fast_direct;
   double *Ua = h->U[h->cur], *Ub = h->U[1 - h->cur];
   double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // SSPRK33.jl:30
   const bool has_cfl = h->mode != MODE_HIGH;                          // FluxDiffRHS never changes dt (rhs.jl:38)
-  if (h->direct && h->fast && h->mode == MODE_SUBCELL && h->dim == 2 && !outs) {
+  if (fast_direct) {
     // Direct schedule: stages 2 and 3 write their result from the stage kernel (run_stage: `direct`), which
     // needs an output buffer other than the stage input: U1 -> Ub (dense update, dt only known after the
     // stage-1 kernel), U2 -> the rpre buffer (free once the stage-1 update has consumed it), U^{n+1} -> over
@@ -1147,8 +1181,11 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
 
 int32_t p2de_last_dt(p2de_handle *h, double *dt_out) {
   if (!h || !dt_out) return P2DE_ERR_ARG;
-  CU(h, cudaMemcpyAsync(dt_out, h->dt_bits, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  DEV(h);
+  double v[2];
+  CU(h, cudaMemcpyAsync(v, h->dt_bits, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  *dt_out = v[1] == 1.0 ? v[0] : std::numeric_limits<double>::quiet_NaN();   // dt_publish: a NaN candidate was seen
   return P2DE_OK;
 }
 
@@ -1182,6 +1219,7 @@ int32_t p2de_ssp33_run(p2de_handle *h, double *t_inout, int64_t max_steps, int64
 
 int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
   if (!h || !dst) return fail(h, P2DE_ERR_ARG, "null argument");
+  DEV(h);
   const int64_t nU = h->K * h->Nq * h->Nc;
   const double *src = nullptr;
   int64_t cnt = 0;
@@ -1209,6 +1247,7 @@ int32_t p2de_get_field(p2de_handle *h, int32_t field, double *dst, int64_t n) {
 
 int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out) {
   if (!h || !out) return P2DE_ERR_ARG;
+  DEV(h);
   if (what < 0 || what > 2) return fail(h, P2DE_ERR_ARG, "unknown reduction %d", what);
   const int blocks = 1024;
   if (h->dim == 1) reduce1d_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->partial + 1024, h->Nq, h->K * h->Nq, h->Jcons, what, h->partial);
@@ -1226,6 +1265,7 @@ int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out) {
 
 int32_t p2de_profile(p2de_handle *h, int32_t enable) {
   if (!h) return P2DE_ERR_ARG;
+  DEV(h);
   CU(h, cudaStreamSynchronize(h->stream));
   prof_clear(h);
   h->profiling = enable != 0;
@@ -1233,6 +1273,7 @@ int32_t p2de_profile(p2de_handle *h, int32_t enable) {
 }
 int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, int64_t *launches) {
   if (!h || !total_ms || !launches) return P2DE_ERR_ARG;
+  DEV(h);
   CU(h, cudaStreamSynchronize(h->stream));
   double tot = 0; int64_t n = 0;
   for (auto &r : h->prof) {
@@ -1242,6 +1283,23 @@ int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, in
     tot += ms; ++n;
   }
   *total_ms = tot; *launches = n;
+  return P2DE_OK;
+}
+
+int32_t p2de_debug_counters(p2de_handle *h, int32_t enable, uint64_t out[P2DE_DBG_COUNT]) {
+  if (!h) return P2DE_ERR_ARG;
+  DEV(h);
+  static_assert((int)P2DE_DBG_COUNT == (int)DBG_COUNT && (int)P2DE_DBG_LIMITER_SLOW == (int)DBG_LIMITER_SLOW, "counter ids");
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (out) {
+    if (h->dbg_buf) CU(h, cudaMemcpy(out, h->dbg_buf, DBG_COUNT * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    else std::memset(out, 0, DBG_COUNT * sizeof(uint64_t));
+  }
+  if (enable && !h->dbg) {
+    if (!h->dbg_buf) if (int rc = dev_alloc(h, &h->dbg_buf, (size_t)DBG_COUNT)) return rc;
+    CU(h, cudaMemset(h->dbg_buf, 0, DBG_COUNT * sizeof(uint64_t)));
+    h->dbg = h->dbg_buf;
+  } else if (!enable) h->dbg = nullptr;
   return P2DE_OK;
 }
 
@@ -1275,7 +1333,7 @@ int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8
   if (!n) return fail(h, P2DE_ERR_NCCL, "%s", why.c_str());
   ncclUniqueId id;
   std::memcpy(&id, unique_id, 128);
-  CU(h, cudaSetDevice(h->device));
+  DEV(h);
   ncclComm_t comm = nullptr;
   ncclResult_t r = n->CommInitRank(&comm, nranks, id, rank);
   if (r != ncclSuccess) return fail(h, P2DE_ERR_NCCL, "ncclCommInitRank: %s", n->GetErrorString(r));

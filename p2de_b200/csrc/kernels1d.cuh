@@ -260,7 +260,7 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
     }
     (void)uP_L; (void)uP_H;
 
-    const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+    const double dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
     if (A.mode == MODE_SUBCELL) {
       // accumulate_f_bar! (subcell.jl:144-160) and subcell_bound_limiter!(::Dim1) (:208-246)
       double fH[3], fL[3], dF[Nq + 1][3];
@@ -305,7 +305,7 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
     if (A.rhsL_diag && do_low) for (int i = 0; i < Nq; ++i) for (int c = 0; c < 3; ++c) A.rhsL_diag[(k * Nq + i) * 3 + c] = rL[i][c];
     if (A.rhsH_diag && do_high) for (int i = 0; i < Nq; ++i) for (int c = 0; c < 3; ++c) A.rhsH_diag[(k * Nq + i) * 3 + c] = rH[i][c];
   }
-  if (do_low && A.nstage == 1 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
+  if (do_low && A.nstage == 1) dt_publish(A.dt_bits, dtloc);
 }
 
 template <int N1D>
@@ -314,7 +314,7 @@ update1d_kernel(const Upd1D A, const Tables1D<N1D> T) {
   constexpr int Nq = N1D;
   const long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (k >= A.K) return;
-  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+  const double dt = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
   double r[Nq][3];
   if (A.mode == MODE_SUBCELL) {
     double lv[Nq + 1];

@@ -111,7 +111,12 @@ struct StageArgs {
   const double *defer_add;
   int rowblocks;                     // FAST kernel: > 0 = 2D grid (rowblocks x Ky), Kx = rowblocks * EPB; 0 = 1D grid over batches
   double *fstar;                     // Gauss + cell entropy: [K][Nfp][2][4] normal components of fstar_H, fstar_L (State.jl:11-12)
+  unsigned long long *dbg;           // nullptr, or the counters of p2de_debug_counters (P2DE_DBG_*): which instantiations ran, data-dependent shortcuts taken
 };
+
+// counters behind p2de_debug_counters (include/p2de_b200.h)
+enum { DBG_CTA_GENERAL = 0, DBG_CTA_INTERIOR = 1, DBG_CTA_DEFER = 2, DBG_ELEM_LOGS = 3, DBG_ELEM = 4, DBG_LINES = 5,
+       DBG_LINES_NOT_EASY = 6, DBG_LIMITER_SLOW = 7, DBG_COUNT = 8 };
 
 struct UpdateArgs {
   const double *rhsL, *dF, *lpre;    // MODE_SUBCELL inputs
@@ -429,7 +434,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
   double BFL[2][4], BFH[2][4];
   double lamPair[N1D], lamFace[2];
   double wJ[N1D], rwJ[N1D];
-  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
+  const double dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   if (active) {
     double uu[N1D], vv[N1D], pp[N1D];
 #pragma unroll
@@ -770,7 +775,7 @@ stage_kernel(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTo
         if ((wmask >> ((tid & 31) ^ off)) & 1u) dtloc = jl_min(dtloc, other);
       }
     }
-    if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
+    if ((tid & 31) == 0) dt_publish(A.dt_bits, dtloc);
   }
 
   if (!active && MODE != MODE_ZHANGSHU && !(MODE == MODE_SUBCELL && (o_cell_entropy || SLIM))) return;
@@ -1087,7 +1092,7 @@ update_kernel(const __grid_constant__ UpdateArgs A, const __grid_constant__ Mesh
     __syncthreads();
   }
   if (!active || d != 0) return;
-  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+  const double dt = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
 #pragma unroll
   for (int a = 0; a < N1D; ++a) {
     int node = a + line * N1D;

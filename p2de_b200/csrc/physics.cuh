@@ -26,6 +26,19 @@ struct Cons2 { double rho, m1, m2, E; };
 P2DE_DEV double jl_min(double a, double b) { return (a < b || a != a) ? a : b; }
 P2DE_DEV double jl_max(double a, double b) { return (a > b || a != a) ? a : b; }
 
+// CFL dt reduction target (low_order_graph_viscosity.jl:222-243): word 0 = minimum over the positive candidates (raw
+// bits of positive doubles are order preserving, so atomicMin works on them); word 1 = 1.0 as long as every candidate
+// was a positive number and 0.0 once some warp saw a NaN or non-positive one.  Julia's `min` propagates NaN, dt then
+// becomes NaN and `while t < T` (SSPRK33.jl:28) ends; dt_read gives every consumer the same NaN.
+P2DE_DEV void dt_publish(unsigned long long *dt_bits, double dtloc) {
+  if (dtloc > 0.0) { if (dtloc < INFINITY) atomicMin(dt_bits, (unsigned long long)__double_as_longlong(dtloc)); }
+  else atomicExch(dt_bits + 1, 0ull);
+}
+P2DE_DEV double dt_read(const double *dt_dev) {
+  const double2 v = *reinterpret_cast<const double2 *>(dt_dev);
+  return v.y == 1.0 ? v.x : __longlong_as_double(0x7ff8000000000000ll);
+}
+
 // pfun, compressible_Navier_Stokes.jl:24-28
 P2DE_DEV double pfun2(double gm1, const Cons2 &U) {
   return gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) / U.rho);

@@ -154,6 +154,10 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   const bool full = INTERIOR || kb + EPB <= M.K;          // no partial batch: skip the per-element guards
   const double gamma = A.gamma, gm1 = A.gamma - 1.0;
   const double *Ubase = A.Uq + kb * (Nq * 4);             // this batch's states; 32-bit offsets from here on
+  if (A.dbg && tid == 0) {   // p2de_debug_counters: which instantiation this CTA runs
+    atomicAdd(A.dbg + (INTERIOR ? DBG_CTA_INTERIOR : DBG_CTA_GENERAL), 1ull);
+    if (DEFER) atomicAdd(A.dbg + DBG_CTA_DEFER, 1ull);
+  }
 
   if (P2DE_FAST_PREFETCH) {
     // pull the states of the batch one full wave of resident CTAs ahead into L2: that batch starts on some SM about
@@ -181,7 +185,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     const int i = tid + it * NT;
     if (i < TF2) treg[it] = reinterpret_cast<const double2 *>(A.tab_dev)[i];
   }
-  const double dtl = A.use_dt_dev ? *A.dt_dev : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
+  const double dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
   // ---- the two neighbour face nodes of this line: issue the loads now (one 32-byte node each, two
   //      16-byte loads) so that their latency is covered by the node phase
   Nbr nb[2];
@@ -398,11 +402,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         fS_rot(A.half_inv_gm1, q[i], q[j], F);
         double Sv = T.SHt[d][i][j][line];
 #pragma unroll
-#ifdef P2DE_EXP_FMA
-        for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }
-#else
         for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
-#endif
       });
     }
 #pragma unroll
@@ -425,15 +425,15 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         dtloc = jl_min(dtloc, A.CFL * 0.5 * (A.Jq * T.wq[a + line * N1D]) / li);
       }
     }
-#pragma unroll
     {
       const unsigned wmask = __activemask();   // the CTA's last warp may be partial
+#pragma unroll
       for (int off = 16; off > 0; off >>= 1) {
         double other = __shfl_xor_sync(wmask, dtloc, off);
         if ((wmask >> ((tid & 31) ^ off)) & 1u) dtloc = jl_min(dtloc, other);
       }
     }
-    if ((tid & 31) == 0 && dtloc < INFINITY) atomicMin(A.dt_bits, (unsigned long long)__double_as_longlong(dtloc));
+    if ((tid & 31) == 0) dt_publish(A.dt_bits, dtloc);
   }
 
   if (!active && MODE != MODE_ZHANGSHU && MODE != MODE_SUBCELL) return;
@@ -546,9 +546,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       double Pm[4], Pp[4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
-#ifdef P2DE_EXP_NOLIM
-      lv[a] = jl_min(lv[a], Pm[0] + c0 + Lrho); lv[a + 1] = jl_min(lv[a + 1], Pp[1] + Lrhoe);
-#else
       // (lv <= 1 throughout, so the common result 1.0 of limiting_param_pos needs no min)
       if (a > 0 || bc0) {
         double qa, qb;
@@ -562,7 +559,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         if (!limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0))
           lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pp[0], Lrho, qa, qb, c0));
       }
-#endif
     }
     }   // !all_easy
     // (update_blending_factor! = 1 without shock capturing, shock_capture.jl:111-114: the FAST path has none, so the
@@ -820,7 +816,7 @@ update_kernel_fast(const __grid_constant__ UpdateArgs A, const __grid_constant__
   }
   __syncthreads();
   if (!active) return;
-  const double dt = A.use_dt_dev ? *A.dt_dev : A.dt_host;
+  const double dt = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
   if (A.Llocal_out)   // interior subcell faces: the stage kernel's coefficients are final
     for (int n = tl; n < NL; n += TPE) {
       const int dd = n / (N1D * NF), r = n % (N1D * NF);

@@ -16,41 +16,44 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(_HERE))
 from p2de_b200.abi import BCDataC, Config, GeometryC, OperatorsC, PackedProblem  # noqa: E402
 
-_LIB = None
-_NATIVE = False
+_LIBS = {}
+_DEFAULT = "ref"
+_SO = {"ref": "libp2de_oracle.so", "native": "libp2de_oracle_native.so", "fma": "libp2de_oracle_fma.so"}
 
 
-def build(force: bool = False, native: bool = False) -> str:
-    """`native`: the -O3 -march=native build for bench.py's CPU arm, compiled on the machine that runs it
-    (oracle/Makefile); otherwise the portable -O2 build the tests check against."""
-    so = os.path.join(_HERE, "libp2de_oracle_native.so" if native else "libp2de_oracle.so")
+def build(force: bool = False, variant: str = "ref") -> str:
+    """Builds one variant of the oracle (oracle/Makefile):
+    "ref"    portable -O2, -ffp-contract=off: THE checker (Julia does not contract a*b+c);
+    "fma"    same source with -ffp-contract=fast -mfma: a legal re-association of the same formulas, used by tests to
+             measure how far the reference formulation itself moves under rounding (tolerance probe);
+    "native" -O3 -march=native, -ffp-contract=off: bench.py's CPU arm, compiled on the machine that runs it."""
+    so = os.path.join(_HERE, _SO[variant])
     src = os.path.join(_HERE, "p2de_oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "p2de_b200.h")
     stale = (not os.path.exists(so)) or any(
         os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr))
     if force or stale:
-        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["native"] if native else []) + (["-B"] if force else []))
+        subprocess.check_call(["make", "-C", _HERE, "-s", _SO[variant]] + (["-B"] if force else []))
     return so
 
 
 def use_native_build():
-    """bench.py's CPU arm: load the -O3 -march=native build (must be called before the first Oracle is made).
-    Falls back to the portable build if it cannot be compiled here; returns the flags actually in use."""
-    global _NATIVE
-    assert _LIB is None, "use_native_build() must precede the first use of the oracle"
+    """bench.py's CPU arm: make the -O3 -march=native build the default variant.  Falls back to the portable build if
+    it cannot be compiled here; returns the flags actually in use."""
+    global _DEFAULT
     try:
-        build(native=True)
-        _NATIVE = True
+        build(variant="native")
+        _DEFAULT = "native"
         return "-O3 -march=native -ffp-contract=off -fopenmp"
     except Exception:
-        _NATIVE = False
+        _DEFAULT = "ref"
         return "-O2 -ffp-contract=off -fopenmp"
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        L = C.CDLL(build(native=_NATIVE))
+def lib(variant: str = None):
+    variant = variant or _DEFAULT
+    if variant not in _LIBS:
+        L = C.CDLL(build(variant=variant))
         L.oracle_phase_times.restype = C.c_int64
         L.oracle_phase_times.argtypes = [C.c_void_p, C.c_char_p, C.c_int64, C.c_int32]
         L.oracle_create.restype = C.c_void_p
@@ -76,15 +79,15 @@ def lib():
         L.oracle_fS_2d.argtypes = [C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_limiting_param_2d.restype = C.c_double
         L.oracle_limiting_param_2d.argtypes = [C.c_double, C.c_void_p, C.c_void_p] + [C.c_double] * 4
-        _LIB = L
-    return _LIB
+        _LIBS[variant] = L
+    return _LIBS[variant]
 
 
 class Oracle:
     """One reference-faithful CPU solver+state (mirrors State/Solver of the reference)."""
 
-    def __init__(self, param, discrete_data, bcdata, *, structured_bc=None, threads=None):
-        self.L = lib()
+    def __init__(self, param, discrete_data, bcdata, *, structured_bc=None, threads=None, variant=None):
+        self.L = lib(variant)
         self.sizes = discrete_data.sizes
         self.packed = PackedProblem(param, discrete_data, bcdata, structured_bc=structured_bc)
         if threads is not None:

@@ -324,14 +324,6 @@ int build_tables(p2de_handle *h, const p2de_operators *o, const double GJ[4]) {
     for (int j = 0; j < Nq; ++j)
       if (j != i && o->MinvVhT[i + (size_t)j * Nq] != 0.0) return fail(h, P2DE_ERR_UNSUPPORTED, "mass matrix is not diagonal");
   }
-  for (int e4 = 0; e4 < 4; ++e4) {
-    for (int node = 0; node < Nq; ++node) T.posn[e4][node] = node_pos<N1D>(e4, node % N1D, node / N1D) - e4 * Nq;
-    for (int line = 0; line < N1D; ++line)
-      for (int a = 0; a < N1D; ++a) {
-        T.posl[0][e4][line][a] = node_pos<N1D>(e4, a, line) - e4 * Nq;
-        T.posl[1][e4][line][a] = node_pos<N1D>(e4, line, a) - e4 * Nq;
-      }
-  }
   for (int f = 0; f < Nfp; ++f) {
     T.minvf[f] = o->MinvVfT[T.fq2q[f] + (size_t)f * Nq];
     for (int i = 0; i < Nq; ++i)   // M^-1 Vf^T = (1/wq) Vf^T (LGL: the 1/wq-scaled face gather)
@@ -487,7 +479,7 @@ __global__ void reduce_kernel(const double *U, const double *wq, int Nq, long lo
 template <int N1D, int MODE, bool FAST>
 int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
-  constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
+  constexpr int TBL = FAST ? fast_table_doubles<N1D>() : (int)((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
   const size_t base = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
   const bool sub = !FAST && MODE == MODE_SUBCELL;
   size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
@@ -509,12 +501,20 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
       CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if constexpr (FAST && MODE == MODE_SUBCELL)
+    if constexpr (FAST && MODE == MODE_SUBCELL) {
       CU(h, cudaFuncSetAttribute(stage_kernel_fast_defer<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_kernel_fast_s1<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_kernel_fast_s3<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     attr_set = smem;
   }
   if constexpr (FAST && MODE == MODE_SUBCELL) {
+    // the direct schedule's kernels know their role at compile time (stage_fast.cuh: KIND); p2de_rhs and the testing
+    // schedules (diagnostics, un-fused stages 2/3, fused without direct output) keep the run-time version
+    const bool nodiag = !A.rhsL_diag && !A.rhsH_diag;
     if (A.defer_add) kern = stage_kernel_fast_defer<N1D, EPB>;
+    else if (P2DE_FAST_KINDS && nodiag && A.nstage == 1 && !A.fuse) kern = stage_kernel_fast_s1<N1D, EPB>;
+    else if (P2DE_FAST_KINDS && nodiag && A.nstage != 1 && A.fuse) kern = stage_kernel_fast_s3<N1D, EPB>;
   }
   dim3 grid((unsigned)((h->K + EPB - 1) / EPB));
   StageArgs A2 = A;

@@ -43,9 +43,6 @@ struct Tables2D {
   double Bf[2][N1D][2];         // physical signed boundary weight at the line ends [d][line][end]
   double wq[N1D * N1D];
   double rwJl[2][N1D][N1D];     // 1 / (Jq * wq) per grid line: [d][line][a]
-  // shared-memory positions used by stage_kernel_fast (see node_pos there), as look-up tables:
-  int posl[2][4][N1D][N1D];     // [d][el & 3][line][a]: node_pos(el, .) - el * Nq of the a-th node of a line
-  int posn[4][N1D * N1D];       // [el & 3][node]: the same for a flat node index
   // ---- generic kernels only
   double SH[2][N1D][N1D][N1D];  // the same S as [d][line][a][b]
   double rwJ[N1D * N1D];        // 1 / (Jq * wq)
@@ -55,8 +52,7 @@ struct Tables2D {
   // Gauss collocation (face nodes are not volume nodes): per line and line end e
   double VfL[2][N1D][2][N1D];   // Vf[f, node(a)]: extrapolation weights of the line's nodes to its end face node
   double SHf[2][N1D][2][N1D];   // physical hybridized S, face row x volume column: GJ_dd * Srsh_db[d][Nq + f, node(a)]
-  static constexpr int FAST_BYTES = (int)(sizeof(double) * (2 * N1D * N1D * N1D + 2 * N1D * N1D + 2 * N1D * 2 + N1D * N1D + 2 * N1D * N1D) +
-                                          sizeof(int) * (2 * 4 * N1D * N1D + 4 * N1D * N1D));
+  static constexpr int FAST_BYTES = (int)(sizeof(double) * (2 * N1D * N1D * N1D + 2 * N1D * N1D + 2 * N1D * 2 + N1D * N1D + 2 * N1D * N1D));
 };
 
 struct MeshTopo {

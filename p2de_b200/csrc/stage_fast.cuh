@@ -36,6 +36,22 @@ namespace p2de {
 #ifndef P2DE_FAST_MIN_BLOCKS5
 #define P2DE_FAST_MIN_BLOCKS5 3   // N=4 (N1D=5): 168 registers, no spills
 #endif
+// A/B switches of this round's restructurings (profiles/README.md has each step's measurement)
+#ifndef P2DE_FAST_SURE_LIMITER
+#define P2DE_FAST_SURE_LIMITER 1   // division-free sufficient test "every coefficient of the line is 1" before the exact evaluation
+#endif
+#ifndef P2DE_FAST_QUIET_PAIRS
+#define P2DE_FAST_QUIET_PAIRS 1    // warps whose elements cannot leave logmean's series branch: two-point flux without logs / selects
+#endif
+#ifndef P2DE_FAST_KINDS
+#define P2DE_FAST_KINDS 1          // stage role (stage 1 / stages 2,3) known at compile time in the direct schedule's kernels
+#endif
+
+// How much of the stage's role is a compile-time fact (MODE_SUBCELL; the other modes use KIND_RT):
+//   KIND_RT   run-time flags of StageArgs (p2de_rhs: any stage index, optional diagnostics, optional fused combine)
+//   KIND_S1   stage 1 of the direct schedule: CFL reduction, writes rhsU, no diagnostics
+//   KIND_S23  stages 2 and 3 of the direct schedule: SSP combine fused, no CFL reduction, no diagnostics
+enum { KIND_RT = 0, KIND_S1 = 1, KIND_S23 = 2 };
 
 // constants of logmean's series branch (:315-317) and its reciprocal: read as constant-bank operands
 __constant__ double kSeries[5] = {-0.2, 0.0512, 0.026038857142857, 0.2, 0.0912};
@@ -52,13 +68,24 @@ P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pr, double dt) {
 struct ConsR { double rho, mn, mt, E; };
 struct PrimR { double rho, un, ut, beta, rholog, betalog; };
 
+// sqrt: MUFU.RSQ64H seed (>= 20 bits) + two coupled Newton steps; relative error ~1e-23 before the final rounding, i.e.
+// within 1 ulp (the residual correction of sqrt_fast only decides the last bit)
+P2DE_DEV double sqrt_newton(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  double g = a * y, h = 0.5 * y;
+  double r = fma(-g, h, 0.5);
+  g = fma(g, r, g); h = fma(h, r, h);
+  r = fma(-g, h, 0.5);
+  return fma(g, r, g);
+}
 P2DE_DEV double wavespeed_rot(double gamma, double gm1, double rinv, double mn, double E) {
   double p = gm1 * (E - 0.5 * (mn * mn) * rinv);
-  return fabs(mn * rinv) + sqrt_fast(gamma * p * rinv);
+  return fabs(mn * rinv) + sqrt_newton(gamma * p * rinv);
 }
 // normal flux of fluxes(::Dim2) (:175-194) in the rotated frame
 P2DE_DEV void flux_rot(const ConsR &U, double un, double ut, double p, double f[4]) {
-  f[0] = U.mn; f[1] = U.mn * un + p; f[2] = U.rho * un * ut; f[3] = un * (U.E + p);
+  f[0] = U.mn; f[1] = U.mn * un + p; f[2] = U.mn * ut; f[3] = un * (U.E + p);   // (rho un ut = mn ut up to one rounding)
 }
 // three independent quotients n_i / a_i, written in lock step so that the three MUFU + Newton
 // chains overlap in the instruction stream (ptxas keeps source order for straight-line code)
@@ -95,6 +122,43 @@ P2DE_DEV void fS_rot(double half_inv_gm1, const PrimR &L, const PrimR &R, double
   F[0] = F1; F[1] = F1 * unavg + pa; F[2] = F1 * utavg; F[3] = f4aux * unavg;
 }
 
+// The same flux for a pair of an element in which rho and beta each vary by less than 6.2e-5 relative (the LAZY_LOGS vote
+// of the node phase): both logmeans are on their series branch, where with f = da/aavg, v = f^2 < 4e-9
+//   logmean(rho)      = aavg (1 - v/5 - O(v^2))        (the dropped terms are < 1e-18 relative)
+//   1 / logmean(beta) = (1 + v_b/5 + O(v_b^2)) / bavg
+// so f is only needed to ~1e-5 relative: the raw MUFU reciprocal (>= 20 bits) without Newton steps, and 1/bavg is the
+// reciprocal pa = aavg / (beta_L + beta_R) needs anyway.  One refined reciprocal, no logs, no selects.
+P2DE_DEV void fS_rot_quiet(double half_inv_gm1, const PrimR &L, const PrimR &R, double F[4]) {
+  const double sa = R.rho + L.rho, da = R.rho - L.rho, sb = R.beta + L.beta, db = R.beta - L.beta;
+  double xa;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(xa) : "d"(sa));
+  const double y = rcp_fast(sb);                       // 1 / (beta_L + beta_R) = 1 / (2 bavg)
+  const double fa = da * xa, fb = db * y;              // f / 2 of rho (approximate) and of beta
+  const double rholog = sa * fma(-0.4, fa * fa, 0.5);  // aavg (1 - f^2 / 5),  f = 2 fa, aavg = sa / 2
+  const double inv_betalog = y * fma(1.6, fb * fb, 2.0);   // (1 + f_b^2 / 5) / bavg
+  const double pa = 0.5 * (sa * y);
+  const double unavg = 0.5 * (L.un + R.un), utavg = 0.5 * (L.ut + R.ut);
+  const double unorm = L.un * R.un + L.ut * R.ut;
+  const double f4aux = fma(0.5 * rholog, unorm, fma(rholog * inv_betalog, half_inv_gm1, pa));
+  const double F1 = rholog * unavg;
+  F[0] = F1; F[1] = fma(F1, unavg, pa); F[2] = F1 * utavg; F[3] = f4aux * unavg;
+}
+
+// run-time indexed access to small per-line arrays inside the (rolled, rarely executed) exact limiter loop: a select chain
+// keeps the arrays in registers
+template <int NF>
+P2DE_DEV double dFv_at(const double (&dFv)[NF][4], int s, int c) {
+  double v = dFv[0][c];
+#pragma unroll
+  for (int t = 1; t < NF; ++t) v = (s == t) ? dFv[t][c] : v;
+  return v;
+}
+template <int NF>
+P2DE_DEV void lv_set_min(double (&lv)[NF], int s, double l) {
+#pragma unroll
+  for (int t = 0; t < NF; ++t) lv[t] = (s == t) ? jl_min(lv[t], l) : lv[t];
+}
+
 // compile-time loop over the node pairs (j, i), j < i, j outer: indices are constants for every N1D, so the
 // per-node arrays of the caller stay in registers (a `#pragma unroll` nest is not unrolled at N1D = 5)
 template <int N1D, int J, int I>
@@ -114,6 +178,14 @@ __host__ __device__ __forceinline__ int node_pos(int el, int i, int j) {
   return el * (N1D * N1D) + i + j * N1D;
 }
 
+// position of the a-th node of grid line `line` along axis d (d = 0: node (a, line); d = 1: node (line, a)); i + j = a + line
+// for both directions, so only the swizzled row depends on d
+template <int N1D>
+__device__ __forceinline__ int line_pos(int el, int d, int line, int a) {
+  if (N1D == 4) return el * 16 + 4 * (((d ? a : line) + el) & 3) + ((a + line) & 3);
+  return el * (N1D * N1D) + (d ? line + a * N1D : a + line * N1D);
+}
+
 // doubles of shared memory per element, besides the tables: 12 node fields, rhsxyL shares (partsL),
 // rhsxyH shares (partsH, not MODE_SUBCELL), the CFL lambda sums [2][Nq] that are later reused as the
 // L_local staging [2*N1D*(N1D+1)], and lmin
@@ -121,10 +193,13 @@ template <int N1D>
 __host__ __device__ constexpr int fast_lamp_per_elem() {
   return 2 * N1D * N1D > 2 * N1D * (N1D + 1) ? 2 * N1D * N1D : 2 * N1D * (N1D + 1);
 }
+// the FAST kernels keep only the table prefix they use in shared memory (rounded up to 16-byte words)
+template <int N1D>
+__host__ __device__ constexpr int fast_table_doubles() { return ((Tables2D<N1D>::FAST_BYTES + 15) / 16) * 2; }
 template <int N1D, int MODE>
 constexpr int fast_smem_doubles_per_elem() {
   constexpr int Nq = N1D * N1D;
-  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + fast_lamp_per_elem<N1D>() + N1D;
+  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + fast_lamp_per_elem<N1D>() + N1D + 1;   // + 1: the element's "quiet" flag
 }
 
 
@@ -132,12 +207,12 @@ constexpr int fast_smem_doubles_per_elem() {
 // are k -+ 1 / k -+ Kx and no face carries a boundary condition, so the boundary-condition branches, the seed
 // f_bar_H - f_bar_L of the prefix sums and the two end-face limiter evaluations of every line vanish at compile time
 // (fewer live registers: the generic version spills the boundary flags across the whole kernel).
-template <int N1D, int MODE, int EPB, bool INTERIOR, bool DEFER>
+template <int N1D, int MODE, int EPB, bool INTERIOR, bool DEFER, int KIND = KIND_RT>
 __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc, const long long kb) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
   constexpr int TBLC = (sizeof(Tables2D<N1D>) + 7) / 8;
-  constexpr int TBL = ((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
+  constexpr int TBL = fast_table_doubles<N1D>();
   constexpr int S = EPB * Nq;
   extern __shared__ double sm[];
   Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
@@ -146,6 +221,11 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   double2 *partsH = partsL + 4 * S;                                   // [d][half][S] (not MODE_SUBCELL)
   double *lamp = reinterpret_cast<double *>(partsH + ((MODE == MODE_SUBCELL) ? 0 : 4 * S));  // [2][S] / lstage
   double *lmin = lamp + EPB * fast_lamp_per_elem<N1D>();   // [EPB][N1D]
+  int *needlog = reinterpret_cast<int *>(lmin + EPB * N1D);   // [EPB] (LAZY_LOGS): some pair of the element may leave logmean's series branch
+  static_assert(KIND == KIND_RT || MODE == MODE_SUBCELL, "stage kinds exist for the subcell limiter's direct schedule only");
+  const bool nst1 = KIND == KIND_S1 || (KIND == KIND_RT && A.nstage == 1);      // CFL reduction in this launch
+  const bool fuse = KIND == KIND_S23 || (KIND == KIND_RT && MODE == MODE_SUBCELL && A.fuse != 0);   // SSP combine fused into the output phase
+  constexpr bool DIAG = KIND == KIND_RT;                                         // rhsL / rhsH diagnostics possible
 
   const int tid = threadIdx.x;
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
@@ -170,7 +250,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       if (tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Uq + kp * (Nq * 4) + tid * 16));
       else if (DEFER && tid < 2 * LINES)      // (resW is Uq itself in that stage)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.defer_add + kp * (Nq * 4) + (tid - LINES) * 16));
-      else if (MODE == MODE_SUBCELL && A.fuse && tid < 2 * LINES)
+      else if (fuse && tid < 2 * LINES)
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
     }
   }
@@ -205,7 +285,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         // an x-neighbour inside this batch is read from shared memory after the node phase (nbpos >= 0)
         const bool in_batch = d == 0 && (e ? el + 1 < EPB : el > 0);
         nbpos[e] = -1;
-        if (in_batch) nbpos[e] = (el + dk) * Nq;   // completed with the swizzle table once the tables are loaded
+        if (in_batch) nbpos[e] = 0;
         else if (DEFER)
           UnbC[e] = load_cons_plus(Ubase + ((long long)(el + dk) * Nq + node) * 4, A.defer_add + kb * (Nq * 4) + ((long long)(el + dk) * Nq + node) * 4, dtl);
         else UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
@@ -233,7 +313,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     if (n < S && (full || kb + n / Nq < M.K)) {
       Uraw[it] = (DEFER) ? load_cons_plus(Ubase + n * 4, A.defer_add + kb * (Nq * 4) + n * 4, dtl)
                                                        : load_cons(Ubase + n * 4);
-      if (MODE == MODE_SUBCELL && A.fuse && !DEFER)   // the flat output phase of this same thread reads resW here: pull it into L2 now
+      if (fuse && !DEFER)   // the flat output phase of this same thread reads resW here: pull it into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
     }
   }
@@ -250,7 +330,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     const bool valid = n < S && (full || kb + e2 < M.K);
     if (valid || (LAZY_LOGS && n < S)) {
       const Cons2 U = Uraw[it];
-      double *o = nodes + e2 * Nq + T.posn[e2 & 3][node];
+      double *o = nodes + node_pos<N1D>(e2, node % N1D, node / N1D);
       double rinv = rcp_fast(U.rho);
       double p = gm1 * (U.E - 0.5 * (U.m1 * U.m1 + U.m2 * U.m2) * rinv);
       double beta = 0.5 * U.rho * rcp_fast(p);
@@ -269,6 +349,8 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
           const int er = hr - __shfl_sync(0xffffffffu, hr, lead), eb = hb - __shfl_sync(0xffffffffu, hb, lead);
           const bool far = (unsigned)(er + 32) > 64u || (unsigned)(eb + 32) > 64u;
           need = ((__ballot_sync(0xffffffffu, far) >> lead) & 0xFFFFu) != 0u;
+          if (P2DE_FAST_QUIET_PAIRS && (tid & 15) == 0) needlog[e2] = need ? 1 : 0;
+          if (A.dbg && (tid & 15) == 0 && valid) { atomicAdd(A.dbg + DBG_ELEM, 1ull); if (need) atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull); }
         }
         if (need) { o[8 * S] = log(U.rho); o[9 * S] = log(beta); }
       }
@@ -283,15 +365,19 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   double G[N1D][4];
   double dF0[4];
 #pragma unroll
-  for (int a = 0; a < N1D; ++a) pos[a] = el * Nq + T.posl[d][el & 3][line][a];
+  for (int a = 0; a < N1D; ++a) pos[a] = line_pos<N1D>(el, d, line, a);
   const double *rwJ = T.rwJl[d][line];   // 1 / (Jq wq) of this line's nodes
+  // warp-uniform (all lanes vote, also those of a partial batch): no element of this warp can leave the series branch of
+  // logmean (constant and smooth regions), so its pairs take fS_rot_quiet
+  bool quiet = false;
+  if (P2DE_FAST_QUIET_PAIRS && LAZY_LOGS) quiet = __all_sync(0xffffffffu, needlog[el] == 0);
   if (active) {
     ConsR Unb[2];
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       if (nbpos[e] >= 0) {   // x-neighbour of this batch: its state is in `nodes`
         const int eln = e ? el + 1 : el - 1;
-        const double *o = nodes + nbpos[e] + T.posl[0][eln & 3][line][e ? 0 : N1D - 1];
+        const double *o = nodes + node_pos<N1D>(eln, e ? 0 : N1D - 1, line);
         UnbC[e].rho = o[0 * S]; UnbC[e].m1 = o[1 * S]; UnbC[e].m2 = o[2 * S]; UnbC[e].E = o[3 * S];
       }
       Unb[e].rho = UnbC[e].rho; Unb[e].mn = d ? UnbC[e].m2 : UnbC[e].m1;
@@ -373,7 +459,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         if (DO_LOW) {
           partsL[(d * 2 + 0) * S + pos[a]] = make_double2(GL[a][0] * rwJ[a], GL[a][1] * rwJ[a]);
           partsL[(d * 2 + 1) * S + pos[a]] = make_double2(GL[a][2] * rwJ[a], GL[a][3] * rwJ[a]);
-          if (A.nstage == 1)   // this direction's share of lambda_i (:222-281): its two volume pairs and its face
+          if (nst1)   // this direction's share of lambda_i (:222-281): its two volume pairs and its face
             lamp[d * S + pos[a]] = ((a > 0 ? lamPair[a - 1] : 0.0) + lamPair[a]) + (a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0));
         }
         // the other modes keep wJ rhsxyH by itself: G starts as -BF_H, the volume pairs below add the rest
@@ -394,16 +480,32 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       for (int a = 0; a < N1D; ++a) {
         const double *o = nodes + pos[a];
         q[a].rho = o[0 * S]; q[a].un = o[(4 + d) * S]; q[a].ut = o[(5 - d) * S];
-        q[a].beta = o[7 * S]; q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
+        q[a].beta = o[7 * S];
       }
-      PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
-        constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
-        double F[4];
-        fS_rot(A.half_inv_gm1, q[i], q[j], F);
-        double Sv = T.SHt[d][i][j][line];
+      if (quiet) {
+        PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
+          constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
+          double F[4];
+          fS_rot_quiet(A.half_inv_gm1, q[i], q[j], F);
+          double Sv = T.SHt[d][i][j][line];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
-      });
+          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+        });
+      } else {
+#pragma unroll
+        for (int a = 0; a < N1D; ++a) {
+          const double *o = nodes + pos[a];
+          q[a].rholog = o[8 * S]; q[a].betalog = o[9 * S];
+        }
+        PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
+          constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
+          double F[4];
+          fS_rot(A.half_inv_gm1, q[i], q[j], F);
+          double Sv = T.SHt[d][i][j][line];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+        });
+      }
     }
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
@@ -416,7 +518,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   __syncthreads();
 
   // ---- CFL: dt = min_i CFL * 0.5 * wJ_i / lambda_i, low_order_graph_viscosity.jl:222-281
-  if (DO_LOW && A.nstage == 1) {
+  if (DO_LOW && nst1) {
     double dtloc = INFINITY;
     if (active && d == 0) {
 #pragma unroll
@@ -443,7 +545,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     // 4..11 are only read before the barrier above, lamp only by the CFL block)
     double2 *tbuf = reinterpret_cast<double2 *>(nodes + 4 * S);   // [d][half][S]
     double *lstage = lamp;                                        // [EPB][2*N1D*NF], L_local layout
-    if (MODE == MODE_SUBCELL && A.nstage == 1) __syncthreads();   // CFL block done with lamp
+    if (nst1) __syncthreads();   // CFL block done with lamp
     if (active) {
     // ---- f_bar_H - f_bar_L by prefix sum (subcell.jl:163-206) and the limiting coefficients of
     //      this line's N1D+1 subcell faces (subcell.jl:248-349)
@@ -469,97 +571,117 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     double lv[NF];
 #pragma unroll
     for (int s = 0; s < NF; ++s) lv[s] = 1.0;
-    // First pass, branch-free: does ANY of this line's evaluations leave the common case "coefficient 1"
-    // (limiting_param_pos_easy)?  One divergent region per line instead of one per evaluation, and the common case
-    // runs as a single basic block in which the independent checks interleave.
+    // First pass, branch-free and division-free: is EVERY coefficient of this line certainly 1?  With u' = u^L + P,
+    //   rho(u') >= zeta rho(u^L)                  <=>  rho' - zeta rho_L >= 0
+    //   rho e(u') >= zeta rho e(u^L)              <=>  rho' (2 rho_L E' - zeta c_L) - |m'|^2 rho_L >= 0,  c_L = 2 rho_L E_L - |m_L|^2
+    // (the second line is 2 rho_L q(1) of the reference's quadratic q(l) = a l^2 + b l + c, limiter_utils.jl:85-90).
+    // rho e is concave in the conserved variables, so q > 0 on all of [0, 1] when q(0) = c > 0 and q(1) > 0: no root in
+    // (0, 1], and limiting_param_bound_rho_rhoe returns min(., 1) = 1.  Both tests carry a margin of 1e-9 relative to the
+    // size of their terms (rounding moves either evaluation by ~1e-16), so a line that passes has all coefficients 1 in
+    // the reference's evaluation as well; everything else -- a sliver of |q(1)| < 1e-9 |terms| around the limiter's
+    // activation and the genuinely limited faces -- goes to the exact evaluation below.
     bool all_easy = true;
-    if (!P2DE_FAST_LIMITER_TWO_PASS) all_easy = false;
-    else {
+    constexpr bool SURE = P2DE_FAST_SURE_LIMITER != 0;
+    static_assert(P2DE_FAST_LIMITER_TWO_PASS, "the single-pass limiter was removed");
+    {
 #pragma unroll
       for (int a = 0; a < N1D; ++a) {
         const double *o = nodes + pos[a];
         double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
         double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
+        // the other direction's share is in ITS rotated frame: momentum components swap
+        double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
+        Cons2 uL;   // u^L = Uq + dt rhsL (subcell.jl:269)
+        uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
+        uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
+        const double kk = 4 * dtl * rwJ[a];     // P = -/+ 4 dt (fH - fL) / wJ, subcell.jl:300,312,328,340
+        if (SURE) {
+          const double r2L = 2.0 * uL.rho, eL = r2L * uL.E;
+          const double cL = fma(-uL.m2, uL.m2, fma(-uL.m1, uL.m1, eL));   // 2 rho rho e of u^L
+          const double zc = A.zeta * cL, tolq = (1e-9 * eL) * uL.rho, tolr = 1e-9 * uL.rho;
+          all_easy = all_easy & (cL > 1e-9 * eL) & (uL.rho > 0.0);
+#pragma unroll
+          for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? (a > 0 || bc0) : (a < N1D - 1 || bc1)) {
+              const double ks = side ? kk : -kk;
+              const double *dFs = dFv[a + side];
+              const double rp = fma(ks, dFs[0], uL.rho), m1p = fma(ks, dFs[1], uL.m1), m2p = fma(ks, dFs[2], uL.m2), Ep = fma(ks, dFs[3], uL.E);
+              const double t1 = fma(r2L, Ep, -zc), msq = fma(m2p, m2p, m1p * m1p);
+              const double q1 = fma(-msq, uL.rho, rp * t1);
+              all_easy = all_easy & (fma(-A.zeta, uL.rho, rp) > tolr) & (q1 > tolq);
+            }
+          }
+        } else {
+          const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
+          const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
+          const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
+          double Pm[4], Pp[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
+          if (a > 0 || bc0) {
+            double qa, qb;
+            quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
+            all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0);
+          }
+          if (a < N1D - 1 || bc1) {
+            double qa, qb;
+            quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
+            all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0);
+          }
+        }
+        if (DIAG) {
+          if (d == 0 && A.rhsL_diag) {
+            const int node = a + line * N1D;
+            double r[4] = {r0, r1, r2, r3};
+            store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+          }
+          if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
+            const int node = d == 0 ? a + line * N1D : line + a * N1D;
+            double *hd = A.rhsH_diag + (k * Nq + node) * 4;
+            atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
+            atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
+          }
+        }
+      }
+    }
+    if (A.dbg) { atomicAdd(A.dbg + DBG_LINES, 1ull); if (!all_easy) atomicAdd(A.dbg + DBG_LINES_NOT_EASY, 1ull); }
+    if (!all_easy) {
+      // exact evaluation (the reference's formulas: quadratic coefficients, root selection), node by node
+      bool one = true;
+#pragma unroll 1
+      for (int a = 0; a < N1D; ++a) {
+        const int pa = line_pos<N1D>(el, d, line, a);   // (= pos[a]; a is a run-time index in this rolled loop)
+        const double *o = nodes + pa;
+        double2 m0 = partsL[(d * 2 + 0) * S + pa], m1 = partsL[(d * 2 + 1) * S + pa];
+        double2 o0 = partsL[((1 - d) * 2 + 0) * S + pa], o1 = partsL[((1 - d) * 2 + 1) * S + pa];
         double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
         Cons2 uL;
         uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
         uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
+        // rhoe_ufun (:75-78) with a Newton reciprocal; c = E rho - |m|^2/2 - rho Lrhoe = (1 - zeta) rho rhoe
         const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
         const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
         const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
         const double kk = 4 * dtl * rwJ[a];
-        double Pm[4], Pp[4];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
-        if (a > 0 || bc0) {
-          double qa, qb;
-          quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
-          all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0);
-        }
-        if (a < N1D - 1 || bc1) {
-          double qa, qb;
-          quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
-          all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0);
-        }
-        if (d == 0 && A.rhsL_diag) {
-          const int node = a + line * N1D;
-          double r[4] = {r0, r1, r2, r3};
-          store4(A.rhsL_diag + (k * Nq + node) * 4, r);
-        }
-        if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
-          const int node = d == 0 ? a + line * N1D : line + a * N1D;
-          double *hd = A.rhsH_diag + (k * Nq + node) * 4;
-          atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
-          atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
-        }
-      }
-    }
-    if (!all_easy) {
+        for (int side = 0; side < 2; ++side) {
+          if (side == 0 ? (a > 0 || bc0) : (a < N1D - 1 || bc1)) {
+            double Pv[4];
 #pragma unroll
-    for (int a = 0; a < N1D; ++a) {
-      const double *o = nodes + pos[a];
-      double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-      double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
-      // the other direction's share is in ITS rotated frame: momentum components swap
-      double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
-      Cons2 uL;
-      uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
-      uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
-      // rhoe_ufun (:75-78) with a Newton reciprocal; c = E rho - |m|^2/2 - rho Lrhoe = (1 - zeta) rho rhoe
-      const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
-      const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
-      const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
-      if (!P2DE_FAST_LIMITER_TWO_PASS) {
-      if (d == 0 && A.rhsL_diag) {
-        const int node = a + line * N1D;
-        double r[4] = {r0, r1, r2, r3};
-        store4(A.rhsL_diag + (k * Nq + node) * 4, r);
+            for (int c = 0; c < 4; ++c) Pv[c] = (side ? kk : -kk) * dFv_at(dFv, a + side, c);
+            double qa, qb;
+            quad_coeff_ab(uL, Pv, Lrhoe, qa, qb);
+            // (lv <= 1 throughout, so the common result 1.0 of limiting_param_pos needs no min)
+            if (!limiting_param_pos_easy(uL.rho, Pv[0], Lrho, qa, qb, c0)) {
+              if (A.dbg) atomicAdd(A.dbg + DBG_LIMITER_SLOW, 1ull);
+              const double lnew = limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pv[0], Lrho, qa, qb, c0);
+              lv_set_min(lv, a + side, lnew);
+              one = one & (lnew >= 1.0);
+            }
+          }
+        }
       }
-      if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
-        const int node = d == 0 ? a + line * N1D : line + a * N1D;
-        double *hd = A.rhsH_diag + (k * Nq + node) * 4;
-        atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
-        atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
-      }
-      }
-      const double kk = 4 * dtl * rwJ[a];
-      double Pm[4], Pp[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
-      // (lv <= 1 throughout, so the common result 1.0 of limiting_param_pos needs no min)
-      if (a > 0 || bc0) {
-        double qa, qb;
-        quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
-        if (!limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0))
-          lv[a] = jl_min(lv[a], limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pm[0], Lrho, qa, qb, c0));
-      }
-      if (a < N1D - 1 || bc1) {
-        double qa, qb;
-        quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
-        if (!limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0))
-          lv[a + 1] = jl_min(lv[a + 1], limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pp[0], Lrho, qa, qb, c0));
-      }
-    }
+      all_easy = one;   // a line the margin sent here may still have all coefficients 1
     }   // !all_easy
     // (update_blending_factor! = 1 without shock capturing, shock_capture.jl:111-114: the FAST path has none, so the
     //  min with A.blend is the identity)
@@ -602,7 +724,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       for (int it = 0; it < NIT; ++it) {   // resW of this thread's nodes: in flight across the barrier
         const int n = tid + it * NT;
         wres[it][0] = make_double2(0.0, 0.0); wres[it][1] = make_double2(0.0, 0.0);
-        if (A.fuse && n < S && (full || kb + n / Nq < M.K)) {
+        if (fuse && n < S && (full || kb + n / Nq < M.K)) {
           const double2 *q = reinterpret_cast<const double2 *>(rw + n * 4);
           wres[it][0] = q[0]; wres[it][1] = q[1];
         }
@@ -616,10 +738,10 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         const int n = tid + it * NT;
         const int e2 = n / Nq, node = n % Nq;
         if (n < S && (full || kb + e2 < M.K)) {
-          const int p2 = e2 * Nq + T.posn[e2 & 3][node];
+          const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
           double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
           double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
-          if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
+          if (fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
             r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
             r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
             r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
@@ -641,14 +763,14 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       const int e2 = n / Nq, node = n % Nq;
       okv[it] = n < S && (full || kb + e2 < M.K);
       // swizzled position: arithmetic for N1D = 4 (no dependent table look-up), table otherwise
-      p2v[it] = N1D == 4 ? node_pos<N1D>(e2, node % N1D, node / N1D) : (n < S ? e2 * Nq + T.posn[e2 & 3][node] : 0);
+      p2v[it] = n < S ? node_pos<N1D>(e2, node % N1D, node / N1D) : 0;
     }
 #pragma unroll
     for (int it = 0; it < NIT; ++it)
       if (okv[it]) {
         const int p2 = p2v[it];
         xv[it][0] = tbuf[0 * S + p2]; xv[it][1] = tbuf[1 * S + p2]; xv[it][2] = tbuf[2 * S + p2]; xv[it][3] = tbuf[3 * S + p2];
-        if (A.fuse) {
+        if (fuse) {
 #pragma unroll
           for (int c = 0; c < 4; ++c) uo[it][c] = nodes[c * S + p2];
         }
@@ -659,7 +781,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       if (okv[it]) {
         const double2 x0 = xv[it][0], x1 = xv[it][1], y0 = xv[it][2], y1 = xv[it][3];
         double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
-        if (A.fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
+        if (fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
           r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (uo[it][0] + dtl * r[0]);
           r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (uo[it][1] + dtl * r[1]);
           r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (uo[it][2] + dtl * r[2]);
@@ -763,16 +885,37 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
   else stage_fast_impl<N1D, MODE, EPB, false, false>(A, M, Tc, kb);
 }
 
-// stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (its own kernel: as a fourth and fifth copy of
-// the body inside stage_kernel_fast it made ptxas' allocation for the other copies 3 % slower)
+// The three kernels of the direct schedule (p2de_ssp33_step, subcell limiter): the stage's role is a compile-time fact
+// (KIND), so the CFL block, the fused combine and the diagnostics are present or absent without run-time flags.  Each is
+// its own __global__ function: as further copies of the body inside one kernel they made ptxas' register allocation for
+// the other copies worse (measured, 3 %).
+template <int N1D, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
+stage_kernel_fast_s1(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                     const __grid_constant__ Tables2D<N1D> Tc) {
+  bool interior;
+  const long long kb = fast_batch<EPB>(A, M, interior);
+  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, false, KIND_S1>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, false, KIND_S1>(A, M, Tc, kb);
+}
+template <int N1D, int EPB>
+__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
+stage_kernel_fast_s3(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
+                     const __grid_constant__ Tables2D<N1D> Tc) {
+  bool interior;
+  const long long kb = fast_batch<EPB>(A, M, interior);
+  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, false, KIND_S23>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, false, KIND_S23>(A, M, Tc, kb);
+}
+// stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (the stage-1 combine formed while loading)
 template <int N1D, int EPB>
 __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
 stage_kernel_fast_defer(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
                         const __grid_constant__ Tables2D<N1D> Tc) {
   bool interior;
   const long long kb = fast_batch<EPB>(A, M, interior);
-  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, true>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, true>(A, M, Tc, kb);
+  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, true, P2DE_FAST_KINDS ? KIND_S23 : KIND_RT>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, true, P2DE_FAST_KINDS ? KIND_S23 : KIND_RT>(A, M, Tc, kb);
 }
 
 // update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation

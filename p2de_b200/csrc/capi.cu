@@ -19,6 +19,7 @@
 #include "../../include/p2de_b200.h"
 #include "kernels2d.cuh"
 #include "stage_fast.cuh"
+#include "stage_subcell.cuh"
 #include "gauss.cuh"
 #include "kernels1d.cuh"
 
@@ -483,6 +484,13 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   const size_t base = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
   const bool sub = !FAST && MODE == MODE_SUBCELL;
   size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
+  constexpr bool SUBK = FAST && MODE == MODE_SUBCELL, SUBK_ENV = SUBK;
+  // the default configuration with the subcell limiter has its own kernel family (stage_subcell.cuh);
+  // P2DE_OLD_SUBCELL=1 keeps stage_fast.cuh's MODE_SUBCELL body (A/B and cross-check aid)
+  const char *old_env = SUBK_ENV ? getenv("P2DE_OLD_SUBCELL") : nullptr;   // read per launch: tests flip it within one process
+  const bool old_subcell = old_env && atoi(old_env) != 0;
+  const bool newsub = SUBK && !old_subcell;
+  if (newsub) smem = sizeof(double) * (fast_table_doubles<N1D>() + (size_t)EPB * subcell_smem_doubles_per_elem<N1D>());
   static const size_t smem_pad = [] { const char *pad = getenv("P2DE_SMEM_PAD"); return pad ? (size_t)atoi(pad) : (size_t)0; }();
   smem += smem_pad;   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
@@ -493,9 +501,19 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
     if (default_gauss) kern = stage_kernel<N1D, MODE, EPB, 1>;
   }
   // (the attribute is per device and per function: one slot per device for this instantiation)
-  static size_t attr_set_dev[64] = {};
+  static size_t attr_set_dev[64] = {}, attr_sub_dev[64] = {};
+  if constexpr (SUBK) {
+    size_t &attr_sub = attr_sub_dev[h->device & 63];
+    if (newsub && smem > attr_sub) {
+      CU(h, cudaFuncSetAttribute(stage_subcell_rt<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s1<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s2<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s3<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_sub = smem;
+    }
+  }
   size_t &attr_set = attr_set_dev[h->device & 63];
-  if (smem > attr_set) {
+  if (!newsub && smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if constexpr (!FAST && MODE == MODE_SUBCELL) {
       CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -512,7 +530,12 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
     // the direct schedule's kernels know their role at compile time (stage_fast.cuh: KIND); p2de_rhs and the testing
     // schedules (diagnostics, un-fused stages 2/3, fused without direct output) keep the run-time version
     const bool nodiag = !A.rhsL_diag && !A.rhsH_diag;
-    if (A.defer_add) kern = stage_kernel_fast_defer<N1D, EPB>;
+    if (newsub) {
+      if (A.defer_add) kern = stage_subcell_s2<N1D, EPB>;
+      else if (nodiag && A.nstage == 1 && !A.fuse) kern = stage_subcell_s1<N1D, EPB>;
+      else if (nodiag && A.nstage != 1 && A.fuse) kern = stage_subcell_s3<N1D, EPB>;
+      else kern = stage_subcell_rt<N1D, EPB>;
+    } else if (A.defer_add) kern = stage_kernel_fast_defer<N1D, EPB>;
     else if (P2DE_FAST_KINDS && nodiag && A.nstage == 1 && !A.fuse) kern = stage_kernel_fast_s1<N1D, EPB>;
     else if (P2DE_FAST_KINDS && nodiag && A.nstage != 1 && A.fuse) kern = stage_kernel_fast_s3<N1D, EPB>;
   }

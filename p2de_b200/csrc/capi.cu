@@ -115,6 +115,7 @@ struct p2de_handle {
   double *U[2] = {nullptr, nullptr};  // state ping-pong; U[cur] is Uq, the other one is resW / next
   bool direct = false;                // FAST subcell path: stages 2/3 write the state from the stage kernel
   bool defer = false;                 // ... and stage 2 forms the stage-1 combine on the fly (P2DE_NO_DEFER=1 disables)
+  bool rpre_w = false;                // the rpre buffer holds stage 1's W = U + cap rhsU (run_stage: wform), not rhsU
   int cur = 0;
   double *rhsL = nullptr, *dF = nullptr, *lpre = nullptr, *rhsU = nullptr;
   double *rpre = nullptr, *dFend = nullptr;   // FAST subcell scratch
@@ -248,6 +249,10 @@ template <> Tables2D<5> &tables<5>(p2de_handle *h) { return h->t5; }
 #define P2DE_EPB5 12   // N=4 (N1D=5): elements per CTA (120 threads, 3 CTAs/SM at 168 registers: measured best of 6..16)
 #endif
 template <int N1D> struct Launch { static constexpr int EPB = N1D == 5 ? P2DE_EPB5 : P2DE_EPB; };
+#ifndef P2DE_EPB_SUB4
+#define P2DE_EPB_SUB4 8   // subcell family at N=3: 8 elements (64 threads) per CTA, 8 CTAs/SM: the CTAs' load phases interleave better (measured +3 %)
+#endif
+template <int N1D> struct LaunchSub { static constexpr int EPB = N1D == 4 ? P2DE_EPB_SUB4 : Launch<N1D>::EPB; };
 
 // Extract the per-line tables from the caller's operators and verify the structure this
 // kernel family relies on (tensor-product LGL collocation on a Cartesian mesh).
@@ -479,65 +484,50 @@ __global__ void reduce_kernel(const double *U, const double *wq, int Nq, long lo
 
 template <int N1D, int MODE, bool FAST>
 int launch_stage_t(p2de_handle *h, const StageArgs &A) {
-  constexpr int EPB = Launch<N1D>::EPB, TPE = 2 * N1D;
+  constexpr bool SUBK = FAST && MODE == MODE_SUBCELL;   // the default configuration with the subcell limiter: stage_subcell.cuh
+  constexpr int EPB = SUBK ? LaunchSub<N1D>::EPB : Launch<N1D>::EPB, TPE = 2 * N1D;
   constexpr int TBL = FAST ? fast_table_doubles<N1D>() : (int)((sizeof(Tables2D<N1D>) + 15) / 16) * 2;
   const size_t base = sizeof(double) * (TBL + (size_t)EPB * (FAST ? fast_smem_doubles_per_elem<N1D, MODE>() : stage_smem_doubles_per_elem<N1D, MODE>()));
   const bool sub = !FAST && MODE == MODE_SUBCELL;
   size_t smem = base + (sub ? sizeof(double) * EPB * stage_smem_extra_doubles_per_elem<N1D>(A.tvd != 0, A.cell_entropy != 0) : 0);
-  constexpr bool SUBK = FAST && MODE == MODE_SUBCELL, SUBK_ENV = SUBK;
-  // the default configuration with the subcell limiter has its own kernel family (stage_subcell.cuh);
-  // P2DE_OLD_SUBCELL=1 keeps stage_fast.cuh's MODE_SUBCELL body (A/B and cross-check aid)
-  const char *old_env = SUBK_ENV ? getenv("P2DE_OLD_SUBCELL") : nullptr;   // read per launch: tests flip it within one process
-  const bool old_subcell = old_env && atoi(old_env) != 0;
-  const bool newsub = SUBK && !old_subcell;
-  if (newsub) smem = sizeof(double) * (fast_table_doubles<N1D>() + (size_t)EPB * subcell_smem_doubles_per_elem<N1D>());
+  // kernel of the subcell family (stage_subcell.cuh): stage 1 in W form when run_stage asked for it, stages 2/3 fused
+  const bool nodiag = !A.rhsL_diag && !A.rhsH_diag;
+  const bool sub_s1 = SUBK && A.wform && nodiag && A.nstage == 1 && !A.fuse && !A.defer_add;
+  const bool sub_s23 = SUBK && (A.defer_add || (nodiag && A.nstage != 1 && A.fuse));
+  if (SUBK) smem = sizeof(double) * (fast_table_doubles<N1D>() + (size_t)EPB * subcell_smem_doubles_per_elem<N1D>(sub_s1 || sub_s23));
   static const size_t smem_pad = [] { const char *pad = getenv("P2DE_SMEM_PAD"); return pad ? (size_t)atoi(pad) : (size_t)0; }();
   smem += smem_pad;   // profiling aid: lowers the number of resident CTAs
   void (*kern)(const StageArgs, const MeshTopo, const Tables2D<N1D>);
-  if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>; else kern = stage_kernel<N1D, MODE, EPB, 0>;
+  if constexpr (SUBK) kern = stage_subcell_rt<N1D, EPB>;
+  else if constexpr (FAST) kern = stage_kernel_fast<N1D, MODE, EPB>;
+  else kern = stage_kernel<N1D, MODE, EPB, 0>;
   // the shipped-examples configuration on Gauss nodes has its options compiled in (kernels2d.cuh: CFG = 1)
   const bool default_gauss = !FAST && MODE == MODE_SUBCELL && h->slim;
   if constexpr (!FAST && MODE == MODE_SUBCELL) {
     if (default_gauss) kern = stage_kernel<N1D, MODE, EPB, 1>;
   }
   // (the attribute is per device and per function: one slot per device for this instantiation)
-  static size_t attr_set_dev[64] = {}, attr_sub_dev[64] = {};
-  if constexpr (SUBK) {
-    size_t &attr_sub = attr_sub_dev[h->device & 63];
-    if (newsub && smem > attr_sub) {
-      CU(h, cudaFuncSetAttribute(stage_subcell_rt<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(h, cudaFuncSetAttribute(stage_subcell_s1<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(h, cudaFuncSetAttribute(stage_subcell_s2<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(h, cudaFuncSetAttribute(stage_subcell_s3<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_sub = smem;
-    }
-  }
+  static size_t attr_set_dev[64] = {};
   size_t &attr_set = attr_set_dev[h->device & 63];
-  if (!newsub && smem > attr_set) {
+  if constexpr (SUBK) {
+    const size_t smem_full = sizeof(double) * (fast_table_doubles<N1D>() + (size_t)EPB * subcell_smem_doubles_per_elem<N1D>(false)) + smem_pad;
+    if (smem_full > attr_set) {
+      CU(h, cudaFuncSetAttribute(stage_subcell_rt<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s1<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s2<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      CU(h, cudaFuncSetAttribute(stage_subcell_s3<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full));
+      attr_set = smem_full;
+    }
+    if (A.defer_add) kern = stage_subcell_s2<N1D, EPB>;
+    else if (sub_s1) kern = stage_subcell_s1<N1D, EPB>;
+    else if (sub_s23) kern = stage_subcell_s3<N1D, EPB>;
+  } else if (smem > attr_set) {
     CU(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if constexpr (!FAST && MODE == MODE_SUBCELL) {
       CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CU(h, cudaFuncSetAttribute(stage_kernel<N1D, MODE, EPB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    if constexpr (FAST && MODE == MODE_SUBCELL) {
-      CU(h, cudaFuncSetAttribute(stage_kernel_fast_defer<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(h, cudaFuncSetAttribute(stage_kernel_fast_s1<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CU(h, cudaFuncSetAttribute(stage_kernel_fast_s3<N1D, EPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
     attr_set = smem;
-  }
-  if constexpr (FAST && MODE == MODE_SUBCELL) {
-    // the direct schedule's kernels know their role at compile time (stage_fast.cuh: KIND); p2de_rhs and the testing
-    // schedules (diagnostics, un-fused stages 2/3, fused without direct output) keep the run-time version
-    const bool nodiag = !A.rhsL_diag && !A.rhsH_diag;
-    if (newsub) {
-      if (A.defer_add) kern = stage_subcell_s2<N1D, EPB>;
-      else if (nodiag && A.nstage == 1 && !A.fuse) kern = stage_subcell_s1<N1D, EPB>;
-      else if (nodiag && A.nstage != 1 && A.fuse) kern = stage_subcell_s3<N1D, EPB>;
-      else kern = stage_subcell_rt<N1D, EPB>;
-    } else if (A.defer_add) kern = stage_kernel_fast_defer<N1D, EPB>;
-    else if (P2DE_FAST_KINDS && nodiag && A.nstage == 1 && !A.fuse) kern = stage_kernel_fast_s1<N1D, EPB>;
-    else if (P2DE_FAST_KINDS && nodiag && A.nstage != 1 && A.fuse) kern = stage_kernel_fast_s3<N1D, EPB>;
   }
   dim3 grid((unsigned)((h->K + EPB - 1) / EPB));
   StageArgs A2 = A;
@@ -618,28 +608,32 @@ int launch_update(p2de_handle *h, const UpdateArgs &A) {
   return fail(h, P2DE_ERR_UNSUPPORTED, "N=%d", h->cfg.N);
 }
 
-// Uout = a resW + b (Uin + dt r): the SSP stage combine (SSPRK33.jl:31-39) as a flat, fully coalesced pass
+// Uout = a resW + b (Uin + dt r): the SSP stage combine (SSPRK33.jl:31-39) as a flat, fully coalesced pass.
+// wcap > 0: r is stage 1's W = Uin + wcap rhsU (stage_subcell.cuh: KIND_S1), so Uin + dt rhsU = Uin + (dt / wcap) (W - Uin)
 __global__ void __launch_bounds__(256)
 axpy_update_kernel(double2 *__restrict__ Uout, const double2 *__restrict__ resW, const double2 *__restrict__ Uin,
-                   const double2 *__restrict__ r, long long n2, double a, double b, const double *dt_dev, double dt_host, int use_dt_dev) {
+                   const double2 *__restrict__ r, long long n2, double a, double b, const double *dt_dev, double dt_host, int use_dt_dev,
+                   double wcap) {
   const double dt = use_dt_dev ? dt_read(dt_dev) : dt_host;
   const bool plain = a == 0.0 && b == 1.0;
+  const double theta = wcap > 0.0 ? dt / wcap : 0.0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
     const double2 u = Uin[i], q = r[i];
     double2 o;
-    if (plain) { o.x = u.x + dt * q.x; o.y = u.y + dt * q.y; }
+    if (wcap > 0.0) { o.x = fma(theta, q.x - u.x, u.x); o.y = fma(theta, q.y - u.y, u.y); }
+    else if (plain) { o.x = u.x + dt * q.x; o.y = u.y + dt * q.y; }
     else { const double2 w = resW[i]; o.x = a * w.x + b * (u.x + dt * q.x); o.y = a * w.y + b * (u.y + dt * q.y); }
     Uout[i] = o;
   }
 }
 int launch_axpy(p2de_handle *h, double *Uout, const double *resW, const double *Uin, const double *r, double a, double b,
-                double dt_host, bool use_dt_dev) {
+                double dt_host, bool use_dt_dev, double wcap = 0.0) {
   const long long n2 = h->K * h->Nq * 2;
   const unsigned grid = (unsigned)std::min<long long>((n2 + 255) / 256, 148ll * 8 * 4);
   prof_begin(h, 1);
   axpy_update_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<double2 *>(Uout), reinterpret_cast<const double2 *>(resW),
                                                   reinterpret_cast<const double2 *>(Uin), reinterpret_cast<const double2 *>(r), n2, a, b,
-                                                  reinterpret_cast<const double *>(h->dt_bits), dt_host, use_dt_dev ? 1 : 0);
+                                                  reinterpret_cast<const double *>(h->dt_bits), dt_host, use_dt_dev ? 1 : 0, wcap);
   prof_end(h);
   CU(h, cudaGetLastError());
   h->launches++;
@@ -911,6 +905,14 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   // ... and the stage kernel's coefficients are final: when L_local is kept (State.jl:21; allocated by keep_diagnostics or
   // by the first p2de_rhs) each stage writes them straight into its own slot L_local[:, :, :, nstage], as SSP33! leaves them
   if (sym_free && h->Llocal) A.lpre = h->Llocal + (size_t)h->nLloc * h->K * (nstage - 1);
+  // stage 1 of a step: nobody but the stage-1 combine reads what the kernel leaves in rpre, and dt is not known before the
+  // whole grid has finished, so the kernel writes W = U + cap rhsU (cap = dt_host, the dt its limiter uses) and the combine
+  // below / the next stage's kernel takes U + (dt / cap) (W - U)  (stage_subcell.cuh: KIND_S1)
+  const bool wform = sym_free && nstage == 1 && !fuse && Uout && a == 0.0 && b == 1.0 && dt_host > 0.0;
+  A.wform = wform ? 1 : 0;
+  A.inv_cap = dt_host > 0.0 ? 1.0 / dt_host : 0.0;
+  if (nstage == 1) h->rpre_w = wform;
+  if (Uadd && !h->rpre_w) return fail(h, P2DE_ERR_STATE, "deferred stage-1 combine without a W-form stage 1");
   if (int rc = launch_stage(h, A)) return rc;
   if (h->comm) {
     if (nstage == 1 && h->mode != MODE_HIGH)   // global CFL dt (low_order_graph_viscosity.jl:242): min over all stripes
@@ -931,7 +933,7 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   B.fstar = h->fstar; B.gamma = h->cfg.gamma;
   if (direct) return 0;   // the stage kernel wrote the new state; nothing to symmetrise on the FAST path
   if (sym_free) {
-    if (Uout && combine) return launch_axpy(h, Uout, resW, Uin, h->rpre, a, b, dt_host, update_dt_dev);   // pure SSP combine
+    if (Uout && combine) return launch_axpy(h, Uout, resW, Uin, h->rpre, a, b, dt_host, update_dt_dev, wform ? dt_host : 0.0);   // pure SSP combine
     return 0;             // combine deferred into the next stage's kernel (StageArgs.defer_add)
   }
   if (h->mode == MODE_SUBCELL || Uout) return launch_update(h, B);
@@ -1181,7 +1183,7 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
     // needs an output buffer other than the stage input: U1 -> Ub (dense update, dt only known after the
     // stage-1 kernel), U2 -> the rpre buffer (free once the stage-1 update has consumed it), U^{n+1} -> over
     // U^n, which stage 3 reads only as its own resW, node by node, by the thread that then writes the node.
-    if (h->defer) {
+    if (h->defer && cap > 0.0) {
       // ... and the stage-1 combine U1 = U^n + dt rhsU is not materialised at all: stage 1 leaves rhsU in the rpre
       // buffer and the stage-2 kernel forms U1 while loading (same bytes as reading U1 and resW = U^n): 4 launches
       if (int rc = run_stage(h, Ua, 1, t, cap, false, true, Ub, Ua, 0.0, 1.0, false, nullptr, false)) return rc;

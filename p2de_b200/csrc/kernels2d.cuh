@@ -102,9 +102,11 @@ struct StageArgs {
   const double *rhsLpre;             // [K][Nq][4] low-order rhs of ALL elements (a MODE_LOW pre-pass): the stencil crosses faces
   int cell_entropy;                  // 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound(beta)
   double bound_beta;
-  // FAST subcell kernel, stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (the stage-1 SSP combine
+  // subcell family, stage 2 of the direct schedule: the stage input is Uq + (dt / dt_host) (defer_add - Uq), defer_add = stage 1's W (the stage-1 SSP combine
   // U1 = U^n + dt rhsU, SSPRK33.jl:31-33, formed on the fly instead of by a separate pass over the mesh)
   const double *defer_add;
+  double inv_cap;                    // 1 / dt_host
+  int wform;                         // stage 1 of p2de_ssp33_step (subcell family): write W = U + dt_host rhsU instead of rhsU (stage_subcell.cuh: KIND_S1)
   int rowblocks;                     // FAST kernel: > 0 = 2D grid (rowblocks x Ky), Kx = rowblocks * EPB; 0 = 1D grid over batches
   double *fstar;                     // Gauss + cell entropy: [K][Nfp][2][4] normal components of fstar_H, fstar_L (State.jl:11-12)
   unsigned long long *dbg;           // nullptr, or the counters of p2de_debug_counters (P2DE_DBG_*): which instantiations ran, data-dependent shortcuts taken

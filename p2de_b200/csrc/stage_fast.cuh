@@ -15,7 +15,7 @@
 //   * that exact zero also makes the interface coefficients 1 on both sides of every interior face, so the
 //     limiter's symmetrisation is the identity and no second kernel follows (see "End faces" below);
 //   * the body is compiled per CTA kind: INTERIOR batches (strictly inside a structured mesh) have no
-//     boundary-condition code at all; DEFER (its own kernel) forms the stage-1 SSP combine while loading;
+//     boundary-condition code at all;
 //   * an L2 prefetch of the batch one wave of resident CTAs ahead, table loads overlapped with the state loads,
 //     a branch-free first pass of the limiter over the whole line (profiles/README.md has each step's measurement).
 #pragma once
@@ -27,9 +27,6 @@ namespace p2de {
 #ifndef P2DE_FAST_MIN_BLOCKS
 #define P2DE_FAST_MIN_BLOCKS 4
 #endif
-#ifndef P2DE_FAST_LIMITER_TWO_PASS
-#define P2DE_FAST_LIMITER_TWO_PASS 1
-#endif
 #ifndef P2DE_FAST_PREFETCH
 #define P2DE_FAST_PREFETCH 1
 #endif
@@ -37,32 +34,15 @@ namespace p2de {
 #define P2DE_FAST_MIN_BLOCKS5 3   // N=4 (N1D=5): 168 registers, no spills
 #endif
 // A/B switches of this round's restructurings (profiles/README.md has each step's measurement)
-#ifndef P2DE_FAST_SURE_LIMITER
-#define P2DE_FAST_SURE_LIMITER 1   // division-free sufficient test "every coefficient of the line is 1" before the exact evaluation
-#endif
 #ifndef P2DE_FAST_QUIET_PAIRS
 #define P2DE_FAST_QUIET_PAIRS 1    // warps whose elements cannot leave logmean's series branch: two-point flux without logs / selects
 #endif
-#ifndef P2DE_FAST_KINDS
-#define P2DE_FAST_KINDS 1          // stage role (stage 1 / stages 2,3) known at compile time in the direct schedule's kernels
-#endif
 
-// How much of the stage's role is a compile-time fact (MODE_SUBCELL; the other modes use KIND_RT):
-//   KIND_RT   run-time flags of StageArgs (p2de_rhs: any stage index, optional diagnostics, optional fused combine)
-//   KIND_S1   stage 1 of the direct schedule: CFL reduction, writes rhsU, no diagnostics
-//   KIND_S23  stages 2 and 3 of the direct schedule: SSP combine fused, no CFL reduction, no diagnostics
-enum { KIND_RT = 0, KIND_S1 = 1, KIND_S23 = 2 };
+// (this file keeps the element-local limiters and the unlimited right-hand sides -- MODE_ZHANGSHU, MODE_LOW, MODE_HIGH -- and
+//  the pointwise helpers; the subcell limiter's kernels are in stage_subcell.cuh)
 
 // constants of logmean's series branch (:315-317) and its reciprocal: read as constant-bank operands
 __constant__ double kSeries[5] = {-0.2, 0.0512, 0.026038857142857, 0.2, 0.0912};
-
-// U + dt * R at one node (the deferred stage-1 combine, StageArgs.defer_add)
-P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pr, double dt) {
-  Cons2 U = load_cons(pu);
-  const Cons2 R = load_cons(pr);
-  U.rho = fma(dt, R.rho, U.rho); U.m1 = fma(dt, R.m1, U.m1); U.m2 = fma(dt, R.m2, U.m2); U.E = fma(dt, R.E, U.E);
-  return U;
-}
 
 // state in the frame of one axis: (rho, normal momentum, tangential momentum, E)
 struct ConsR { double rho, mn, mt, E; };
@@ -187,7 +167,7 @@ __device__ __forceinline__ int line_pos(int el, int d, int line, int a) {
 }
 
 // doubles of shared memory per element, besides the tables: 12 node fields, rhsxyL shares (partsL),
-// rhsxyH shares (partsH, not MODE_SUBCELL), the CFL lambda sums [2][Nq] that are later reused as the
+// rhsxyH shares (partsH), the CFL lambda sums [2][Nq] that are later reused as the
 // L_local staging [2*N1D*(N1D+1)], and lmin
 template <int N1D>
 __host__ __device__ constexpr int fast_lamp_per_elem() {
@@ -199,7 +179,7 @@ __host__ __device__ constexpr int fast_table_doubles() { return ((Tables2D<N1D>:
 template <int N1D, int MODE>
 constexpr int fast_smem_doubles_per_elem() {
   constexpr int Nq = N1D * N1D;
-  return 12 * Nq + 8 * Nq + ((MODE == MODE_SUBCELL) ? 0 : 8 * Nq) + fast_lamp_per_elem<N1D>() + N1D + 1;   // + 1: the element's "quiet" flag
+  return 12 * Nq + 8 * Nq + 8 * Nq + fast_lamp_per_elem<N1D>() + N1D + 1;   // + 1: the element's "quiet" flag
 }
 
 
@@ -207,7 +187,7 @@ constexpr int fast_smem_doubles_per_elem() {
 // are k -+ 1 / k -+ Kx and no face carries a boundary condition, so the boundary-condition branches, the seed
 // f_bar_H - f_bar_L of the prefix sums and the two end-face limiter evaluations of every line vanish at compile time
 // (fewer live registers: the generic version spills the boundary flags across the whole kernel).
-template <int N1D, int MODE, int EPB, bool INTERIOR, bool DEFER, int KIND = KIND_RT>
+template <int N1D, int MODE, int EPB, bool INTERIOR>
 __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTopo &M, const Tables2D<N1D> &Tc, const long long kb) {
   constexpr int Nq = N1D * N1D, NF = N1D + 1, NFLD = 12, HALF = EPB * N1D, NT = 2 * HALF;
   constexpr bool DO_LOW = MODE != MODE_HIGH, DO_HIGH = MODE != MODE_LOW;
@@ -218,14 +198,12 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
   double *nodes = sm + TBL;                       // [NFLD][S]   swizzled node positions
   double2 *partsL = reinterpret_cast<double2 *>(nodes + NFLD * S);   // [d][half][S]
-  double2 *partsH = partsL + 4 * S;                                   // [d][half][S] (not MODE_SUBCELL)
-  double *lamp = reinterpret_cast<double *>(partsH + ((MODE == MODE_SUBCELL) ? 0 : 4 * S));  // [2][S] / lstage
+  double2 *partsH = partsL + 4 * S;                                   // [d][half][S]
+  double *lamp = reinterpret_cast<double *>(partsH + 4 * S);          // [2][S]
   double *lmin = lamp + EPB * fast_lamp_per_elem<N1D>();   // [EPB][N1D]
   int *needlog = reinterpret_cast<int *>(lmin + EPB * N1D);   // [EPB] (LAZY_LOGS): some pair of the element may leave logmean's series branch
-  static_assert(KIND == KIND_RT || MODE == MODE_SUBCELL, "stage kinds exist for the subcell limiter's direct schedule only");
-  const bool nst1 = KIND == KIND_S1 || (KIND == KIND_RT && A.nstage == 1);      // CFL reduction in this launch
-  const bool fuse = KIND == KIND_S23 || (KIND == KIND_RT && MODE == MODE_SUBCELL && A.fuse != 0);   // SSP combine fused into the output phase
-  constexpr bool DIAG = KIND == KIND_RT;                                         // rhsL / rhsH diagnostics possible
+  static_assert(MODE != MODE_SUBCELL, "the subcell limiter has its own kernel family (stage_subcell.cuh)");
+  const bool nst1 = A.nstage == 1;      // CFL reduction in this launch
 
   const int tid = threadIdx.x;
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
@@ -236,7 +214,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
   const double *Ubase = A.Uq + kb * (Nq * 4);             // this batch's states; 32-bit offsets from here on
   if (A.dbg && tid == 0) {   // p2de_debug_counters: which instantiation this CTA runs
     atomicAdd(A.dbg + (INTERIOR ? DBG_CTA_INTERIOR : DBG_CTA_GENERAL), 1ull);
-    if (DEFER) atomicAdd(A.dbg + DBG_CTA_DEFER, 1ull);
   }
 
   if (P2DE_FAST_PREFETCH) {
@@ -248,10 +225,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     constexpr int LINES = EPB * Nq * 32 / 128;
     if (kp + EPB <= M.K) {
       if (tid < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(A.Uq + kp * (Nq * 4) + tid * 16));
-      else if (DEFER && tid < 2 * LINES)      // (resW is Uq itself in that stage)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.defer_add + kp * (Nq * 4) + (tid - LINES) * 16));
-      else if (fuse && tid < 2 * LINES)
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kp * (Nq * 4) + (tid - LINES) * 16));
     }
   }
   // tables: coalesced copy from global memory (an indexed read of the kernel parameter would be a lane-serialised
@@ -286,8 +259,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         const bool in_batch = d == 0 && (e ? el + 1 < EPB : el > 0);
         nbpos[e] = -1;
         if (in_batch) nbpos[e] = 0;
-        else if (DEFER)
-          UnbC[e] = load_cons_plus(Ubase + ((long long)(el + dk) * Nq + node) * 4, A.defer_add + kb * (Nq * 4) + ((long long)(el + dk) * Nq + node) * 4, dtl);
         else UnbC[e] = load_cons(Ubase + ((long long)(el + dk) * Nq + node) * 4);
       }
     } else if (active) {
@@ -298,7 +269,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       for (int e = 0; e < 2; ++e) {
         nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
         const long long noff = (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4;
-        UnbC[e] = (DEFER) ? load_cons_plus(A.Uq + noff, A.defer_add + noff, dtl) : load_cons(A.Uq + noff);
+        UnbC[e] = load_cons(A.Uq + noff);
       }
     }
   }
@@ -311,10 +282,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     const int n = tid + it * NT;
     Uraw[it].rho = 1.0; Uraw[it].m1 = 0.0; Uraw[it].m2 = 0.0; Uraw[it].E = 1.0;
     if (n < S && (full || kb + n / Nq < M.K)) {
-      Uraw[it] = (DEFER) ? load_cons_plus(Ubase + n * 4, A.defer_add + kb * (Nq * 4) + n * 4, dtl)
-                                                       : load_cons(Ubase + n * 4);
-      if (fuse && !DEFER)   // the flat output phase of this same thread reads resW here: pull it into L2 now
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
+      Uraw[it] = load_cons(Ubase + n * 4);
     }
   }
 #pragma unroll
@@ -417,14 +385,6 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
       double BFH[2][4];
 #pragma unroll
       for (int c = 0; c < 4; ++c) dF0[c] = 0.0;
-      if (MODE == MODE_SUBCELL) {
-        // G = wJ (rhsxyH - rhsxyL) starts as Q0F1 - (BF_H - BF_L): the volume part of -GL; the surface terms
-        // cancel identically on interior faces (identity projection) and leave the LF term on inflow/outflow faces
-#pragma unroll
-        for (int a = 0; a < N1D; ++a)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) G[a][c] = -GL[a][c];
-      }
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int ae = e ? N1D - 1 : 0;
@@ -447,9 +407,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
           double bfs = B * (0.5 * (fl[ae][c] + fP[c]));
           double lf = lamB * (up[c] - uf[c]);
           GL[ae][c] -= bfs - lf;                         // - BF_L
-          if (MODE == MODE_SUBCELL) { if (bce) G[ae][c] -= lf; }
-          else BFH[e][c] = bce ? bfs : bfs - lf;         // BF_H (LFc = 0 on inflow/outflow faces)
-          if (e == 0 && bce) dF0[c] = lf;                // BF_H - BF_L on the seed face
+          BFH[e][c] = bce ? bfs : bfs - lf;              // BF_H (LFc = 0 on inflow/outflow faces)
         }
         lamFace[e] = lamB;
       }
@@ -462,14 +420,12 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
           if (nst1)   // this direction's share of lambda_i (:222-281): its two volume pairs and its face
             lamp[d * S + pos[a]] = ((a > 0 ? lamPair[a - 1] : 0.0) + lamPair[a]) + (a == 0 ? lamFace[0] : (a == N1D - 1 ? lamFace[1] : 0.0));
         }
-        // the other modes keep wJ rhsxyH by itself: G starts as -BF_H, the volume pairs below add the rest
-        if (MODE != MODE_SUBCELL) {
+        // G = wJ rhsxyH starts as -BF_H, the volume pairs below add the rest
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            double bh = a == 0 ? BFH[0][c] : 0.0;
-            if (a == N1D - 1) bh += BFH[1][c];
-            G[a][c] = -bh;
-          }
+        for (int c = 0; c < 4; ++c) {
+          double bh = a == 0 ? BFH[0][c] : 0.0;
+          if (a == N1D - 1) bh += BFH[1][c];
+          G[a][c] = -bh;
         }
       }
     }
@@ -509,7 +465,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     }
 #pragma unroll
     for (int a = 0; a < N1D; ++a) {
-      if (MODE != MODE_SUBCELL && DO_HIGH) {
+      if (DO_HIGH) {
         partsH[(d * 2 + 0) * S + pos[a]] = make_double2(G[a][0] * rwJ[a], G[a][1] * rwJ[a]);
         partsH[(d * 2 + 1) * S + pos[a]] = make_double2(G[a][2] * rwJ[a], G[a][3] * rwJ[a]);
       }
@@ -538,270 +494,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
     if ((tid & 31) == 0) dt_publish(A.dt_bits, dtloc);
   }
 
-  if (!active && MODE != MODE_ZHANGSHU && MODE != MODE_SUBCELL) return;
-
-  if (MODE == MODE_SUBCELL) {
-    // shared-memory staging of this kernel's outputs (regions that are dead by now: node fields
-    // 4..11 are only read before the barrier above, lamp only by the CFL block)
-    double2 *tbuf = reinterpret_cast<double2 *>(nodes + 4 * S);   // [d][half][S]
-    double *lstage = lamp;                                        // [EPB][2*N1D*NF], L_local layout
-    if (nst1) __syncthreads();   // CFL block done with lamp
-    if (active) {
-    // ---- f_bar_H - f_bar_L by prefix sum (subcell.jl:163-206) and the limiting coefficients of
-    //      this line's N1D+1 subcell faces (subcell.jl:248-349)
-    double dFv[NF][4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) dFv[0][c] = INTERIOR ? 0.0 : dF0[c];
-#pragma unroll
-    for (int s = 1; s < NF; ++s)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dFv[s][c] = (INTERIOR && s == 1) ? G[0][c] : dFv[s - 1][c] + G[s - 1][c];
-    // End faces.  f_bar_H - f_bar_L on an element face is BF_H - BF_L there, which with the identity projection is
-    // exactly zero unless the face carries an inflow/outflow condition (the seed dF0 above; at the far end the prefix
-    // sum returns to it up to rounding, ~1e-16 |flux|).  The exact zero is used: the face's P is then zero, its
-    // coefficient is 1 from both sides without evaluating limiting_param, and the interface symmetrisation
-    // (subcell.jl:418-456) is the identity (boundary faces are their own partners), so no second kernel is needed.
-    const bool bc0 = !INTERIOR && nb[0].bc != 0, bc1 = !INTERIOR && nb[1].bc != 0;
-    if (!bc1) {
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dFv[N1D][c] = 0.0;
-    }
-    // node by node: u^L = Uq + dt rhsL (subcell.jl:269), its bounds, and the two subcell faces
-    // next to it (P = -/+ 4 dt (fH - fL) / wJ, subcell.jl:300,312,328,340)
-    double lv[NF];
-#pragma unroll
-    for (int s = 0; s < NF; ++s) lv[s] = 1.0;
-    // First pass, branch-free and division-free: is EVERY coefficient of this line certainly 1?  With u' = u^L + P,
-    //   rho(u') >= zeta rho(u^L)                  <=>  rho' - zeta rho_L >= 0
-    //   rho e(u') >= zeta rho e(u^L)              <=>  rho' (2 rho_L E' - zeta c_L) - |m'|^2 rho_L >= 0,  c_L = 2 rho_L E_L - |m_L|^2
-    // (the second line is 2 rho_L q(1) of the reference's quadratic q(l) = a l^2 + b l + c, limiter_utils.jl:85-90).
-    // rho e is concave in the conserved variables, so q > 0 on all of [0, 1] when q(0) = c > 0 and q(1) > 0: no root in
-    // (0, 1], and limiting_param_bound_rho_rhoe returns min(., 1) = 1.  Both tests carry a margin of 1e-9 relative to the
-    // size of their terms (rounding moves either evaluation by ~1e-16), so a line that passes has all coefficients 1 in
-    // the reference's evaluation as well; everything else -- a sliver of |q(1)| < 1e-9 |terms| around the limiter's
-    // activation and the genuinely limited faces -- goes to the exact evaluation below.
-    bool all_easy = true;
-    constexpr bool SURE = P2DE_FAST_SURE_LIMITER != 0;
-    static_assert(P2DE_FAST_LIMITER_TWO_PASS, "the single-pass limiter was removed");
-    {
-#pragma unroll
-      for (int a = 0; a < N1D; ++a) {
-        const double *o = nodes + pos[a];
-        double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-        double2 o0 = partsL[((1 - d) * 2 + 0) * S + pos[a]], o1 = partsL[((1 - d) * 2 + 1) * S + pos[a]];
-        // the other direction's share is in ITS rotated frame: momentum components swap
-        double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
-        Cons2 uL;   // u^L = Uq + dt rhsL (subcell.jl:269)
-        uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
-        uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
-        const double kk = 4 * dtl * rwJ[a];     // P = -/+ 4 dt (fH - fL) / wJ, subcell.jl:300,312,328,340
-        if (SURE) {
-          const double r2L = 2.0 * uL.rho, eL = r2L * uL.E;
-          const double cL = fma(-uL.m2, uL.m2, fma(-uL.m1, uL.m1, eL));   // 2 rho rho e of u^L
-          const double zc = A.zeta * cL, tolq = (1e-9 * eL) * uL.rho, tolr = 1e-9 * uL.rho;
-          all_easy = all_easy & (cL > 1e-9 * eL) & (uL.rho > 0.0);
-#pragma unroll
-          for (int side = 0; side < 2; ++side) {
-            if (side == 0 ? (a > 0 || bc0) : (a < N1D - 1 || bc1)) {
-              const double ks = side ? kk : -kk;
-              const double *dFs = dFv[a + side];
-              const double rp = fma(ks, dFs[0], uL.rho), m1p = fma(ks, dFs[1], uL.m1), m2p = fma(ks, dFs[2], uL.m2), Ep = fma(ks, dFs[3], uL.E);
-              const double t1 = fma(r2L, Ep, -zc), msq = fma(m2p, m2p, m1p * m1p);
-              const double q1 = fma(-msq, uL.rho, rp * t1);
-              all_easy = all_easy & (fma(-A.zeta, uL.rho, rp) > tolr) & (q1 > tolq);
-            }
-          }
-        } else {
-          const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
-          const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
-          const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
-          double Pm[4], Pp[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) { Pm[c] = -kk * dFv[a][c]; Pp[c] = kk * dFv[a + 1][c]; }
-          if (a > 0 || bc0) {
-            double qa, qb;
-            quad_coeff_ab(uL, Pm, Lrhoe, qa, qb);
-            all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pm[0], Lrho, qa, qb, c0);
-          }
-          if (a < N1D - 1 || bc1) {
-            double qa, qb;
-            quad_coeff_ab(uL, Pp, Lrhoe, qa, qb);
-            all_easy = all_easy & limiting_param_pos_easy(uL.rho, Pp[0], Lrho, qa, qb, c0);
-          }
-        }
-        if (DIAG) {
-          if (d == 0 && A.rhsL_diag) {
-            const int node = a + line * N1D;
-            double r[4] = {r0, r1, r2, r3};
-            store4(A.rhsL_diag + (k * Nq + node) * 4, r);
-          }
-          if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
-            const int node = d == 0 ? a + line * N1D : line + a * N1D;
-            double *hd = A.rhsH_diag + (k * Nq + node) * 4;
-            atomicAdd(hd + 0, m0.x + G[a][0] * rwJ[a]); atomicAdd(hd + 1 + d, m0.y + G[a][1] * rwJ[a]);
-            atomicAdd(hd + 2 - d, m1.x + G[a][2] * rwJ[a]); atomicAdd(hd + 3, m1.y + G[a][3] * rwJ[a]);
-          }
-        }
-      }
-    }
-    if (A.dbg) { atomicAdd(A.dbg + DBG_LINES, 1ull); if (!all_easy) atomicAdd(A.dbg + DBG_LINES_NOT_EASY, 1ull); }
-    if (!all_easy) {
-      // exact evaluation (the reference's formulas: quadratic coefficients, root selection), node by node
-      bool one = true;
-#pragma unroll 1
-      for (int a = 0; a < N1D; ++a) {
-        const int pa = line_pos<N1D>(el, d, line, a);   // (= pos[a]; a is a run-time index in this rolled loop)
-        const double *o = nodes + pa;
-        double2 m0 = partsL[(d * 2 + 0) * S + pa], m1 = partsL[(d * 2 + 1) * S + pa];
-        double2 o0 = partsL[((1 - d) * 2 + 0) * S + pa], o1 = partsL[((1 - d) * 2 + 1) * S + pa];
-        double r0 = m0.x + o0.x, r1 = m0.y + o1.x, r2 = m1.x + o0.y, r3 = m1.y + o1.y;
-        Cons2 uL;
-        uL.rho = o[0 * S] + dtl * r0; uL.m1 = o[(1 + d) * S] + dtl * r1;
-        uL.m2 = o[(2 - d) * S] + dtl * r2; uL.E = o[3 * S] + dtl * r3;
-        // rhoe_ufun (:75-78) with a Newton reciprocal; c = E rho - |m|^2/2 - rho Lrhoe = (1 - zeta) rho rhoe
-        const double rhoeL = uL.E - 0.5 * (uL.m1 * uL.m1 + uL.m2 * uL.m2) * rcp_fast(uL.rho);
-        const double Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoeL;
-        const double c0 = (1.0 - A.zeta) * uL.rho * rhoeL;
-        const double kk = 4 * dtl * rwJ[a];
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-          if (side == 0 ? (a > 0 || bc0) : (a < N1D - 1 || bc1)) {
-            double Pv[4];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) Pv[c] = (side ? kk : -kk) * dFv_at(dFv, a + side, c);
-            double qa, qb;
-            quad_coeff_ab(uL, Pv, Lrhoe, qa, qb);
-            // (lv <= 1 throughout, so the common result 1.0 of limiting_param_pos needs no min)
-            if (!limiting_param_pos_easy(uL.rho, Pv[0], Lrho, qa, qb, c0)) {
-              if (A.dbg) atomicAdd(A.dbg + DBG_LIMITER_SLOW, 1ull);
-              const double lnew = limiting_param_pos_slow(A.ZEROTOL, uL.rho, Pv[0], Lrho, qa, qb, c0);
-              lv_set_min(lv, a + side, lnew);
-              one = one & (lnew >= 1.0);
-            }
-          }
-        }
-      }
-      all_easy = one;   // a line the margin sent here may still have all coefficients 1
-    }   // !all_easy
-    // (update_blending_factor! = 1 without shock capturing, shock_capture.jl:111-114: the FAST path has none, so the
-    //  min with A.blend is the identity)
-    // this line's share of the un-symmetrised limited rhs (subcell.jl:841-924 with the line's own
-    // coefficients): t_d = rhsxyL_d + (l_{a+1} dF_{a+1} - l_a dF_a) / wJ, in the line's rotated frame
-    if (all_easy) {
-      // every coefficient of the line is 1: l_{a+1} dF_{a+1} - l_a dF_a is the prefix sum's own increment G[a],
-      // i.e. the share is rhsxyH_d
-#pragma unroll
-      for (int a = 0; a < N1D; ++a) {
-        double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-        tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + G[a][0] * rwJ[a], m0.y + G[a][1] * rwJ[a]);
-        tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + G[a][2] * rwJ[a], m1.y + G[a][3] * rwJ[a]);
-      }
-    } else {
-#pragma unroll
-    for (int a = 0; a < N1D; ++a) {
-      double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-      // (INTERIOR: dF is exactly zero on the two end faces, the products are dropped at compile time)
-      double hi[4], lo[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        hi[c] = (INTERIOR && a == N1D - 1) ? 0.0 : lv[a + 1] * dFv[a + 1][c];
-        lo[c] = (INTERIOR && a == 0) ? 0.0 : lv[a] * dFv[a][c];
-      }
-      tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(m0.x + (hi[0] - lo[0]) * rwJ[a], m0.y + (hi[1] - lo[1]) * rwJ[a]);
-      tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(m1.x + (hi[2] - lo[2]) * rwJ[a], m1.y + (hi[3] - lo[3]) * rwJ[a]);
-    }
-    }   // !all_easy
-#pragma unroll
-    for (int s = 0; s < NF; ++s) lstage[el * (2 * N1D * NF) + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];
-    }   // active
-    // ---- flat, coalesced output phase: rpre = x share + y share (y share un-rotated), lpre
-    constexpr int NIT = (S + NT - 1) / NT;
-    constexpr int NL = 2 * N1D * NF;
-    double2 wres[NIT][2];
-    {
-      const double *rw = A.fuse_resW + kb * (Nq * 4);
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {   // resW of this thread's nodes: in flight across the barrier
-        const int n = tid + it * NT;
-        wres[it][0] = make_double2(0.0, 0.0); wres[it][1] = make_double2(0.0, 0.0);
-        if (fuse && n < S && (full || kb + n / Nq < M.K)) {
-          const double2 *q = reinterpret_cast<const double2 *>(rw + n * 4);
-          wres[it][0] = q[0]; wres[it][1] = q[1];
-        }
-      }
-    }
-    __syncthreads();
-    double *out = A.rpre + kb * (Nq * 4);
-    if (NIT > 2) {   // N1D = 5: node by node (three nodes' worth of staging registers spills)
-#pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        const int n = tid + it * NT;
-        const int e2 = n / Nq, node = n % Nq;
-        if (n < S && (full || kb + e2 < M.K)) {
-          const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
-          double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
-          double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
-          if (fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
-            r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
-            r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
-            r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (nodes[2 * S + p2] + dtl * r[2]);
-            r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (nodes[3 * S + p2] + dtl * r[3]);
-          }
-          store4(out + n * 4, r);
-        }
-      }
-    } else {
-    // all shared-memory loads of this thread's NIT nodes first, then the arithmetic and the stores (the loads of
-    // one node used to wait behind the stores of the previous one)
-    int p2v[NIT];
-    bool okv[NIT];
-    double2 xv[NIT][4];
-    double uo[NIT][4];
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int n = tid + it * NT;
-      const int e2 = n / Nq, node = n % Nq;
-      okv[it] = n < S && (full || kb + e2 < M.K);
-      // swizzled position: arithmetic for N1D = 4 (no dependent table look-up), table otherwise
-      p2v[it] = n < S ? node_pos<N1D>(e2, node % N1D, node / N1D) : 0;
-    }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it)
-      if (okv[it]) {
-        const int p2 = p2v[it];
-        xv[it][0] = tbuf[0 * S + p2]; xv[it][1] = tbuf[1 * S + p2]; xv[it][2] = tbuf[2 * S + p2]; xv[it][3] = tbuf[3 * S + p2];
-        if (fuse) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) uo[it][c] = nodes[c * S + p2];
-        }
-      }
-#pragma unroll
-    for (int it = 0; it < NIT; ++it) {
-      const int n = tid + it * NT;
-      if (okv[it]) {
-        const double2 x0 = xv[it][0], x1 = xv[it][1], y0 = xv[it][2], y1 = xv[it][3];
-        double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
-        if (fuse) {   // stages 2, 3: dt is known, so the SSP combine (SSPRK33.jl:34-39) of the un-corrected rhs is done here
-          r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (uo[it][0] + dtl * r[0]);
-          r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (uo[it][1] + dtl * r[1]);
-          r[2] = A.fuse_a * wres[it][1].x + A.fuse_b * (uo[it][2] + dtl * r[2]);
-          r[3] = A.fuse_a * wres[it][1].y + A.fuse_b * (uo[it][3] + dtl * r[3]);
-        }
-        store4(out + n * 4, r);
-      }
-    }
-    }   // NIT <= 2
-    double *lout = A.lpre + kb * NL;
-    if (full && (EPB * NL) % 2 == 0) {   // 16-byte copies
-      const double2 *ls2 = reinterpret_cast<const double2 *>(lstage);
-      double2 *lo2 = reinterpret_cast<double2 *>(lout);
-      for (int n = tid; n < EPB * NL / 2; n += NT) lo2[n] = ls2[n];
-    } else {
-      for (int n = tid; n < EPB * NL; n += NT)
-        if (kb + n / NL < M.K) lout[n] = lstage[n];
-    }
-    return;
-  }
+  if (!active && MODE != MODE_ZHANGSHU) return;
 
   // ---- element-local limiters / no limiter: x-line threads produce rhsU
   double rL[N1D][4], rH[N1D][4];
@@ -881,41 +574,8 @@ stage_kernel_fast(const __grid_constant__ StageArgs A, const __grid_constant__ M
                   const __grid_constant__ Tables2D<N1D> Tc) {
   bool interior;
   const long long kb = fast_batch<EPB>(A, M, interior);
-  if (interior) stage_fast_impl<N1D, MODE, EPB, true, false>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE, EPB, false, false>(A, M, Tc, kb);
-}
-
-// The three kernels of the direct schedule (p2de_ssp33_step, subcell limiter): the stage's role is a compile-time fact
-// (KIND), so the CFL block, the fused combine and the diagnostics are present or absent without run-time flags.  Each is
-// its own __global__ function: as further copies of the body inside one kernel they made ptxas' register allocation for
-// the other copies worse (measured, 3 %).
-template <int N1D, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
-stage_kernel_fast_s1(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
-                     const __grid_constant__ Tables2D<N1D> Tc) {
-  bool interior;
-  const long long kb = fast_batch<EPB>(A, M, interior);
-  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, false, KIND_S1>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, false, KIND_S1>(A, M, Tc, kb);
-}
-template <int N1D, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
-stage_kernel_fast_s3(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
-                     const __grid_constant__ Tables2D<N1D> Tc) {
-  bool interior;
-  const long long kb = fast_batch<EPB>(A, M, interior);
-  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, false, KIND_S23>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, false, KIND_S23>(A, M, Tc, kb);
-}
-// stage 2 of the direct schedule: the stage input is Uq + dt * defer_add (the stage-1 combine formed while loading)
-template <int N1D, int EPB>
-__global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_FAST_MIN_BLOCKS5 : P2DE_FAST_MIN_BLOCKS))
-stage_kernel_fast_defer(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M,
-                        const __grid_constant__ Tables2D<N1D> Tc) {
-  bool interior;
-  const long long kb = fast_batch<EPB>(A, M, interior);
-  if (interior) stage_fast_impl<N1D, MODE_SUBCELL, EPB, true, true, P2DE_FAST_KINDS ? KIND_S23 : KIND_RT>(A, M, Tc, kb);
-  else stage_fast_impl<N1D, MODE_SUBCELL, EPB, false, true, P2DE_FAST_KINDS ? KIND_S23 : KIND_RT>(A, M, Tc, kb);
+  if (interior) stage_fast_impl<N1D, MODE, EPB, true>(A, M, Tc, kb);
+  else stage_fast_impl<N1D, MODE, EPB, false>(A, M, Tc, kb);
 }
 
 // update kernel for the FAST stage kernel's scratch (rpre, dFend, lpre): interface symmetrisation

@@ -23,8 +23,29 @@
 
 namespace p2de {
 
+// How much of the stage's role is a compile-time fact:
+//   KIND_RT   run-time flags of StageArgs (p2de_rhs: any stage index, optional diagnostics, optional fused combine);
+//             exchanges plain low-order shares and writes rhsU (or the fused combine)
+//   KIND_S1   stage 1 of p2de_ssp33_step: CFL reduction; the limiter's dt is the cap (rhs.jl:46,52), the step's dt does not
+//             exist before the whole grid has finished, so the kernel writes W = U + cap rhsU and whoever forms
+//             U1 = U + dt rhsU (SSPRK33.jl:31-33) takes the convex combination U + (dt / cap) (W - U)
+//   KIND_S23  stages 2 and 3: the SSP combine a resW + b (U + dt rhsU) is fused, no CFL reduction
+enum { KIND_RT = 0, KIND_S1 = 1, KIND_S23 = 2 };
+
+// U + theta (W - U) at one node: the stage-1 combine from stage 1's W = U + cap rhsU, theta = dt / cap in (0, 1]
+P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pw, double theta) {
+  Cons2 U = load_cons(pu);
+  const Cons2 W = load_cons(pw);
+  U.rho = fma(theta, W.rho - U.rho, U.rho); U.m1 = fma(theta, W.m1 - U.m1, U.m1);
+  U.m2 = fma(theta, W.m2 - U.m2, U.m2); U.E = fma(theta, W.E - U.E, U.E);
+  return U;
+}
+
 #ifndef P2DE_SUB_MIN_BLOCKS
 #define P2DE_SUB_MIN_BLOCKS 4
+#endif
+#ifndef P2DE_SUB_MIN_BLOCKS_S23
+#define P2DE_SUB_MIN_BLOCKS_S23 P2DE_SUB_MIN_BLOCKS   // stages 2, 3 (their shared memory allows a fifth CTA per SM)
 #endif
 #ifndef P2DE_SUB_MIN_BLOCKS5
 #define P2DE_SUB_MIN_BLOCKS5 3
@@ -32,10 +53,13 @@ namespace p2de {
 
 // doubles of shared memory per element besides the table prefix: U [4][Nq], the low-order shares [2][2][Nq] double2,
 // the limited shares [2][2][Nq] double2, the CFL lambda sums [2][Nq] / L_local staging [2 N1D (N1D+1)]
+// The kernels of the direct schedule (A-form exchange) do not need U after the line phase: their L_local staging lives in
+// the dead U block, and stage 1's lambda sums in the not yet written limited-share block
 template <int N1D>
-__host__ __device__ constexpr int subcell_smem_doubles_per_elem() {
-  return N1D * N1D * (4 + 8 + 8) + fast_lamp_per_elem<N1D>();
+__host__ __device__ constexpr int subcell_smem_doubles_per_elem(bool aform) {
+  return N1D * N1D * (4 + 8 + 8) + (aform ? 0 : fast_lamp_per_elem<N1D>());
 }
+static_assert(2 * 4 * 5 <= 4 * 16 && 2 * 5 * 6 <= 4 * 25 && 2 * 3 * 4 <= 4 * 9 && 2 * 2 * 3 <= 4 * 4, "L_local staging fits the U block");
 
 // log for the line threads of a non-quiet warp (operands are positive normals: rho, beta)
 P2DE_DEV double log_pos(double x) { return log(x); }
@@ -46,8 +70,8 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
   constexpr int TBL = fast_table_doubles<N1D>();
   constexpr int S = EPB * Nq;
   constexpr int NL = 2 * N1D * NF;
-  // A-form exchange (see the header): the stage's dt is the limiter's dt and the combine is fused
-  constexpr bool AFORM = KIND == KIND_S23;
+  // A-form exchange (see the header): the limiter's dt multiplies everything the kernel writes
+  constexpr bool AFORM = KIND == KIND_S23 || KIND == KIND_S1;
   constexpr bool DIAG = KIND == KIND_RT;
   // quiet vote: an element's N1D line threads of one direction are adjacent lanes of one warp
   constexpr bool QUIET_PATH = N1D == 4 && HALF % 32 == 0;
@@ -56,8 +80,10 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
   double *nodes = sm + TBL;                                            // [4][S] rho, m1, m2, E at swizzled positions
   double2 *partsL = reinterpret_cast<double2 *>(nodes + 4 * S);        // [d][half][S] low-order shares (or A_d)
   double2 *tbuf = partsL + 4 * S;                                      // [d][half][S] limited shares
-  double *lamp = reinterpret_cast<double *>(tbuf + 4 * S);             // [2][S] CFL sums, later [EPB][NL] L_local staging
-  double *lstage = lamp;
+  // [2][S] CFL sums and [EPB][NL] L_local staging.  AFORM: the sums sit in the limited-share block (written only after the
+  // CFL block's barrier) and the staging in the U block (dead after the line phase)
+  double *lamp = AFORM ? reinterpret_cast<double *>(tbuf) : reinterpret_cast<double *>(tbuf + 4 * S);
+  double *lstage = AFORM ? nodes : lamp;
 
   const int tid = threadIdx.x;
   const int d = tid / HALF, rr = tid % HALF, el = rr / N1D, line = rr % N1D;
@@ -73,7 +99,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     if (DEFER) atomicAdd(A.dbg + DBG_CTA_DEFER, 1ull);
   }
   if (P2DE_FAST_PREFETCH) {   // the batch one wave of resident CTAs ahead, into L2 (stage_fast.cuh)
-    constexpr int AHEAD = 148 * (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : P2DE_SUB_MIN_BLOCKS);
+    constexpr int AHEAD = 148 * (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : P2DE_SUB_MIN_BLOCKS * (16 / (EPB < 16 ? EPB : 16)));
     const long long kp = kb + (long long)AHEAD * EPB;
     constexpr int LINES = EPB * Nq * 32 / 128;
     if (kp + EPB <= M.K) {
@@ -92,7 +118,11 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     const int i = tid + it * NT;
     if (i < TF2) treg[it] = reinterpret_cast<const double2 *>(A.tab_dev)[i];
   }
-  const double dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;   // dt the limiter sees (rhs.jl:46,52)
+  // dt the limiter sees (rhs.jl:46,52).  Only the deferred combine needs it while loading; otherwise its (uniform) load is
+  // issued after the first barrier, where its latency hides behind the line phase instead of stalling the CTA's start
+  double dtl = A.dt_host;
+  if (DEFER) dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
+  const double theta = DEFER ? dtl * A.inv_cap : 1.0;   // stage 1 wrote W = U + cap rhsU with cap = dt_host (the same in all stages)
   // ---- the two neighbour face nodes of this line (one 32-byte node each)
   Nbr nb[2];
   Cons2 UnbC[2];
@@ -108,7 +138,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       nb_in_batch[e] = d == 0 && (e ? el + 1 < EPB : el > 0);   // read from shared memory after the barrier
       if (!nb_in_batch[e]) {
         const long long off = ((long long)(el + dk) * Nq + node) * 4;
-        UnbC[e] = DEFER ? load_cons_plus(Ubase + off, A.defer_add + kb * (Nq * 4) + off, dtl) : load_cons(Ubase + off);
+        UnbC[e] = DEFER ? load_cons_plus(Ubase + off, A.defer_add + kb * (Nq * 4) + off, theta) : load_cons(Ubase + off);
       }
     }
   } else if (active) {
@@ -119,7 +149,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     for (int e = 0; e < 2; ++e) {
       nb[e] = neighbor<N1D>(M, k, ix, iy, (2 * d + e) * N1D + line);
       const long long noff = (nb[e].kP * Nq + Tc.fq2q[nb[e].fP]) * 4;
-      UnbC[e] = DEFER ? load_cons_plus(A.Uq + noff, A.defer_add + noff, dtl) : load_cons(A.Uq + noff);
+      UnbC[e] = DEFER ? load_cons_plus(A.Uq + noff, A.defer_add + noff, theta) : load_cons(A.Uq + noff);
     }
   }
   // ---- the batch's states: flat coalesced loads, stored at their swizzled positions
@@ -130,7 +160,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     const int n = tid + it * NT;
     Uraw[it].rho = 1.0; Uraw[it].m1 = 0.0; Uraw[it].m2 = 0.0; Uraw[it].E = 1.0;   // partial batch: harmless dummy state
     if (n < S && (full || kb + n / Nq < M.K)) {
-      Uraw[it] = DEFER ? load_cons_plus(Ubase + n * 4, A.defer_add + kb * (Nq * 4) + n * 4, dtl) : load_cons(Ubase + n * 4);
+      Uraw[it] = DEFER ? load_cons_plus(Ubase + n * 4, A.defer_add + kb * (Nq * 4) + n * 4, theta) : load_cons(Ubase + n * 4);
       if (fuse && !DEFER)   // the flat output phase of this same thread reads resW here: pull it into L2 now
         asm volatile("prefetch.global.L2 [%0];" ::"l"(A.fuse_resW + kb * (Nq * 4) + n * 4));
     }
@@ -150,6 +180,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     }
   }
   __syncthreads();
+  if (!DEFER) dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
 
   // ---- line phase (all threads; threads of a partial batch's missing elements work on the dummy state and store nothing)
   int pos[N1D];
@@ -188,7 +219,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     // surface flux at line end e against the neighbour state (low_order_graph_viscosity.jl:168-204,
     // flux_differencing.jl:90-151,223-272): returns -BF_L's contribution to the low-order sum in Fc
     auto face = [&](int e, const ConsR &U, const double fl[4], double ws, double Fc[4], double &lamB_out, double Gadj[4]) {
-      const double B = T.Bf[d][line][e], nn = fabs(B);
+      const double B = T.Bf[d][line][e], nn = fabs(B), hB = 0.5 * B;
       double rinvP = rcp_fast(Unb[e].rho);
       const double wsP = wavespeed_rot(gamma, gm1, rinvP, Unb[e].mn, Unb[e].E);
       const double lamB = 0.5 * nn * fmax(ws, wsP);
@@ -204,9 +235,8 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       const double up[4] = {uP.rho, uP.mn, uP.mt, uP.E}, uf[4] = {U.rho, U.mn, U.mt, U.E};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const double bfs = B * (0.5 * (fl[c] + fP[c]));
         const double lf = lamB * (up[c] - uf[c]);
-        Fc[c] = lf - bfs;                              // - BF_L
+        Fc[c] = fma(-hB, fl[c] + fP[c], lf);           // - BF_L = -(B (f + f_P) / 2 - lf)
         Gadj[c] = bce ? lf : 0.0;                      // BF_H - BF_L: zero unless the face carries a boundary condition
       }
       lamB_out = lamB;
@@ -286,7 +316,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       fS_rot_quiet(A.half_inv_gm1, q[i], q[j], F);
       const double Sv = T.SHt[d][i][j][line];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { const double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+      for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }
     });
   } else {
 #pragma unroll
@@ -297,7 +327,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       fS_rot(A.half_inv_gm1, q[i], q[j], F);
       const double Sv = T.SHt[d][i][j][line];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { const double Sf = Sv * F[c]; G[i][c] -= Sf; G[j][c] += Sf; }
+      for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }
     });
   }
   __syncthreads();
@@ -476,9 +506,14 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       const int p2 = node_pos<N1D>(e2, node % N1D, node / N1D);
       const double2 x0 = tbuf[0 * S + p2], x1 = tbuf[1 * S + p2], y0 = tbuf[2 * S + p2], y1 = tbuf[3 * S + p2];
       double r[4] = {x0.x + y0.x, x0.y + y1.x, x1.x + y0.y, x1.y + y1.y};
-      if (AFORM) {          // t_x + t_y = U + dt rhsU: the SSP combine (SSPRK33.jl:34-39) is one FMA per component
+      if (KIND == KIND_S1) {
+        // t_x + t_y = W = U + cap rhsU is what stage 1 leaves behind (see KIND_S1)
+      } else if (AFORM) {   // t_x + t_y = U + dt rhsU: the SSP combine (SSPRK33.jl:34-39) is one FMA per component
         r[0] = fma(A.fuse_a, wres[it][0].x, A.fuse_b * r[0]); r[1] = fma(A.fuse_a, wres[it][0].y, A.fuse_b * r[1]);
         r[2] = fma(A.fuse_a, wres[it][1].x, A.fuse_b * r[2]); r[3] = fma(A.fuse_a, wres[it][1].y, A.fuse_b * r[3]);
+      } else if (KIND == KIND_RT && A.wform) {   // stage 1 in W form with diagnostics on: W = U + cap rhsU, cap = dtl
+        r[0] = fma(dtl, r[0], nodes[0 * S + p2]); r[1] = fma(dtl, r[1], nodes[1 * S + p2]);
+        r[2] = fma(dtl, r[2], nodes[2 * S + p2]); r[3] = fma(dtl, r[3], nodes[3 * S + p2]);
       } else if (fuse) {    // run-time version (p2de_rhs-side schedules): the combine of the un-corrected rhs
         r[0] = A.fuse_a * wres[it][0].x + A.fuse_b * (nodes[0 * S + p2] + dtl * r[0]);
         r[1] = A.fuse_a * wres[it][0].y + A.fuse_b * (nodes[1 * S + p2] + dtl * r[1]);
@@ -489,10 +524,15 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     }
   }
   double *lout = A.lpre + kb * NL;
-  if (full && (EPB * NL) % 2 == 0) {   // 16-byte copies
+  if (full && (EPB * NL) % 2 == 0) {   // 16-byte copies, all loads first
     const double2 *ls2 = reinterpret_cast<const double2 *>(lstage);
     double2 *lo2 = reinterpret_cast<double2 *>(lout);
-    for (int n = tid; n < EPB * NL / 2; n += NT) lo2[n] = ls2[n];
+    constexpr int NC = EPB * NL / 2, NITL = (NC + NT - 1) / NT;
+    double2 lreg[NITL];
+#pragma unroll
+    for (int it = 0; it < NITL; ++it) if (tid + it * NT < NC) lreg[it] = ls2[tid + it * NT];
+#pragma unroll
+    for (int it = 0; it < NITL; ++it) if (tid + it * NT < NC) lo2[tid + it * NT] = lreg[it];
   } else {
     for (int n = tid; n < EPB * NL; n += NT)
       if (kb + n / NL < M.K) lout[n] = lstage[n];
@@ -501,7 +541,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
 
 #define P2DE_SUBCELL_KERNEL(NAME, DEFER_, KIND_)                                                                        \
   template <int N1D, int EPB>                                                                                           \
-  __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : P2DE_SUB_MIN_BLOCKS))             \
+  __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : (KIND_ != KIND_RT ? P2DE_SUB_MIN_BLOCKS_S23 : P2DE_SUB_MIN_BLOCKS) * (16 / (EPB < 16 ? EPB : 16)))) \
   NAME(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M, const __grid_constant__ Tables2D<N1D> Tc) { \
     bool interior;                                                                                                      \
     const long long kb = fast_batch<EPB>(A, M, interior);                                                               \
@@ -511,7 +551,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
 // Four kernels (each its own __global__ function: further copies of the body inside one kernel made ptxas' register
 // allocation for the other copies worse, measured 3 %):
 P2DE_SUBCELL_KERNEL(stage_subcell_rt, false, KIND_RT)        // p2de_rhs and the testing schedules: run-time flags, diagnostics
-P2DE_SUBCELL_KERNEL(stage_subcell_s1, false, KIND_S1)        // stage 1 of the direct schedule: CFL reduction, writes rhsU
+P2DE_SUBCELL_KERNEL(stage_subcell_s1, false, KIND_S1)        // stage 1: CFL reduction, writes W = U + cap rhsU
 P2DE_SUBCELL_KERNEL(stage_subcell_s2, true, KIND_S23)        // stage 2: forms U1 = U^n + dt rhsU while loading, writes U2
 P2DE_SUBCELL_KERNEL(stage_subcell_s3, false, KIND_S23)       // stage 3: writes U^{n+1}
 #undef P2DE_SUBCELL_KERNEL

@@ -24,8 +24,8 @@ CASES = {
     "kh-N4-60x6": lambda: P.kelvin_helmholtz(N=4, K=(60, 6)),  # 12 elements per CTA
     "kh-N4-66x5": lambda: P.kelvin_helmholtz(N=4, K=(66, 5)),
     "wave-N3-64x5": lambda: P.wave2d(N=3, K=(64, 5)),
-    "vortex-N1-64x4": lambda: P.vortex(N=1, K=(64, 4)),
-    "vortex-N2-64x4": lambda: P.vortex(N=2, K=(64, 4)),
+    "vortex-N1-64x4": lambda: P.vortex(N=1, K=(64, 4), T=10.0),   # (T far away: the smoke test's T = 2e-2 is reached after two steps)
+    "vortex-N2-64x4": lambda: P.vortex(N=2, K=(64, 4), T=10.0),
     "sedov-N3-64x6": lambda: P.sedov(N=3, K=(64, 6)),
 }
 DT = {"dmr": 5e-4, "sedov": 2e-2}

@@ -412,6 +412,14 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
           all_easy = all_easy & (fma(-A.zeta, uL.rho, rp) > tolr) & (q1 > tolq);
         }
       }
+      // this line's limited share, written here on the assumption that every coefficient of the line is 1 (then the
+      // increment l_{a+1} dF_{a+1} - l_a dF_a is the prefix sum's own G[a]); each direction adds half of the common part
+      // r (AFORM: u^L, otherwise rhsL), so t_x + t_y = r + (increment_x + increment_y) w.  Rewritten below otherwise.
+      {
+        const double w = AFORM ? dtl * rwJ[a] : rwJ[a];
+        tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(fma(G[a][0], w, 0.5 * r[0]), fma(G[a][1], w, 0.5 * r[1]));
+        tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(fma(G[a][2], w, 0.5 * r[2]), fma(G[a][3], w, 0.5 * r[3]));
+      }
       if (DIAG) {
         if (d == 0 && A.rhsL_diag) store4(A.rhsL_diag + (k * Nq + a + line * N1D) * 4, r);
         if (A.rhsH_diag) {   // diagnostics: rhsxyH_d = rhsxyL_d + G / wJ; each line adds its share (buffer pre-zeroed)
@@ -457,16 +465,15 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       all_easy = one;   // a line the margin sent here may still have all coefficients 1
     }
     // this line's share of the un-symmetrised limited rhs (subcell.jl:841-924 with the line's own coefficients), in the
-    // line's rotated frame:  t_d = rhsxyL_d + (l_{a+1} dF_{a+1} - l_a dF_a) / wJ      (AFORM: A_d + dt (...) / wJ)
+    // line's rotated frame:  t_d = r / 2 + (l_{a+1} dF_{a+1} - l_a dF_a) w,  w = 1 / wJ (AFORM: dt / wJ).  Only lines with a
+    // coefficient below 1 get here; all others wrote their share in the first pass.
+    if (!all_easy) {
 #pragma unroll
-    for (int a = 0; a < N1D; ++a) {
-      const double2 m0 = partsL[(d * 2 + 0) * S + pos[a]], m1 = partsL[(d * 2 + 1) * S + pos[a]];
-      const double w = AFORM ? dtl * rwJ[a] : rwJ[a];
-      double inc[4];
-      if (all_easy) {   // every coefficient is 1: the increment is the prefix sum's own G[a], i.e. the share is rhsxyH_d
-#pragma unroll
-        for (int c = 0; c < 4; ++c) inc[c] = G[a][c];
-      } else {
+      for (int a = 0; a < N1D; ++a) {
+        double r[4];
+        low_state(pos[a], r);
+        const double w = AFORM ? dtl * rwJ[a] : rwJ[a];
+        double inc[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           // (INTERIOR: dF is exactly zero on the two end faces, the products are dropped at compile time)
@@ -474,9 +481,9 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
           const double lo = (INTERIOR && a == 0) ? 0.0 : lv[a] * dFv[a][c];
           inc[c] = hi - lo;
         }
+        tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(fma(inc[0], w, 0.5 * r[0]), fma(inc[1], w, 0.5 * r[1]));
+        tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(fma(inc[2], w, 0.5 * r[2]), fma(inc[3], w, 0.5 * r[3]));
       }
-      tbuf[(d * 2 + 0) * S + pos[a]] = make_double2(fma(inc[0], w, m0.x), fma(inc[1], w, m0.y));
-      tbuf[(d * 2 + 1) * S + pos[a]] = make_double2(fma(inc[2], w, m1.x), fma(inc[3], w, m1.y));
     }
 #pragma unroll
     for (int s = 0; s < NF; ++s) lstage[el * NL + d * (N1D * NF) + (d == 0 ? s + line * NF : line + s * N1D)] = lv[s];

@@ -29,6 +29,9 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 import numpy as np  # noqa: E402
 
+# host cores available to this process, taken before any OpenMP runtime binds the main thread (OMP_PROC_BIND below)
+NCORES = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
 METRIC = "DOF-updates/sec (FP64, per RK stage)"
 UNIT = "DOF-updates/s"
 
@@ -38,6 +41,12 @@ WORKLOADS = {
     "S-DMR-small": dict(problem="dmr", N=3, K=(512, 128), note="S-DMR at 512x128"),
     "S-DMR-mid": dict(problem="dmr", N=3, K=(1024, 512), note="S-DMR at 1024x512 (profiling size)"),
     "S-KH": dict(problem="kelvin_helmholtz", N=4, K=(4096, 512), note="Kelvin-Helmholtz, N=4 LGL, 4096x512 per GPU, periodic"),
+    # data-independence checks of the headline (same mesh and scheme as S-DMR, different data):
+    "S-WAVE": dict(problem="wave2d", N=3, K=(4096, 1024), note="plateau-free smooth periodic data (tests/problems.py: wave2d), N=3 LGL, 4096x1024: "
+                   "no constant elements, most node pairs off logmean's series branch (logs evaluated everywhere)"),
+    "S-DMR-developed": dict(problem="dmr", N=3, K=(4096, 1024), developed=dict(K=(512, 128), steps=8000, tile=(8, 8)),
+                            note="S-DMR mesh and boundary conditions; initial state = the double-Mach-reflection data advanced 8000 SSP-RK3 steps "
+                                 "on a 512x128 mesh and tiled 8x8 (developed shocks and reflections, tile seams add further discontinuities)"),
     # the configuration of examples/2D/kelvin-helmholtz.jl:44-55: Gauss collocation,
     # NodewiseScaledExtrapolation, LaxFriedrichsOnProjectedVal, subcell positivity limiter
     "S-KH-gauss": dict(problem="kelvin_helmholtz", N=3, K=(2048, 512), gauss=True,
@@ -139,6 +148,41 @@ def initial_state(param, rd, ic, out):
         out[s:s + len(k)] = np.stack([np.broadcast_to(c, xq.shape) for c in ic(param, xq, yq)], axis=-1)
 
 
+def source_hash():
+    """sha256 over the kernel sources: profiles/*_traffic.json is only quoted for the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "p2de_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        with open(os.path.join(d, f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def developed_state(workload, host_np, device):
+    """Initial state of S-DMR-developed: a small double-Mach-reflection run on the GPU (through the same library), tiled."""
+    import problems as P
+    from p2de_b200.api import State
+    from p2de_b200.types import Solver
+    dv = WORKLOADS[workload]["developed"]
+    w = WORKLOADS[workload]
+    param, rd, md, dd, bc, U0 = P.setup(getattr(P, w["problem"])(N=w["N"], K=dv["K"], T=1e9))
+    st = State(Solver(param=param, rd=rd, md=md, discrete_data=dd), bc, device=device)
+    st.set_state(U0)
+    t = 0.0
+    for _ in range(dv["steps"]):
+        t += st.ssp33_step(t)
+    U = st.preallocation.Uq
+    st.close()
+    kx, ky = dv["K"]; tx, ty = dv["tile"]
+    Us = U.reshape(ky, kx, U.shape[1], U.shape[2])
+    Kx = kx * tx
+    for jy in range(ty):                       # fill row-block by row-block (no 2 GB temporary)
+        rowblock = np.tile(Us, (1, tx, 1, 1)).reshape(ky * Kx, U.shape[1], U.shape[2])
+        host_np[jy * ky * Kx:(jy + 1) * ky * Kx] = rowblock
+    return {"small_mesh": list(dv["K"]), "steps": dv["steps"], "t_end": t, "tile": list(dv["tile"])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -152,16 +196,53 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    w = WORKLOADS[args.workload]
+    out = measure(args, args.workload, world, rank, local, headline=True)
+    if out is not None and rank == 0:
+        if world == 1 and not args.no_extra and not args.no_e2e and args.workload == "S-DMR":
+            # the headline data is the reference's prescribed initial condition, which is mostly plateau: the same mesh
+            # and scheme on plateau-free and on developed-shock data, with the data-dependent shortcuts counted
+            out["extra"] = {}
+            for wl in ("S-WAVE", "S-DMR-developed"):
+                try:
+                    ex = measure(args, wl, world, rank, local, headline=False)
+                    out["extra"][wl] = ex
+                except Exception as e:      # an extra line must never cost the headline
+                    out["extra"][wl] = {"error": repr(e)}
+            vals = [v["value"] for v in out["extra"].values() if "value" in v] + [out["value"]]
+            out["extra"]["worst_case_value"] = min(vals)
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(args.workload, steps=6, warmup=1)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def multi_gpu_check(world, rank, local):
+    """Outside the timed region: y-stripes over `world` ranks against the whole mesh on rank 0's GPU (tests/multigpu_check.py)."""
+    import multigpu_check as mc
+    res = mc.run_cases(rank, world, local, quick=True)
+    if res is None:
+        return None
+    return {"world": world, "bitwise_equal": all(r["bitwise_equal"] for r in res), "ok": all(r["ok"] for r in res), "cases": res}
+
+
+def measure(args, workload, world, rank, local, headline):
+    import torch
+    import torch.distributed as dist
+    from p2de_b200 import initialize_data
+    from p2de_b200.api import State
+    from p2de_b200.types import Solver
+    w = WORKLOADS[workload]
     K = w["K"]
     # weak scaling: every rank owns a K[0] x K[1] stripe of element rows of a K[0] x (K[1]*world)
     # mesh on a domain stretched in y accordingly (y-stripes, SURVEY.md 8e)
     import dataclasses
     from p2de_b200.partition import local_bcdata, local_param
-    gparam, ic, _ = build_problem(args.workload, K)
+    gparam, ic, _ = build_problem(workload, K)
     Ly = gparam.xR[1] - gparam.xL[1]
     gparam = dataclasses.replace(gparam, K=(K[0], K[1] * world), xR=(gparam.xR[0], gparam.xL[1] + Ly * world))
-    gbc, periodic = boundary_data_light(gparam, args.workload)
+    gbc, periodic = boundary_data_light(gparam, workload)
     param = local_param(gparam, rank, world)
     bc = local_bcdata(gparam, gbc, rank, world)
     rd, md, dd = initialize_data(param, light=True)
@@ -177,7 +258,11 @@ def run_ours(args):
         st.comm_init(rank, world, bytes(uid.cpu().tolist()))
     sz = dd.sizes
     host = torch.empty((sz.K, sz.Nq, sz.Nc), dtype=torch.float64, pin_memory=True)
-    initial_state(param, rd, ic, host.numpy())
+    dev_info = None
+    if w.get("developed"):
+        dev_info = developed_state(workload, host.numpy(), local)
+    else:
+        initial_state(param, rd, ic, host.numpy())
     st.set_state_async_ptr(host.data_ptr())
     st.synchronize()
     t0 = param.timestepping_param.t0
@@ -220,6 +305,27 @@ def run_ours(args):
         ms = float(tm.item())
     dof_per_stage = sz.K * sz.Nq * world
     value = 3.0 * dof_per_stage * args.steps / (ms * 1e-3)
+    # data-dependent shortcuts taken, counted by the kernels themselves during one more (untimed) step
+    counters = None
+    if param.rhs_limiter.code == 2 and not w.get("gauss"):
+        st.debug_counters(True)
+        st.ssp33_step(t)
+        c = st.debug_counters(False)
+        if c["elem"] and c["lines"]:
+            counters = {"elements_with_logs_frac": c["elem_logs"] / c["elem"], "lines_not_all_easy_frac": c["lines_not_easy"] / c["lines"],
+                        "limiter_slow_calls_per_element": c["limiter_slow"] / c["elem"],
+                        "interior_cta_frac": c["cta_interior"] / max(c["cta_interior"] + c["cta_general"], 1), "raw": c}
+    peak, peak_src = peaks()
+    A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
+    stage_total_ms = (stage_ms + upd_ms + proj_ms) / max(n_stage, 1)          # all kernels of one stage, device time
+    achieved = A * sz.K * sz.Nq / (stage_total_ms * 1e-3) / 1e9 if n_stage else None
+    if not headline:
+        mr, mre = st.reduce(1), st.reduce(2)
+        st.close()
+        del host
+        return {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
+                "roofline_frac": (achieved / peak) if achieved else None, "gpu_launches": int(launches), "counters": counters,
+                "description": w["note"], "developed": dev_info, "min_rho": mr, "min_rhoe": mre}
 
     # ---- end to end through the C ABI with host buffers: every step = host->device copy of that step's
     # input state (pinned), the 3 stages, device->host copy of the result.  Steps are independent jobs,
@@ -255,14 +361,9 @@ def run_ours(args):
 
     e2e_steps = max(3, min(args.steps, 9))
     if args.no_e2e:      # kernel A/B runs only (tools/ab_variants.sh): not a bench line the driver reads
-        if rank == 0:
-            print(json.dumps({"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
-                              "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd,
-                              "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}))
-        if world > 1:
-            dist.barrier()
-            dist.destroy_process_group()
-        return
+        return {"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
+                "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd, "counters": counters,
+                "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}
     e2e_loop([st], [stream], [host], 2)
     initial_state(param, rd, ic, host.numpy())
     serial_ms = timed_e2e([st], [stream], [host], e2e_steps)
@@ -292,33 +393,37 @@ def run_ours(args):
     for s2 in states[1:]:
         s2.close()
 
-    traffic, fp64 = None, None
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    # DRAM traffic and FP64 instruction counts come from one ncu --set full capture (profiles/r2_traffic.json, written by
+    # tools/summarize_ncu.py); they are only quoted for the kernel sources they were captured from (source_hash)
+    traffic, fp64, traffic_note = None, None, "no ncu capture of these kernel sources in profiles/ (traffic: null)"
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            tj = json.load(f).get(args.workload, {})
-        traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
+            tall = json.load(f)
+        tj = tall.get(workload, {})
+        if tall.get("source_hash") == source_hash():
+            traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
+            traffic_note = ("DRAM bytes per stage (dram__bytes_read.sum + dram__bytes_write.sum of the three stage kernels of one step / 3) from one "
+                            "ncu --set full capture of these kernel sources (profiles/r2_traffic.json, source hash checked)")
+        else:
+            traffic_note = "profiles/r2_traffic.json was captured from other kernel sources (hash mismatch): not quoted"
     fp64_peak = None
     ppath = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
     if os.path.exists(ppath):
         with open(ppath) as f:
             fp64_peak = json.load(f)
-    peak, peak_src = peaks()
-    A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
-    stage_total_ms = (stage_ms + upd_ms + proj_ms) / max(n_stage, 1)          # all kernels of one stage, device time
-    achieved = A * sz.K * sz.Nq / (stage_total_ms * 1e-3) / 1e9 if n_stage else None
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": w["note"], "N": param.N, "elements_per_gpu": list(K),
+        "config": {"workload": workload, "description": w["note"], "N": param.N, "elements_per_gpu": list(K),
                    "dof_updates_per_stage": dof_per_stage, "stages_per_step": 3,
                    "l2": "state arrays (2.1 GB each at S-DMR) are far larger than the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (y-stripes)" if world > 1 else "single GPU"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_note": "DRAM bytes per stage (all hot-path kernels of one SSP-RK3 step / 3) from one ncu --set full capture, profiles/r1_traffic.json (S-DMR only)",
-                     "kernel": "all kernels of one RK stage (FAST path: stage_kernel_fast only; generic path: + projection / update kernels)", "algorithmic_bytes_per_dof_update": A,
+                     "traffic_note": traffic_note,
+                     "kernel": "all kernels of one RK stage (subcell family: one stage_subcell_s1/s2/s3 launch; generic path: + projection / update kernels)", "algorithmic_bytes_per_dof_update": A,
                      "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
                      "stage_kernel_share": stage_ms / max(stage_ms + upd_ms + proj_ms, 1e-30),
                      "projection_kernel_ms": (proj_ms / n_proj) if n_proj else None},
@@ -331,22 +436,24 @@ def run_ours(args):
                            "frac": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3) / 1e12 / fp64_peak["dfma_tflops"],
                            "pipe_frac": fp64["lane_ops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3)
                                         / (fp64_peak["dadd_per_clk_sm"] * fp64_peak["sms"] * fp64_peak["clock_mhz"] * 1e6),
-                           "kernel": "stage_kernel_fast", "flops_per_dof_update": fp64["flops_per_dof_update"],
+                           "kernel": "stage_subcell_s1/s2/s3", "flops_per_dof_update": fp64["flops_per_dof_update"],
                            "source": "ncu thread-instruction counts (profiles/r1_traffic.json) and tools/fp64_peak.cu (profiles/r1_fp64_peak.json)"}
                           if (fp64 and fp64_peak and n_stage) else None),
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps,
-                "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others",
-                "serial_value": serial_value, "serial_ms_per_step": serial_ms / e2e_steps},
-        "gpu_launches": int(launches), "clocks": clocks,
+        # headline e2e = ONE handle on ONE stream: host->device copy of the state, the step, device->host copy, strictly in
+        # sequence like a time loop that needs step n's output before step n+1 (PCIe-bound: 4.3 GB per step).  The pipelined
+        # figure (three independent jobs in flight, copies overlapping compute) is kept beside it.
+        "e2e": {"value": serial_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+                "steps": e2e_steps, "ms_per_step": serial_ms / e2e_steps,
+                "mode": "serial: one handle, one stream, copy in -> 3 stages -> copy out per step",
+                "pipelined_value": e2e_value, "pipelined_ms_per_step": e2e_ms / e2e_steps,
+                "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others"},
+        "gpu_launches": int(launches), "clocks": clocks, "counters": counters,
+        "source_hash": source_hash(),
     }
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(args.workload, steps=6, warmup=1)
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    if world > 1 and not args.no_multi_gpu_check:
+        out["multi_gpu_check"] = multi_gpu_check(world, rank, local)
+    st.close()
+    return out
 
 
 def cpu_baseline(workload, steps, warmup):
@@ -359,7 +466,7 @@ def cpu_baseline(workload, steps, warmup):
     K = CPU_SAMPLE_K
     param, ic, bcf = build_problem(workload, K)
     param_, rd, md, dd, bc, U0 = P.setup((param, ic, bcf))
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores = NCORES
     orc = O.Oracle(param, dd, bc, threads=cores)
     orc.set_state(U0)
     t = param.timestepping_param.t0
@@ -408,6 +515,8 @@ def main():
     ap.add_argument("--workload", default="S-DMR", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="device-resident timing only (kernel A/B runs)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the S-WAVE / S-DMR-developed lines under `extra`")
+    ap.add_argument("--no-multi-gpu-check", action="store_true", help="skip the stripes-vs-single-GPU check at N > 1")
     args = ap.parse_args()
     os.environ.setdefault("OMP_PROC_BIND", "close")     # CPU arm: pinned threads (read when libgomp loads)
     os.environ.setdefault("OMP_PLACES", "cores")

@@ -546,9 +546,14 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
   }
 }
 
+#ifdef P2DE_SUB_MAXNREG   // experiment: register cap instead of a minimum CTA count (9 CTAs of 64 threads per SM at 112 registers)
+#define P2DE_SUB_BOUNDS(KIND_) __maxnreg__(P2DE_SUB_MAXNREG)
+#else
+#define P2DE_SUB_BOUNDS(KIND_) __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : (KIND_ != KIND_RT ? P2DE_SUB_MIN_BLOCKS_S23 : P2DE_SUB_MIN_BLOCKS) * (16 / (EPB < 16 ? EPB : 16))))
+#endif
 #define P2DE_SUBCELL_KERNEL(NAME, DEFER_, KIND_)                                                                        \
   template <int N1D, int EPB>                                                                                           \
-  __global__ void __launch_bounds__(EPB * 2 * N1D, (N1D == 5 ? P2DE_SUB_MIN_BLOCKS5 : (KIND_ != KIND_RT ? P2DE_SUB_MIN_BLOCKS_S23 : P2DE_SUB_MIN_BLOCKS) * (16 / (EPB < 16 ? EPB : 16)))) \
+  __global__ void P2DE_SUB_BOUNDS(KIND_)                                                                                \
   NAME(const __grid_constant__ StageArgs A, const __grid_constant__ MeshTopo M, const __grid_constant__ Tables2D<N1D> Tc) { \
     bool interior;                                                                                                      \
     const long long kb = fast_batch<EPB>(A, M, interior);                                                               \

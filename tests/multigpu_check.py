@@ -23,13 +23,9 @@ from p2de_b200.types import Solver  # noqa: E402
 from p2de_b200 import initialize_data  # noqa: E402
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    ok = True
+def default_cases(quick=False):
     cases = [("dmr-subcell", P.dmr(N=3, K=(16, 12)), (False, False)),
-             ("vortex-periodic-subcell", P.vortex(N=2, K=(6, 8), CFL=0.5), (True, True)),
+             ("vortex-periodic-subcell", P.vortex(N=2, K=(6, 8), CFL=0.5, T=10.0), (True, True)),
              ("kh-periodic-zhangshu", P.kelvin_helmholtz(N=3, K=(8, 8), limiter=ZhangShuLimiter()), (True, True)),
              # wide enough for batches strictly inside the mesh: on one GPU the rows next to the cut run the kernel's
              # compile-time INTERIOR version, in the stripes its general version (same arithmetic, different instantiation)
@@ -38,7 +34,18 @@ def main():
              # un-symmetrised coefficients travel with the halo rows
              ("kh-gauss-nodewise-subcell", P.kelvin_helmholtz(N=2, K=(8, 8), basis=GaussCollocation(), entropyproj_limiter=NodewiseScaledExtrapolation(),
                                                            rhs=ESLimitedLowOrderPos(LaxFriedrichsOnProjectedVal(), LaxFriedrichsOnProjectedVal())), (True, True))]
-    for name, problem, periodic in cases:
+    if quick:      # bench.py --gpus N: the headline configuration on a mesh with 3 rows per rank, plus one periodic case
+        cases = [("dmr-wide-subcell", None, (False, False)), ("kh-periodic-subcell", None, (True, True))]
+    return cases
+
+
+def run_cases(rank, world, local, quick=False, nsteps=4):
+    """Each rank advances its y-stripe with halo exchange over NCCL; rank 0 also advances the whole mesh on its own GPU.
+    Needs an initialised torch.distributed NCCL group.  Returns one record per case on rank 0 (None elsewhere)."""
+    out = []
+    for name, problem, periodic in default_cases(quick):
+        if problem is None:
+            problem = P.dmr(N=3, K=(64, 3 * world)) if name.startswith("dmr") else P.kelvin_helmholtz(N=3, K=(64, 3 * world))
         param, rd, md, dd, bc, U0 = P.setup(problem)
         Kx, Ky = param.K
         lp = local_param(param, rank, world)
@@ -53,30 +60,49 @@ def main():
         st.comm_init(rank, world, bytes(uid.cpu().tolist()))
         st.set_state(U0[iy0 * Kx:iy1 * Kx])
         t, dts = param.timestepping_param.t0, []
-        for _ in range(4):
+        for _ in range(nsteps):
             dt = st.ssp33_step(t); t += dt; dts.append(dt)
         mine = torch.from_numpy(st.preallocation.Uq).cuda()
         parts = [torch.empty((stripe_rows(Ky, r, world)[1] - stripe_rows(Ky, r, world)[0]) * Kx, *mine.shape[1:],
                              dtype=torch.float64, device="cuda") for r in range(world)]
-        dist.all_gather(parts, mine) if len({p.shape for p in parts}) == 1 else [dist.broadcast(parts[r] if r != rank else mine, r) for r in range(world)]
-        if len({p.shape for p in parts}) != 1:
-            parts[rank] = mine
+        if len({p.shape for p in parts}) == 1:
+            dist.all_gather(parts, mine)
+        else:
+            for r in range(world):
+                if r == rank:
+                    parts[r] = mine
+                dist.broadcast(parts[r], r)
         if rank == 0:
             full = State(Solver(param=param, rd=rd, md=md, discrete_data=dd), bc, device=local)
             full.set_state(U0)
             t2, dts2 = param.timestepping_param.t0, []
-            for _ in range(4):
+            for _ in range(nsteps):
                 dt = full.ssp33_step(t2); t2 += dt; dts2.append(dt)
             ref = full.preallocation.Uq
             got = torch.cat(parts).cpu().numpy()
-            same = np.array_equal(got, ref) and dts == dts2
-            if not same and name == "dmr-wide-subcell":     # two instantiations of the same source: allow the last bits
-                same = np.abs(got - ref).max() <= 1e-13 * np.abs(ref).max() and np.allclose(dts, dts2, rtol=1e-14, atol=0)
-            print(f"[multigpu_check] {name}: world={world} bitwise_equal={same} max|diff|={np.abs(got - ref).max():.3e} dt={dts[-1]:.6e}")
-            ok = ok and same
+            bitwise = bool(np.array_equal(got, ref) and dts == dts2)
+            maxdiff = float(np.abs(got - ref).max())
+            # the rows next to a cut run the INTERIOR instantiation on one GPU and the general one in the stripes (two
+            # instantiations of the same source): the last bits may differ there
+            ok = bitwise or (maxdiff <= 1e-13 * float(np.abs(ref).max()) and np.allclose(dts, dts2, rtol=1e-14, atol=0))
+            out.append({"case": name, "mesh": [int(Kx), int(Ky)], "world": world, "steps": nsteps, "bitwise_equal": bitwise,
+                        "max_abs_diff": maxdiff, "ok": bool(ok)})
             full.close()
         dist.barrier()
-        st.close()          # ncclCommDestroy: one library communicator per case, not five alive at once
+        st.close()          # ncclCommDestroy: one library communicator per case, not several alive at once
+    return out if rank == 0 else None
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    res = run_cases(rank, world, local)
+    ok = True
+    if rank == 0:
+        for r in res:
+            print(f"[multigpu_check] {r['case']}: world={world} bitwise_equal={r['bitwise_equal']} max|diff|={r['max_abs_diff']:.3e} ok={r['ok']}")
+            ok = ok and r["ok"]
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -153,7 +153,7 @@ def source_hash():
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "p2de_b200", "csrc")
-    for f in sorted(os.listdir(d)):
+    for f in sorted(x for x in os.listdir(d) if x.endswith((".cu", ".cuh"))):
         with open(os.path.join(d, f), "rb") as fh:
             h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]

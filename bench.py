@@ -221,6 +221,7 @@ def run_ours(args):
 def multi_gpu_check(world, rank, local):
     """Outside the timed region: y-stripes over `world` ranks against the whole mesh on rank 0's GPU (tests/multigpu_check.py)."""
     import multigpu_check as mc
+    os.environ["P2DE_OVERLAP_MIN_ROWS"] = "3"       # the check's stripes are 3 rows tall: run the overlapped exchange on them
     res = mc.run_cases(rank, world, local, quick=True)
     if res is None:
         return None
@@ -268,15 +269,26 @@ def measure(args, workload, world, rank, local, headline):
     t0 = param.timestepping_param.t0
     nbytes = host.numel() * 8
 
+    trace = os.environ.get("P2DE_BENCH_TRACE") == "1"
+
+    def tr(msg):
+        if trace:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def barrier():
+        # (device first: a host-side barrier collective must not be launched into a GPU that still runs the step's own
+        #  collectives on another communicator)
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     # ---- device-resident throughput (`value`)
     t = t0
+    tr("state set")
     for _ in range(args.warmup):
         t += st.ssp33_step(t)
+    tr("warm-up done")
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
@@ -285,18 +297,26 @@ def measure(args, workload, world, rank, local, headline):
     launches0 = st.kernel_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if world > 1:
+        # one more untimed step: its halo exchange aligns the ranks on the DEVICE timeline (after a host barrier the ranks'
+        # first launches are milliseconds apart, and the early rank's clock would run while it waits for the late one)
+        st.ssp33_step_async(t)
+        st.profile(True)
     ev0.record(stream)
     tt = t
     for _ in range(args.steps):
         st.ssp33_step_async(tt)
         tt += 0.0          # t only enters through the (T - t) cap; T is far away for the bench configs
     ev1.record(stream)
+    tr("timed steps enqueued")
     barrier()
+    tr("timed steps done")
     ms = ev0.elapsed_time(ev1)
     launches = st.kernel_launch_count() - launches0
     stage_ms, n_stage = st.profile_get(0)
     upd_ms, n_upd = st.profile_get(1)
     proj_ms, n_proj = st.profile_get(2)       # Gauss: entropy-projection kernel (0 launches otherwise)
+    gap_ms, n_gap = st.profile_get(100)       # device time between consecutive hot-path launches (exchanges, collectives, bubbles)
     st.profile(False)
     clocks = sampler.stop()
     if world > 1:
@@ -363,6 +383,7 @@ def measure(args, workload, world, rank, local, headline):
     if args.no_e2e:      # kernel A/B runs only (tools/ab_variants.sh): not a bench line the driver reads
         return {"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
                 "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd, "counters": counters,
+                "between_launches_ms_per_step": gap_ms / args.steps,
                 "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}
     e2e_loop([st], [stream], [host], 2)
     initial_state(param, rd, ic, host.numpy())
@@ -448,6 +469,7 @@ def measure(args, workload, world, rank, local, headline):
                 "pipelined_value": e2e_value, "pipelined_ms_per_step": e2e_ms / e2e_steps,
                 "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others"},
         "gpu_launches": int(launches), "clocks": clocks, "counters": counters,
+        "between_launches_ms_per_step": gap_ms / args.steps,
         "source_hash": source_hash(),
     }
     if world > 1 and not args.no_multi_gpu_check:

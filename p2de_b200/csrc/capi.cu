@@ -44,6 +44,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
   const char *(*GetErrorString)(ncclResult_t);
 };
 
@@ -72,6 +73,7 @@ const NcclApi *nccl_api(std::string *why) {
       api.Send = reinterpret_cast<decltype(api.Send)>(sym("ncclSend"));
       api.Recv = reinterpret_cast<decltype(api.Recv)>(sym("ncclRecv"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(sym("ncclAllReduce"));
+      api.AllGather = reinterpret_cast<decltype(api.AllGather)>(sym("ncclAllGather"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(sym("ncclGetErrorString"));
       state = ok ? 1 : -1;
     }
@@ -144,6 +146,23 @@ struct p2de_handle {
   int rank = 0, nranks = 1, rank_lo = 0, rank_hi = 0;
   bool has_lo = false, has_hi = false;
   ncclComm_t comm = nullptr;
+  // overlapped halo exchange (run_step_overlapped): NCCL runs on its own high-priority stream
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t ev_rows = nullptr, ev_all = nullptr, ev_halo = nullptr, ev_dt = nullptr;
+  int overlap_min_rows = 64;   // P2DE_OVERLAP_MIN_ROWS
+  bool overlap = false;        // p2de_comm_init: the direct schedule exchanges each stage's OUTPUT rows behind its interior rows
+  bool halo_current = false;   // the halo rows of U[cur] hold the neighbours' current boundary rows
+  bool halo_pending = false;   // ev_halo has been recorded and not yet waited for by the compute stream
+  // peer-to-peer halo rows (p2p_setup): the neighbouring stripes' buffers mapped through CUDA IPC; boundary rows travel by
+  // copy engine over NVLink straight into the neighbour's halo rows, a flag word per direction says "rows of exchange #seq
+  // have landed".  Buffer index: 0, 1 = the two state buffers, 2 = rpre.
+  bool p2p = false;
+  double *peer_lo[3] = {nullptr, nullptr, nullptr}, *peer_hi[3] = {nullptr, nullptr, nullptr};   // first OWNED entry of the neighbour's buffer
+  unsigned int *flags = nullptr;                 // [2]: written by the lower / upper neighbour
+  unsigned int *peer_lo_flags = nullptr, *peer_hi_flags = nullptr;
+  std::vector<void *> ipc_opened;
+  unsigned int seq = 0;                          // exchanges issued so far
+  unsigned int wait_seq = 0;                     // flag value the compute stream has to see before the next boundary launch (0 = none pending)
   // optional per-kernel timing (p2de_profile): one event pair per launch, on h->stream
   bool profiling = false;
   struct ProfRec { cudaEvent_t a, b; int kid; };
@@ -225,15 +244,20 @@ int dev_alloc_halo(p2de_handle *h, double **p, size_t n, size_t row) {
 // halo exchange of one boundary element row (`row` doubles) with the stripes below and above.
 // Issue order (sends up, down; receives from below, above) keeps the pairing right when both
 // neighbours are the same rank (2 ranks, periodic).
-int exchange_rows(p2de_handle *h, double *owned, size_t row) {
+int exchange_rows(p2de_handle *h, double *owned, size_t row, cudaStream_t stream = nullptr, bool on_stream = false) {
   if (!h->comm) return 0;
+  if (!on_stream) {
+    stream = h->stream;
+    // (ordering against the overlapped schedule's communication stream: wait for whatever it still has in flight)
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+  }
   const NcclApi *n = nccl_api(nullptr);
   const size_t nown = (size_t)h->cfg.Ky * row;
   NC(h, n->GroupStart());
-  if (h->has_hi) NC(h, n->Send(owned + nown - row, row, ncclDouble, h->rank_hi, h->comm, h->stream));
-  if (h->has_lo) NC(h, n->Send(owned, row, ncclDouble, h->rank_lo, h->comm, h->stream));
-  if (h->has_lo) NC(h, n->Recv(owned - row, row, ncclDouble, h->rank_lo, h->comm, h->stream));
-  if (h->has_hi) NC(h, n->Recv(owned + nown, row, ncclDouble, h->rank_hi, h->comm, h->stream));
+  if (h->has_hi) NC(h, n->Send(owned + nown - row, row, ncclDouble, h->rank_hi, h->comm, stream));
+  if (h->has_lo) NC(h, n->Send(owned, row, ncclDouble, h->rank_lo, h->comm, stream));
+  if (h->has_lo) NC(h, n->Recv(owned - row, row, ncclDouble, h->rank_lo, h->comm, stream));
+  if (h->has_hi) NC(h, n->Recv(owned + nown, row, ncclDouble, h->rank_hi, h->comm, stream));
   NC(h, n->GroupEnd());
   return 0;
 }
@@ -533,8 +557,9 @@ int launch_stage_t(p2de_handle *h, const StageArgs &A) {
   StageArgs A2 = A;
   if (FAST && !h->topo.mapP32 && h->cfg.Kx % EPB == 0 && h->cfg.Ky <= 65535) {
     A2.rowblocks = h->cfg.Kx / EPB;
-    grid = dim3((unsigned)A2.rowblocks, (unsigned)h->cfg.Ky);
-  }
+    if (A.nrows > 0) grid = dim3((unsigned)A2.rowblocks, (unsigned)A.nrows);
+    else { A2.row0 = 0; A2.row_stride = 1; grid = dim3((unsigned)A2.rowblocks, (unsigned)h->cfg.Ky); }
+  } else if (A.nrows > 0) return fail(h, P2DE_ERR_STATE, "row-range launch needs the 2D grid (Kx a multiple of the batch size)");
   prof_begin(h, 0);
   kern<<<grid, EPB * TPE, smem, h->stream>>>(A2, h->topo, tables<N1D>(h));
   prof_end(h);
@@ -940,6 +965,228 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
   return 0;
 }
 
+// ---- peer-to-peer halo rows ---------------------------------------------------------------------------------------------
+// "rows of exchange #seq have landed": written into the neighbour's flag word once the copies in front of it are done
+__global__ void p2p_signal_kernel(volatile unsigned int *flag_a, volatile unsigned int *flag_b, unsigned int seq) {
+  __threadfence_system();
+  if (flag_a) *flag_a = seq;
+  if (flag_b) *flag_b = seq;
+  __threadfence_system();
+}
+// fallback of cuStreamWaitValue32: one thread spins until both flags have reached seq
+__global__ void p2p_wait_kernel(volatile unsigned int *flag_a, volatile unsigned int *flag_b, unsigned int seq) {
+  if (flag_a) while ((int)(*flag_a - seq) < 0) __nanosleep(200);
+  if (flag_b) while ((int)(*flag_b - seq) < 0) __nanosleep(200);
+  __threadfence_system();
+}
+typedef int (*StreamWaitValue32Fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);   // cuStreamWaitValue32(CUstream, CUdeviceptr, value, flags)
+StreamWaitValue32Fn stream_wait_value32() {
+  static StreamWaitValue32Fn fn = [] {
+    const char *no = getenv("P2DE_NO_STREAM_MEMOPS");
+    if (no && atoi(no)) return (StreamWaitValue32Fn) nullptr;
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<StreamWaitValue32Fn>(f);
+  }();
+  return fn;
+}
+
+// An IPC handle names the driver's whole underlying allocation (small cudaMalloc blocks are carved out of larger ones), and
+// cudaIpcOpenMemHandle returns that allocation's base: the exporter sends its pointer's offset from the base along.
+struct PeerInfo { cudaIpcMemHandle_t buf[3]; cudaIpcMemHandle_t flags; long long off[4]; long long Ky; long long pad; };
+typedef int (*MemGetAddressRangeFn)(unsigned long long *, size_t *, unsigned long long);   // cuMemGetAddressRange(CUdeviceptr *, size_t *, CUdeviceptr)
+bool alloc_base_offset(const void *p, long long *off) {
+  static MemGetAddressRangeFn fn = [] {
+    void *f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) f = nullptr;
+    return reinterpret_cast<MemGetAddressRangeFn>(f);
+  }();
+  if (!fn) return false;
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (fn(&base, &size, (unsigned long long)(uintptr_t)p) != 0) return false;
+  *off = (long long)((unsigned long long)(uintptr_t)p - base);
+  return true;
+}
+
+// Map the neighbouring stripes' state buffers and flag words into this process (CUDA IPC; one process per GPU).  Any
+// failure leaves h->p2p false and the NCCL send/recv exchange in place.
+int p2p_setup(p2de_handle *h) {
+  // EXPERIMENTAL, off unless P2DE_P2P=1: bitwise-correct in tests/multigpu_check.py and tests/multigpu_async.py on 2 GPUs,
+  // but the first step hung inside bench.py's process on the same box (unresolved at the end of round 2), so the NCCL
+  // send/recv exchange stays the default.
+  const char *yes = getenv("P2DE_P2P");
+  if (!(yes && atoi(yes)) || !h->fast || h->mode != MODE_SUBCELL || !h->rpre) return 0;
+  const NcclApi *n = nccl_api(nullptr);
+  const size_t rowU = (size_t)h->cfg.Kx * h->Nq * 4;
+  // (an allocation of its own underlying block: IPC handles have the granularity of the driver's blocks, small allocations
+  //  share one and their handle names the whole block)
+  if (int rc = dev_alloc(h, &h->flags, (size_t)(4u << 20) / sizeof(unsigned int))) return rc;
+  CU(h, cudaMemset(h->flags, 0, 2 * sizeof(unsigned int)));
+  PeerInfo mine{};
+  double *bufs[3] = {h->U[0], h->U[1], h->rpre};
+  bool ok = true;
+  for (int i = 0; i < 3; ++i)   // (the buffer starts one halo row before its first owned entry)
+    ok = ok && cudaIpcGetMemHandle(&mine.buf[i], bufs[i] - rowU) == cudaSuccess && alloc_base_offset(bufs[i] - rowU, &mine.off[i]);
+  ok = ok && cudaIpcGetMemHandle(&mine.flags, h->flags) == cudaSuccess && alloc_base_offset(h->flags, &mine.off[3]);
+  mine.Ky = h->cfg.Ky;
+  cudaGetLastError();
+  // every rank must take the same decision: gather (ok, info) from all ranks
+  static_assert(sizeof(PeerInfo) % 8 == 0, "gathered as doubles");
+  const size_t nd = sizeof(PeerInfo) / 8 + 1;
+  std::vector<double> sendb(nd, 0.0), recvb(nd * h->nranks, 0.0);
+  std::memcpy(sendb.data(), &mine, sizeof(PeerInfo));
+  sendb[nd - 1] = ok ? 1.0 : 0.0;
+  double *dsend = nullptr, *drecv = nullptr;
+  if (int rc = dev_alloc(h, &dsend, nd)) return rc;
+  if (int rc = dev_alloc(h, &drecv, nd * h->nranks)) return rc;
+  CU(h, cudaMemcpy(dsend, sendb.data(), nd * 8, cudaMemcpyHostToDevice));
+  NC(h, n->AllGather(dsend, drecv, nd, ncclDouble, h->comm, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(recvb.data(), drecv, nd * 8 * h->nranks, cudaMemcpyDeviceToHost));
+  for (int r = 0; r < h->nranks; ++r) ok = ok && recvb[(size_t)r * nd + nd - 1] == 1.0;
+  if (!ok) return 0;
+  auto open_peer = [&](int r, double *out[3], unsigned int **fl, long long *Ky) -> bool {
+    PeerInfo pi;
+    std::memcpy(&pi, recvb.data() + (size_t)r * nd, sizeof(PeerInfo));
+    for (int i = 0; i < 3; ++i) {
+      void *q = nullptr;
+      if (cudaIpcOpenMemHandle(&q, pi.buf[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+      h->ipc_opened.push_back(q);
+      out[i] = reinterpret_cast<double *>(static_cast<char *>(q) + pi.off[i]) + rowU;
+    }
+    void *q = nullptr;
+    if (cudaIpcOpenMemHandle(&q, pi.flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) return false;
+    h->ipc_opened.push_back(q);
+    *fl = reinterpret_cast<unsigned int *>(static_cast<char *>(q) + pi.off[3]);
+    *Ky = pi.Ky;
+    return true;
+  };
+  long long Ky_lo = 0, Ky_hi = 0;
+  bool opened = true;
+  if (h->has_lo) opened = opened && open_peer(h->rank_lo, h->peer_lo, &h->peer_lo_flags, &Ky_lo);
+  if (opened && h->has_hi) {
+    if (h->has_lo && h->rank_hi == h->rank_lo) {   // two ranks, periodic: one neighbour on both sides, one mapping
+      for (int i = 0; i < 3; ++i) h->peer_hi[i] = h->peer_lo[i];
+      h->peer_hi_flags = h->peer_lo_flags; Ky_hi = Ky_lo;
+    } else opened = opened && open_peer(h->rank_hi, h->peer_hi, &h->peer_hi_flags, &Ky_hi);
+  }
+  cudaGetLastError();
+  // the lower neighbour's upper halo row sits behind ITS owned rows
+  if (opened && h->has_lo) for (int i = 0; i < 3; ++i) h->peer_lo[i] += (size_t)Ky_lo * rowU;   // now: the neighbour's upper halo row
+  if (opened && h->has_hi) for (int i = 0; i < 3; ++i) h->peer_hi[i] -= rowU;                      // now: the neighbour's lower halo row
+  // (again a collective decision: a rank that could not map its neighbours keeps everybody on NCCL)
+  double flag = opened ? 1.0 : 0.0;
+  CU(h, cudaMemcpy(dsend, &flag, 8, cudaMemcpyHostToDevice));
+  NC(h, n->AllReduce(dsend, dsend, 1, ncclDouble, ncclMin, h->comm, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  CU(h, cudaMemcpy(&flag, dsend, 8, cudaMemcpyDeviceToHost));
+  h->p2p = flag == 1.0;
+  return 0;
+}
+
+// boundary rows of `buf` (index bi) into the neighbours' halo rows, then the flags; all on the communication stream
+int p2p_push_rows(p2de_handle *h, const double *buf, int bi) {
+  const size_t rowU = (size_t)h->cfg.Kx * h->Nq * 4;
+  ++h->seq;
+  if (h->has_hi) CU(h, cudaMemcpyAsync(h->peer_hi[bi], buf + (size_t)(h->cfg.Ky - 1) * rowU, rowU * sizeof(double), cudaMemcpyDeviceToDevice, h->comm_stream));
+  if (h->has_lo) CU(h, cudaMemcpyAsync(h->peer_lo[bi], buf, rowU * sizeof(double), cudaMemcpyDeviceToDevice, h->comm_stream));
+  // I am the upper neighbour's LOWER neighbour (its flag word 0) and the lower neighbour's UPPER neighbour (its flag word 1)
+  p2p_signal_kernel<<<1, 1, 0, h->comm_stream>>>(h->has_hi ? h->peer_hi_flags + 0 : nullptr, h->has_lo ? h->peer_lo_flags + 1 : nullptr, h->seq);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  h->wait_seq = h->seq;
+  return 0;
+}
+// the compute stream waits until both neighbours' rows of exchange #wait_seq have landed in this stripe's halo rows
+int p2p_wait_rows(p2de_handle *h) {
+  if (!h->wait_seq) return 0;
+  const unsigned int seq = h->wait_seq;
+  h->wait_seq = 0;
+  if (StreamWaitValue32Fn wv = stream_wait_value32()) {
+    bool ok = true;
+    if (h->has_lo) ok = ok && wv(h->stream, (unsigned long long)(uintptr_t)(h->flags + 0), seq, 0x1 /* CU_STREAM_WAIT_VALUE_GEQ */) == 0;
+    if (ok && h->has_hi) ok = ok && wv(h->stream, (unsigned long long)(uintptr_t)(h->flags + 1), seq, 0x1) == 0;
+    if (ok) return 0;
+  }
+  p2p_wait_kernel<<<1, 1, 0, h->stream>>>(h->has_lo ? h->flags + 0 : nullptr, h->has_hi ? h->flags + 1 : nullptr, seq);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  return 0;
+}
+
+// One SSP-RK3 step of the subcell family on a y-stripe with the halo exchange hidden behind the interior rows.
+// Per stage: the two boundary element rows run first (a 2-row launch of the same kernel), their OUTPUT rows travel to
+// the neighbouring stripes on the communication stream (NCCL send/recv) while the remaining rows run on the compute
+// stream; the next stage's boundary launch waits for the exchange.  What travels is what the next stage reads beyond
+// the cut: stage 1's W, stage 2's U2, stage 3's U^{n+1} (whose halo stays valid for stages 1 and 2 of the next step).
+// The CFL dt all-reduce (low_order_graph_viscosity.jl:242) is issued on the same communication stream once both
+// stage-1 launches are done; it is the only exposed collective of the step.
+int run_step_overlapped(p2de_handle *h, double t, double cap) {
+  double *Ua = h->U[h->cur], *Ub = h->U[1 - h->cur];
+  const size_t rowU = (size_t)h->cfg.Kx * h->Nq * 4;
+  const NcclApi *n = nccl_api(nullptr);
+  auto buf_index = [&](const double *b) { return b == h->U[0] ? 0 : b == h->U[1] ? 1 : 2; };
+  // rows of `buf` to the neighbours, on the communication stream, after whatever the compute stream has enqueued so far
+  auto send_rows = [&](double *buf, cudaEvent_t after) -> int {
+    CU(h, cudaEventRecord(after, h->stream));
+    CU(h, cudaStreamWaitEvent(h->comm_stream, after, 0));
+    if (h->p2p) { if (int rc = p2p_push_rows(h, buf, buf_index(buf))) return rc; }
+    else if (int rc = exchange_rows(h, buf, rowU, h->comm_stream, true)) return rc;
+    CU(h, cudaEventRecord(h->ev_halo, h->comm_stream));
+    h->halo_pending = true;
+    return 0;
+  };
+  // the compute stream may read the halo rows: NCCL: the exchange (send and receive) is done; P2P: the neighbours' flags
+  auto wait_rows = [&]() -> int {
+    if (h->p2p) return p2p_wait_rows(h);
+    if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }
+    return 0;
+  };
+  if (!h->halo_current) {   // first step after set_state: the halo of U^n has not travelled yet
+    if (int rc = send_rows(Ua, h->ev_all)) return rc;
+    h->halo_current = true;
+  }
+  set_dt_kernel<<<1, 1, 0, h->stream>>>(h->dt_bits, cap, 1);
+  CU(h, cudaGetLastError());
+  h->launches++;
+  struct StageIO { const double *in; double *out; const double *resW; double a, b; const double *add; };
+  const StageIO io[3] = {{Ua, h->rpre, nullptr, 0.0, 1.0, nullptr},
+                         {Ua, Ub, Ua, 3.0 / 4.0, 1.0 / 4.0, h->rpre},
+                         {Ub, Ua, Ua, 1.0 / 3.0, 2.0 / 3.0, nullptr}};
+  for (int st = 1; st <= 3; ++st) {
+    const StageIO &s = io[st - 1];
+    StageArgs A = stage_args(h, s.in, st, cap, st > 1);
+    A.rpre = s.out;
+    if (st == 1) { A.wform = 1; }
+    else { A.fuse = 1; A.fuse_a = s.a; A.fuse_b = s.b; A.fuse_resW = s.resW; }
+    A.inv_cap = 1.0 / cap;
+    A.defer_add = s.add;
+    if (h->Llocal) A.lpre = h->Llocal + (size_t)h->nLloc * h->K * (st - 1);
+    if (st == 1) h->rpre_w = true;
+    // boundary rows: need the halo of this stage's input
+    if (int rc = wait_rows()) return rc;
+    StageArgs B = A;
+    B.row0 = 0; B.row_stride = h->cfg.Ky - 1; B.nrows = 2;
+    if (int rc = launch_stage(h, B)) return rc;
+    if (int rc = send_rows(s.out, h->ev_rows)) return rc;
+    // interior rows
+    StageArgs I = A;
+    I.row0 = 1; I.row_stride = 1; I.nrows = h->cfg.Ky - 2;
+    if (int rc = launch_stage(h, I)) return rc;
+    if (st == 1) {   // global CFL dt: min over all stripes, after both stage-1 launches
+      CU(h, cudaEventRecord(h->ev_all, h->stream));
+      CU(h, cudaStreamWaitEvent(h->comm_stream, h->ev_all, 0));
+      NC(h, n->AllReduce(h->dt_bits, h->dt_bits, 2, ncclDouble, ncclMin, h->comm, h->comm_stream));
+      CU(h, cudaEventRecord(h->ev_dt, h->comm_stream));
+      CU(h, cudaStreamWaitEvent(h->stream, h->ev_dt, 0));
+    }
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1106,7 +1353,11 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
 int32_t p2de_destroy(p2de_handle *h) {
   if (!h) return P2DE_OK;
   DEV(h);
+  if (h->comm_stream) cudaStreamSynchronize(h->comm_stream);
   if (h->comm) { if (const NcclApi *n = nccl_api(nullptr)) n->CommDestroy(h->comm); }
+  for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
+  for (cudaEvent_t e : {h->ev_rows, h->ev_all, h->ev_halo, h->ev_dt}) if (e) cudaEventDestroy(e);
+  if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
   prof_clear(h);
   for (void *p : h->owned) cudaFree(p);
   delete h;
@@ -1123,14 +1374,17 @@ int32_t p2de_synchronize(p2de_handle *h) {
   if (!h) return P2DE_ERR_ARG;
   DEV(h);
   CU(h, cudaStreamSynchronize(h->stream));
+  if (h->comm_stream) CU(h, cudaStreamSynchronize(h->comm_stream));
   return P2DE_OK;
 }
 
 int32_t p2de_set_state_async(p2de_handle *h, const double *Uq_host) {
   if (!h || !Uq_host) return fail(h, P2DE_ERR_ARG, "null argument");
   DEV(h);
+  if (h->halo_pending) { CU(h, cudaStreamWaitEvent(h->stream, h->ev_halo, 0)); h->halo_pending = false; }   // the last exchange still reads the old boundary rows
   CU(h, cudaMemcpyAsync(h->U[h->cur], Uq_host, (size_t)h->K * h->Nq * h->Nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   h->have_state = true;
+  h->halo_current = false;
   return P2DE_OK;
 }
 int32_t p2de_set_state(p2de_handle *h, const double *Uq_host) {
@@ -1178,6 +1432,11 @@ int32_t p2de_ssp33_step_async(p2de_handle *h, double t) {
   double *Ua = h->U[h->cur], *Ub = h->U[1 - h->cur];
   double cap = std::fmin(h->cfg.CFL * h->cfg.dt0, h->cfg.T - t);   // SSPRK33.jl:30
   const bool has_cfl = h->mode != MODE_HIGH;                          // FluxDiffRHS never changes dt (rhs.jl:38)
+  // (stripes of at least 64 element rows: below that the two extra launches per stage cost more than the exchange they hide)
+  if (fast_direct && h->comm && h->overlap && h->defer && cap > 0.0 && h->cfg.Ky >= (h->p2p ? 3 : h->overlap_min_rows) && h->cfg.Ky <= 65535 &&
+      h->cfg.Kx % (h->N1D == 4 ? LaunchSub<4>::EPB : h->N1D == 5 ? LaunchSub<5>::EPB : LaunchSub<2>::EPB) == 0)
+    return run_step_overlapped(h, t, cap);
+  h->halo_current = false;   // the schedules below exchange in front of every stage and leave the new state's halo stale
   if (fast_direct) {
     // Direct schedule: stages 2 and 3 write their result from the stage kernel (run_stage: `direct`), which
     // needs an output buffer other than the stage input: U1 -> Ub (dense update, dt only known after the
@@ -1301,6 +1560,15 @@ int32_t p2de_profile_get(p2de_handle *h, int32_t kernel_id, double *total_ms, in
   DEV(h);
   CU(h, cudaStreamSynchronize(h->stream));
   double tot = 0; int64_t n = 0;
+  if (kernel_id == 100) {   // device time BETWEEN consecutive profiled launches (exchanges, collectives, launch bubbles)
+    for (size_t i = 0; i + 1 < h->prof.size(); ++i) {
+      float ms = 0;
+      CU(h, cudaEventElapsedTime(&ms, h->prof[i].b, h->prof[i + 1].a));
+      tot += ms; ++n;
+    }
+    *total_ms = tot; *launches = n;
+    return P2DE_OK;
+  }
   for (auto &r : h->prof) {
     if (r.kid != kernel_id) continue;
     float ms = 0;
@@ -1363,6 +1631,15 @@ int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8
   ncclResult_t r = n->CommInitRank(&comm, nranks, id, rank);
   if (r != ncclSuccess) return fail(h, P2DE_ERR_NCCL, "ncclCommInitRank: %s", n->GetErrorString(r));
   h->comm = comm;
+  {
+    const char *no = getenv("P2DE_NO_OVERLAP");   // testing / A-B aid: blocking exchange in front of every stage kernel
+    h->overlap = !(no && atoi(no));
+    if (const char *mr = getenv("P2DE_OVERLAP_MIN_ROWS")) h->overlap_min_rows = std::max(3, atoi(mr));
+    int lo = 0, hi = 0;
+    CU(h, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CU(h, cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t *e : {&h->ev_rows, &h->ev_all, &h->ev_halo, &h->ev_dt}) CU(h, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
   // y-stripes: rank r owns element rows [r*Ky, (r+1)*Ky) of the global mesh; the stripe below /
   // above is rank -/+ 1, wrapping around when the global mesh is periodic in y.
   const bool per_y = h->topo.periodic_y != 0;
@@ -1371,6 +1648,7 @@ int32_t p2de_comm_init(p2de_handle *h, int32_t rank, int32_t nranks, const uint8
   h->rank_lo = (rank - 1 + nranks) % nranks;
   h->rank_hi = (rank + 1) % nranks;
   h->topo.ghost_lo = h->has_lo; h->topo.ghost_hi = h->has_hi;
+  if (h->overlap) if (int rc = p2p_setup(h)) return rc;
   return P2DE_OK;
 }
 

@@ -107,7 +107,8 @@ struct StageArgs {
   const double *defer_add;
   double inv_cap;                    // 1 / dt_host
   int wform;                         // stage 1 of p2de_ssp33_step (subcell family): write W = U + dt_host rhsU instead of rhsU (stage_subcell.cuh: KIND_S1)
-  int rowblocks;                     // FAST kernel: > 0 = 2D grid (rowblocks x Ky), Kx = rowblocks * EPB; 0 = 1D grid over batches
+  int rowblocks;                     // FAST kernel: > 0 = 2D grid (rowblocks x rows), Kx = rowblocks * EPB; 0 = 1D grid over batches
+  int row0, row_stride, nrows;       // 2D grid: the launch covers element rows row0 + i * row_stride, i < nrows (nrows = 0: all Ky rows)
   double *fstar;                     // Gauss + cell entropy: [K][Nfp][2][4] normal components of fstar_H, fstar_L (State.jl:11-12)
   unsigned long long *dbg;           // nullptr, or the counters of p2de_debug_counters (P2DE_DBG_*): which instantiations ran, data-dependent shortcuts taken
 };

@@ -556,8 +556,13 @@ P2DE_DEV long long fast_batch(const StageArgs &A, const MeshTopo &M, bool &inter
   long long kb;
   interior = false;
   if (A.rowblocks) {   // structured mesh with Kx a multiple of EPB: 2D grid (batch in row, element row), no division
-    kb = ((long long)blockIdx.y * A.rowblocks + blockIdx.x) * EPB;
-    interior = blockIdx.x > 0u && blockIdx.x + 1u < (unsigned)A.rowblocks && blockIdx.y > 0u && blockIdx.y + 1u < gridDim.y;
+    // (a launch may cover a subset of the element rows: row = row0 + blockIdx.y * row_stride, see run_step_overlapped)
+    const unsigned row = (unsigned)A.row0 + blockIdx.y * (unsigned)A.row_stride;
+    kb = ((long long)row * A.rowblocks + blockIdx.x) * EPB;
+    // a stripe's first / last row is interior too when its neighbour row is a halo row (stored right before / after the
+    // owned rows, no boundary condition on the cut)
+    interior = blockIdx.x > 0u && blockIdx.x + 1u < (unsigned)A.rowblocks &&
+               (row > 0u || M.ghost_lo) && (row + 1u < (unsigned)M.Ky || M.ghost_hi);
   } else {
     kb = (long long)blockIdx.x * EPB;
     if (!M.mapP32 && kb + EPB <= M.K && M.K < 0x7fffffffll) {

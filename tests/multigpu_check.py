@@ -12,6 +12,7 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+os.environ.setdefault("P2DE_OVERLAP_MIN_ROWS", "3")   # exercise the overlapped exchange on these small stripes too (read at comm_init)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as P  # noqa: E402

@@ -209,6 +209,20 @@ int32_t p2de_ssp33_run(p2de_handle *h, double *t_inout, int64_t max_steps,
 
 int32_t p2de_reduce(p2de_handle *h, int32_t what, double *out);
 
+/* calculate_error (src/dg/postprocess.jl:1-28) on the device: `exact_host` = the exact solution's conserved
+ * variables at the nodes, double[K][Nq][Nc] (evaluated by the caller's exact_sol callback); `out` receives
+ * double[6][Nc] = sum wJ |ex-U|, sum wJ |ex-U|^2, max |ex-U|, sum wJ |ex|, sum wJ |ex|^2, max |ex| per component
+ * (wJ = wq[i] * Jq).  The relative norms of :29-37 are three divisions away.                              */
+int32_t p2de_calculate_error(p2de_handle *h, const double *exact_host, double *out);
+
+/* DataHistory of SSP33! (src/timestepping/SSPRK33.jl:41-55, src/common/types/State.jl): p2de_ssp33_run keeps a
+ * copy of Uq on the device whenever the reference would push one to Uhist (step counter i % output_interval == 0
+ * or |t - T| < 1e-10), in a ring of `slots` states (the newest `slots` survive).  slots = 0 frees the ring.
+ * p2de_snapshot_get copies snapshot `index` (0-based, in the order they were taken) and its time / step counter. */
+int32_t p2de_snapshot_ring(p2de_handle *h, int32_t slots, int64_t output_interval);
+int64_t p2de_snapshot_count(const p2de_handle *h);
+int32_t p2de_snapshot_get(p2de_handle *h, int64_t index, double *Uq_host, double *t_out, int64_t *step_out);
+
 /* ---- multi-GPU: element rows are partitioned in y, one handle (one process) per GPU.
  * `unique_id` is the 128-byte ncclUniqueId produced by p2de_comm_unique_id on rank 0
  * and broadcast by the host.  After this call p2de_rhs / p2de_ssp33_step exchange the

@@ -175,6 +175,39 @@ class State:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         _lib.check(self.L, self.h, self.L.p2de_comm_init(self.h, rank, nranks, buf))
 
+    def ssp33_run(self, t: float, max_steps: int = 2 ** 62):
+        """The `while t < T` loop of SSP33! inside the library (p2de_ssp33_run): returns (t, dthist)."""
+        tt, n = C.c_double(t), C.c_int64()
+        cap = min(max_steps, 1 << 22)
+        dth = np.empty(cap, dtype=np.float64)
+        _lib.check(self.L, self.h, self.L.p2de_ssp33_run(self.h, C.byref(tt), cap, C.byref(n), dth.ctypes.data))
+        return tt.value, dth[:n.value].copy()
+
+    def snapshot_ring(self, slots: int, output_interval: int):
+        _lib.check(self.L, self.h, self.L.p2de_snapshot_ring(self.h, int(slots), int(output_interval)))
+
+    def snapshots(self):
+        """[(t, step, Uq)] of the snapshots still in the ring, oldest first."""
+        n = int(self.L.p2de_snapshot_count(self.h))
+        out, sz = [], self.sizes
+        for idx in range(n):
+            U = np.empty((sz.K, sz.Nq, sz.Nc), dtype=np.float64)
+            t, step = C.c_double(), C.c_int64()
+            rc = self.L.p2de_snapshot_get(self.h, idx, U.ctypes.data, C.byref(t), C.byref(step))
+            if rc == 0:
+                out.append((t.value, int(step.value), U))
+        return out
+
+    def error_sums(self, exact: np.ndarray) -> np.ndarray:
+        """p2de_calculate_error: [6, Nc] = sum wJ|ex-U|, sum wJ|ex-U|^2, max|ex-U|, sum wJ|ex|, sum wJ ex^2, max|ex|."""
+        sz = self.sizes
+        ex = np.ascontiguousarray(exact, dtype=np.float64)
+        if ex.shape != (sz.K, sz.Nq, sz.Nc):
+            raise ValueError(f"exact must have shape {(sz.K, sz.Nq, sz.Nc)}, got {ex.shape}")
+        out = np.empty((6, sz.Nc), dtype=np.float64)
+        _lib.check(self.L, self.h, self.L.p2de_calculate_error(self.h, ex.ctypes.data, out.ctypes.data))
+        return out
+
     DBG_NAMES = ("cta_general", "cta_interior", "cta_defer", "elem_logs", "elem", "lines", "lines_not_easy", "limiter_slow")
 
     def debug_counters(self, enable: bool = True) -> dict:
@@ -218,40 +251,40 @@ def check_conservation(state: State, solver: Solver) -> float:
     return state.reduce(T.REDUCE_CONSERVATION)
 
 
-def SSP33(state: State, solver: Solver, state_param: StateParam, verbose: bool = False) -> DataHistory:
-    """`SSP33!` (SSPRK33.jl:1-62): the time loop; three fused stages per step stay on the device."""
+def SSP33(state: State, solver: Solver, state_param: StateParam, verbose: bool = False, max_snapshots: int = 64) -> DataHistory:
+    """`SSP33!` (SSPRK33.jl:1-62): the whole time loop runs inside the library (p2de_ssp33_run), three fused stages per
+    step on the device; the states the reference pushes to Uhist every `output_interval` steps and at the final time are
+    kept in a device-side ring (the newest `max_snapshots`) and read back afterwards.  Lhist / thetahist carry the
+    values of the last step (State.jl:21-24 keeps one L per stage, not a history)."""
     tp = solver.param.timestepping_param
     output_interval = solver.param.postprocessing_param.output_interval
     hist = DataHistory()
-    t, i = tp.t0, 1
-    while t < tp.T:
-        dt = state.ssp33_step(t)
-        t = t + dt
-        i = i + 1
-        hist.dthist.append(dt)
-        if i % output_interval == 0 or abs(t - tp.T) < 1e-10:
-            hist.thist.append(t)
-            hist.Uhist.append(state.preallocation.Uq)
-            hist.Lhist.append(state.preallocation.L)
-            hist.thetahist.append(state.preallocation.theta)
-            if verbose:
-                print(f"Current time {t} with time step size {dt}, and final time {tp.T}, step {i}")
-                print("total_conservation =", check_conservation(state, solver))
+    state.snapshot_ring(max_snapshots, output_interval)
+    t, dth = state.ssp33_run(tp.t0)
+    hist.dthist.extend(float(d) for d in dth)
+    for ts, step, U in state.snapshots():
+        hist.thist.append(ts)
+        hist.Uhist.append(U)
+        hist.Lhist.append(state.preallocation.L)
+        hist.thetahist.append(state.preallocation.theta)
+        if verbose:
+            print(f"Snapshot at time {ts}, step {step}, final time {tp.T}")
+    if verbose:
+        print("total_conservation =", check_conservation(state, solver))
+    state.snapshot_ring(0, 0)
     return hist
 
 
 def calculate_error(state: State, solver: Solver, exact_sol: Callable, verbose: bool = False) -> ErrorData:
-    """calculate_error (postprocess.jl:1-46); `exact_sol(equation, x[, y], t)` returns primitives."""
-    param, md, dd = solver.param, solver.md, solver.discrete_data
-    Uq = state.preallocation.Uq
+    """calculate_error (postprocess.jl:1-46); `exact_sol(equation, x[, y], t)` returns primitives.  The caller's callback
+    is evaluated on the host (it is the caller's code), the weighted sums and maxima over the mesh are taken on the device
+    (p2de_calculate_error)."""
+    param, md = solver.param, solver.md
     Tend = param.timestepping_param.T
     args = (md.xq,) if md.yq is None else (md.xq, md.yq)
     ex = np.stack([np.broadcast_to(np.asarray(c, dtype=np.float64), md.xq.shape) for c in
                    primitive_to_conservative(param.equation, exact_sol(param.equation, *args, Tend))], axis=-1)
-    wJ = (dd.ops.wq * dd.geom.Jq.reshape(-1)[0])[None, :, None]     # wq[i] * Jq[i] (linear index, :15)
-    diff = np.abs(ex - Uq)
-    L1err, L2err, Linferr = (wJ * diff).sum((0, 1)), (wJ * diff ** 2).sum((0, 1)), diff.max((0, 1))
-    L1ex, L2ex, Linfex = (wJ * np.abs(ex)).sum((0, 1)), (wJ * ex ** 2).sum((0, 1)), np.abs(ex).max((0, 1))
+    L1err, L2err, Linferr, L1ex, L2ex, Linfex = state.error_sums(ex)
     L1 = L2 = Linf = 0.0
     for c in range(param.equation.Nc):
         if Linfex[c] > 1e-14:

@@ -142,6 +142,13 @@ struct p2de_handle {
   double *bc_val[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<void *> owned;
   double last_dt = 0;
+  // DataHistory snapshots (SSPRK33.jl:45-55): a ring of state copies on the device, filled by p2de_ssp33_run
+  int snap_slots = 0;
+  int64_t snap_interval = 0, snap_count = 0;
+  double *snap_buf = nullptr;
+  std::vector<double> snap_t;
+  std::vector<int64_t> snap_step;
+  double *err_stage = nullptr;   // staging buffer of p2de_calculate_error
   // multi-GPU (y-stripes, one handle per GPU): NCCL communicator and stripe neighbours
   int rank = 0, nranks = 1, rank_lo = 0, rank_hi = 0;
   bool has_lo = false, has_hi = false;
@@ -504,6 +511,34 @@ __global__ void reduce_kernel(const double *U, const double *wq, int Nq, long lo
     __syncthreads();
   }
   if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// calculate_error (postprocess.jl:1-28): per component sum wJ |ex - U|, sum wJ |ex - U|^2, max |ex - U| and the same of ex.
+// One chunk of nodes per launch; per-block partials [block][6][Nc] are added up on the host.
+__global__ void error_norm_kernel(const double *U, const double *ex, const double *wq, int Nq, int Nc, long long node0, long long n_nodes,
+                                  double J, double *partial) {
+  __shared__ double sh[256];
+  double acc[6][4];
+  for (int q = 0; q < 6; ++q) for (int c = 0; c < 4; ++c) acc[q][c] = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_nodes; i += (long long)gridDim.x * blockDim.x) {
+    const double wJ = J * wq[(node0 + i) % Nq];
+    for (int c = 0; c < Nc; ++c) {
+      const double e = ex[i * Nc + c], d = fabs(e - U[(node0 + i) * Nc + c]);
+      acc[0][c] += wJ * d; acc[1][c] += wJ * d * d; acc[2][c] = fmax(acc[2][c], d);
+      acc[3][c] += wJ * fabs(e); acc[4][c] += wJ * e * e; acc[5][c] = fmax(acc[5][c], fabs(e));
+    }
+  }
+  for (int q = 0; q < 6; ++q)
+    for (int c = 0; c < Nc; ++c) {
+      sh[threadIdx.x] = acc[q][c];
+      __syncthreads();
+      for (int st = blockDim.x / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st) sh[threadIdx.x] = (q == 2 || q == 5) ? fmax(sh[threadIdx.x], sh[threadIdx.x + st]) : sh[threadIdx.x] + sh[threadIdx.x + st];
+        __syncthreads();
+      }
+      if (threadIdx.x == 0) partial[(blockIdx.x * 6 + q) * 4 + c] = sh[0];
+      __syncthreads();
+    }
 }
 
 template <int N1D, int MODE, bool FAST>
@@ -1495,9 +1530,77 @@ int32_t p2de_ssp33_run(p2de_handle *h, double *t_inout, int64_t max_steps, int64
     t += dt;
     if (dthist) dthist[n] = dt;
     ++n;
+    // DataHistory (SSPRK33.jl:41-55: `i` starts at 1 and is incremented before the test): a copy of Uq every
+    // output_interval steps and at the final time, kept in the device-side ring
+    if (h->snap_slots > 0 && ((h->snap_interval > 0 && (n + 1) % h->snap_interval == 0) || std::fabs(t - h->cfg.T) < 1e-10)) {
+      const size_t nU = (size_t)h->K * h->Nq * h->Nc;
+      const int slot = (int)(h->snap_count % h->snap_slots);
+      CU(h, cudaMemcpyAsync(h->snap_buf + (size_t)slot * nU, h->U[h->cur], nU * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+      h->snap_t[slot] = t; h->snap_step[slot] = n + 1;
+      ++h->snap_count;
+    }
   }
   *t_inout = t;
   if (steps_out) *steps_out = n;
+  return P2DE_OK;
+}
+
+int32_t p2de_snapshot_ring(p2de_handle *h, int32_t slots, int64_t output_interval) {
+  if (!h || slots < 0) return fail(h, P2DE_ERR_ARG, "slots must be >= 0");
+  DEV(h);
+  CU(h, cudaStreamSynchronize(h->stream));
+  const size_t nU = (size_t)h->K * h->Nq * h->Nc;
+  if (slots != h->snap_slots) {
+    if (h->snap_buf) { cudaFree(h->snap_buf); h->owned.erase(std::remove(h->owned.begin(), h->owned.end(), (void *)h->snap_buf), h->owned.end()); h->snap_buf = nullptr; }
+    if (slots > 0) if (int rc = dev_alloc(h, &h->snap_buf, nU * (size_t)slots)) return rc;
+    h->snap_slots = slots;
+  }
+  h->snap_interval = output_interval; h->snap_count = 0;
+  h->snap_t.assign((size_t)slots, 0.0); h->snap_step.assign((size_t)slots, 0);
+  return P2DE_OK;
+}
+int64_t p2de_snapshot_count(const p2de_handle *h) { return h ? h->snap_count : 0; }
+int32_t p2de_snapshot_get(p2de_handle *h, int64_t index, double *Uq_host, double *t_out, int64_t *step_out) {
+  if (!h) return P2DE_ERR_ARG;
+  DEV(h);
+  const int64_t first = h->snap_count > h->snap_slots ? h->snap_count - h->snap_slots : 0;
+  if (index < first || index >= h->snap_count) return fail(h, P2DE_ERR_ARG, "snapshot %lld is not in the ring (%lld..%lld)", (long long)index, (long long)first, (long long)h->snap_count - 1);
+  const int slot = (int)(index % h->snap_slots);
+  const size_t nU = (size_t)h->K * h->Nq * h->Nc;
+  if (Uq_host) {
+    CU(h, cudaMemcpyAsync(Uq_host, h->snap_buf + (size_t)slot * nU, nU * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  if (t_out) *t_out = h->snap_t[slot];
+  if (step_out) *step_out = h->snap_step[slot];
+  return P2DE_OK;
+}
+
+int32_t p2de_calculate_error(p2de_handle *h, const double *exact_host, double *out) {
+  if (!h || !exact_host || !out) return fail(h, P2DE_ERR_ARG, "null argument");
+  if (!h->have_state) return fail(h, P2DE_ERR_STATE, "calculate_error before set_state");
+  DEV(h);
+  const long long n_nodes = h->K * h->Nq, chunk = 1ll << 20;
+  const int blocks = 256, Nc = h->Nc;
+  if (!h->err_stage) if (int rc = dev_alloc(h, &h->err_stage, (size_t)chunk * 4 + (size_t)blocks * 24)) return rc;
+  double *partial = h->err_stage + (size_t)chunk * 4;
+  std::vector<double> part((size_t)blocks * 24), acc(24, 0.0);
+  for (long long n0 = 0; n0 < n_nodes; n0 += chunk) {
+    const long long nn = std::min(chunk, n_nodes - n0);
+    CU(h, cudaMemcpyAsync(h->err_stage, exact_host + n0 * Nc, (size_t)nn * Nc * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    error_norm_kernel<<<blocks, 256, 0, h->stream>>>(h->U[h->cur], h->err_stage, h->partial + 1024, h->Nq, Nc, n0, nn, h->Jq, partial);
+    CU(h, cudaGetLastError());
+    h->launches++;
+    CU(h, cudaMemcpyAsync(part.data(), partial, part.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    for (int b = 0; b < blocks; ++b)
+      for (int q = 0; q < 6; ++q)
+        for (int c = 0; c < Nc; ++c) {
+          const double v = part[((size_t)b * 6 + q) * 4 + c];
+          acc[q * 4 + c] = (q == 2 || q == 5) ? std::fmax(acc[q * 4 + c], v) : acc[q * 4 + c] + v;
+        }
+  }
+  for (int q = 0; q < 6; ++q) for (int c = 0; c < Nc; ++c) out[q * Nc + c] = acc[q * 4 + c];
   return P2DE_OK;
 }
 

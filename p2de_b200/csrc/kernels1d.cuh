@@ -110,6 +110,10 @@ P2DE_DEV double limiting_param_pos1(double ZEROTOL, const Cons1 &U, const double
   return jl_min(l, 1.0);
 }
 P2DE_DEV double find_alpha1(double POSTOL, const Cons1 &ui, const Cons1 &ut) {   // low_order_graph_viscosity.jl:299-327
+  if (!P2DE_FIND_ALPHA_BISECT) {   // closed form of what the bisection converges to (kernels2d.cuh: find_alpha_closed)
+    const double dr = ut.rho - ui.rho, dm = ut.m - ui.m, dE = ut.E - ui.E;
+    return find_alpha_closed<void>(POSTOL, ui.rho, ui.E, ui.m * ui.m, dr, dE, ui.m * dm, dm * dm);
+  }
   double alphaL = 0.0, alphaR = 1.0;
   Cons1 s;
   auto sub = [&](double al) { s.rho = al * ui.rho - ut.rho; s.m = al * ui.m - ut.m; s.E = al * ui.E - ut.E; };

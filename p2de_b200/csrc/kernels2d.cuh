@@ -185,8 +185,39 @@ P2DE_DEV void store4(double *p, const double v[4]) {
 }
 P2DE_DEV void cons_arr(const Cons2 &U, double v[4]) { v[0] = U.rho; v[1] = U.m1; v[2] = U.m2; v[3] = U.E; }
 
-// find_alpha, low_order_graph_viscosity.jl:299-327
+#ifndef P2DE_FIND_ALPHA_BISECT
+#define P2DE_FIND_ALPHA_BISECT 0   // 1: the reference's 50-step bisection (validation aid)
+#endif
+// find_alpha, low_order_graph_viscosity.jl:299-327: the smallest alpha with rho(alpha u - u~) > eps and
+// rho e(alpha u - u~) > eps.  The reference brackets it by doubling and bisects 50 times (an interval of 2^-50 alpha_0);
+// what the bisection converges to is known in closed form.  With beta = alpha - 1 and delta = u~ - u (formed first, so
+// that nothing cancels when u~ is close to u), alpha u - u~ = beta u - delta and
+//   rho > eps                   <=>  beta > (delta_rho + eps) / rho
+//   E rho - |m|^2/2 > eps rho   <=>  A beta^2 + B beta + C > 0,   A = E rho - |m|^2/2  (> 0),
+//                                    B = -(E delta_rho + delta_E rho) + m . delta_m - eps rho,
+//                                    C = delta_E delta_rho - |delta_m|^2/2 + eps delta_rho,
+// so alpha = 1 + max(density bound, larger root), the root taken in its cancellation-free form.  Agrees with the
+// bisection to its own evaluation noise (1e-14 typical, the predicate is evaluated on differences of size eps); alpha
+// only enters the CFL dt (lambda_B_CFL :287-293), tested to 1e-12.
+template <class C>
+P2DE_DEV double find_alpha_closed(double eps, double rho, double E, double msq, double drho, double dE, double mdm, double dmsq) {
+  double beta = (drho + eps) / rho;
+  const double Aq = E * rho - 0.5 * msq;
+  const double Bq = -(E * drho + dE * rho) + mdm - eps * rho;
+  const double Cq = dE * drho - 0.5 * dmsq + eps * drho;
+  const double disc = Bq * Bq - 4.0 * Aq * Cq;
+  if (disc >= 0.0) {
+    const double sq = sqrt(disc);
+    const double root = Bq <= 0.0 ? (sq - Bq) / (2.0 * Aq) : -2.0 * Cq / (Bq + sq);
+    beta = fmax(beta, root);
+  }
+  return fmax(1.0 + beta, 8.881784197001252e-16);   // (the bisection never returns less than 2^-50)
+}
 P2DE_DEV double find_alpha(double POSTOL, const Cons2 &ui, const Cons2 &ut) {
+  if (!P2DE_FIND_ALPHA_BISECT) {
+    const double dr = ut.rho - ui.rho, d1 = ut.m1 - ui.m1, d2 = ut.m2 - ui.m2, dE = ut.E - ui.E;
+    return find_alpha_closed<void>(POSTOL, ui.rho, ui.E, ui.m1 * ui.m1 + ui.m2 * ui.m2, dr, dE, ui.m1 * d1 + ui.m2 * d2, d1 * d1 + d2 * d2);
+  }
   double alphaL = 0.0, alphaR = 1.0;
   Cons2 s;
   auto sub = [&](double al) { s.rho = al * ui.rho - ut.rho; s.m1 = al * ui.m1 - ut.m1; s.m2 = al * ui.m2 - ut.m2; s.E = al * ui.E - ut.E; };

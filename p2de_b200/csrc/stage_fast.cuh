@@ -371,7 +371,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         for (int a = 0; a < N1D - 1; ++a) {
           const int i = a + 1, j = a;
           double Sv = T.S0[d][line][a];
-          double lam = fabs(Sv) * fmax(ws[i], ws[j]);
+          double lam = fabs(Sv) * jl_max(ws[i], ws[j]);
           lamPair[a] = lam;
           const double ui[4] = {U[i].rho, U[i].mn, U[i].mt, U[i].E}, uj[4] = {U[j].rho, U[j].mn, U[j].mt, U[j].E};
 #pragma unroll
@@ -391,7 +391,7 @@ __device__ __forceinline__ void stage_fast_impl(const StageArgs &A, const MeshTo
         double B = T.Bf[d][line][e], nn = fabs(B);
         double rinvP = rcp_fast(Unb[e].rho);
         double wsP = wavespeed_rot(gamma, gm1, rinvP, Unb[e].mn, Unb[e].E);
-        double lamB = 0.5 * nn * fmax(ws[ae], wsP);
+        double lamB = 0.5 * nn * jl_max(ws[ae], wsP);
         ConsR uP = Unb[e];
         const int bce = INTERIOR ? 0 : nb[e].bc;
         if (bce) {

@@ -222,7 +222,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       const double B = T.Bf[d][line][e], nn = fabs(B), hB = 0.5 * B;
       double rinvP = rcp_fast(Unb[e].rho);
       const double wsP = wavespeed_rot(gamma, gm1, rinvP, Unb[e].mn, Unb[e].E);
-      const double lamB = 0.5 * nn * fmax(ws, wsP);
+      const double lamB = 0.5 * nn * jl_max(ws, wsP);   // (Julia's max: a NaN wavespeed reaches the CFL dt)
       ConsR uP = Unb[e];
       const int bce = INTERIOR ? 0 : nb[e].bc;
       if (bce) {
@@ -275,7 +275,7 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       derive(a, Uc, flc, wsc);
       // low-order graph-viscosity pair (a, a-1), low_order_graph_viscosity.jl:139-166
       const double Sv = T.S0[d][line][a - 1];
-      const double lam = fabs(Sv) * fmax(wsc, wsp);
+      const double lam = fabs(Sv) * jl_max(wsc, wsp);
       const double ui[4] = {Uc.rho, Uc.mn, Uc.mt, Uc.E}, uj[4] = {Up.rho, Up.mn, Up.mt, Up.E};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {

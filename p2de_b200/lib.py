@@ -17,7 +17,8 @@ EXPORTS = [
     "p2de_set_state_async", "p2de_get_state_async", "p2de_synchronize", "p2de_rhs", "p2de_get_field",
     "p2de_ssp33_step", "p2de_ssp33_step_async", "p2de_last_dt", "p2de_ssp33_run", "p2de_reduce",
     "p2de_comm_unique_id", "p2de_comm_init", "p2de_kernel_launch_count", "p2de_device_state_ptr",
-    "p2de_profile", "p2de_profile_get", "p2de_debug_counters",
+    "p2de_profile", "p2de_profile_get", "p2de_debug_counters", "p2de_calculate_error",
+    "p2de_snapshot_ring", "p2de_snapshot_count", "p2de_snapshot_get",
 ]
 
 _LIB = None
@@ -58,6 +59,10 @@ def load():
     L.p2de_comm_init.restype = i32; L.p2de_comm_init.argtypes = [vp, i32, i32, vp]
     L.p2de_profile.restype = i32; L.p2de_profile.argtypes = [vp, i32]
     L.p2de_profile_get.restype = i32; L.p2de_profile_get.argtypes = [vp, i32, dp, C.POINTER(i64)]
+    L.p2de_calculate_error.restype = i32; L.p2de_calculate_error.argtypes = [vp, vp, vp]
+    L.p2de_snapshot_ring.restype = i32; L.p2de_snapshot_ring.argtypes = [vp, i32, i64]
+    L.p2de_snapshot_count.restype = i64; L.p2de_snapshot_count.argtypes = [vp]
+    L.p2de_snapshot_get.restype = i32; L.p2de_snapshot_get.argtypes = [vp, i64, vp, dp, C.POINTER(i64)]
     L.p2de_debug_counters.restype = i32; L.p2de_debug_counters.argtypes = [vp, i32, vp]
     L.p2de_kernel_launch_count.restype = i64; L.p2de_kernel_launch_count.argtypes = [vp]
     L.p2de_device_state_ptr.restype = vp; L.p2de_device_state_ptr.argtypes = [vp]

@@ -487,6 +487,13 @@ __global__ void set_dt_kernel(unsigned long long *dt_bits, double v, int with_fl
 }
 
 // minimum(s_modified) over all nodes (initialize_s_modified!, subcell.jl:19-35); s_modified > 0
+__global__ void smin1d_kernel(const double *U, long long n_nodes, double gamma, unsigned long long *out_bits) {
+  double m = INFINITY;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_nodes; i += (long long)gridDim.x * blockDim.x)
+    m = fmin(m, s_modified1(gamma, load1(U + i * 3)));
+  for (int off = 16; off > 0; off >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m < INFINITY) atomicMin(out_bits, (unsigned long long)__double_as_longlong(m));
+}
 __global__ void smin_kernel(const double *U, long long n_nodes, double gamma, unsigned long long *out_bits) {
   double m = INFINITY;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_nodes; i += (long long)gridDim.x * blockDim.x)
@@ -802,6 +809,26 @@ int run_stage_1d(p2de_handle *h, const double *Uin, int nstage, double dt_host, 
   A.Jq = h->Jq; A.rxJ = h->rxJ1; A.blend = 1.0; A.mode = h->mode;
   A.vol_flux = h->cfg.vol_flux; A.surf_low = h->cfg.surf_flux_low; A.surf_high = h->cfg.surf_flux_high;
   A.roundtrip = h->cfg.lgl_projection_roundtrip;
+  A.tvd = h->tvd; A.rhsLpre = h->rhsLpre; A.entropy_bound = h->entropy_bound; A.cell_entropy = h->cell_entropy;
+  A.hennemann = h->cfg.shockcapture == P2DE_SHOCKCAPTURE_HENNEMANN; A.N = h->cfg.N;
+  A.hen_a = h->cfg.hennemann_a; A.hen_c = h->cfg.hennemann_c; A.bound_beta = h->cfg.bound_beta;
+  A.VDM_inv = h->VDM_inv; A.smin_dev = reinterpret_cast<const double *>(h->smin_bits);
+  if (h->tvd) {
+    // TVD bounds (subcell.jl:86-110): rho + dt rhsL[1] of the stencil nodes across the element faces needs the neighbours'
+    // finished low-order rhs: a MODE_LOW pre-pass of the same kernel writes it for all elements
+    Args1D P = A;
+    P.mode = MODE_LOW; P.rhsU = h->rhsLpre; P.nstage = 2;   // nstage != 1: no CFL reduction in the pre-pass
+    P.rhsH_diag = nullptr; P.rhsL_diag = nullptr; P.tvd = 0; P.entropy_bound = 0; P.cell_entropy = 0; P.hennemann = 0;
+    Upd1D none{};
+    int rc = 0;
+    switch (h->N1D) {
+      case 2: rc = run_stage_1d_t<2>(h, P, none, false); break;
+      case 3: rc = run_stage_1d_t<3>(h, P, none, false); break;
+      case 4: rc = run_stage_1d_t<4>(h, P, none, false); break;
+      case 5: rc = run_stage_1d_t<5>(h, P, none, false); break;
+    }
+    if (rc) return rc;
+  }
   Upd1D B{};
   B.rhsL = h->rhsL; B.dF = h->dF; B.lpre = h->lpre; B.rhsU_in = h->rhsU;
   B.Llocal_out = (want_outputs && h->mode == MODE_SUBCELL) ? h->Llocal + (size_t)h->nLloc * h->K * (nstage - 1) : nullptr;
@@ -874,6 +901,13 @@ int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *ge
   CU(h, cudaMemcpy(h->partial + 1024, h->wq.data(), Nq * sizeof(double), cudaMemcpyHostToDevice));
   if (h->mode == MODE_SUBCELL)
     if ((rc = dev_alloc(h, &h->rhsL, nU)) || (rc = dev_alloc(h, &h->dF, (size_t)K * (Nq + 1) * 3)) || (rc = dev_alloc(h, &h->lpre, (size_t)K * (Nq + 1)))) return rc;
+  if (h->tvd && (rc = dev_alloc(h, &h->rhsLpre, nU))) return rc;
+  if ((rc = dev_alloc(h, &h->smin_bits, 1))) return rc;
+  CU(h, cudaMemset(h->smin_bits, 0, sizeof(unsigned long long)));   // s_modified_min starts at 0.0 (State.jl:180)
+  if (ops->VDM_inv) {
+    if ((rc = dev_alloc(h, &h->VDM_inv, (size_t)Nq * Nq))) return rc;
+    CU(h, cudaMemcpy(h->VDM_inv, ops->VDM_inv, (size_t)Nq * Nq * sizeof(double), cudaMemcpyHostToDevice));
+  }
   if (h->cfg.keep_diagnostics) {
     if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return rc;
     CU(h, cudaMemset(h->rhsH_diag, 0, nU * sizeof(double))); CU(h, cudaMemset(h->rhsL_diag, 0, nU * sizeof(double)));
@@ -920,7 +954,15 @@ int run_stage(p2de_handle *h, const double *Uin, int nstage, double t, double dt
     CU(h, cudaGetLastError());
     h->launches++;
   }
-  if (h->dim == 1) return run_stage_1d(h, Uin, nstage, dt_host, limiter_dt_dev, update_dt_dev, Uout, resW, a, b, want_outputs);
+  if (h->dim == 1) {
+    if (h->entropy_bound && nstage == 1 && t == h->cfg.t0) {   // subcell.jl:32-34: global minimum of the initial condition
+      set_dt_kernel<<<1, 1, 0, h->stream>>>(h->smin_bits, INFINITY, 0);
+      smin1d_kernel<<<64, 256, 0, h->stream>>>(Uin, h->K * h->Nq, h->cfg.gamma, h->smin_bits);
+      CU(h, cudaGetLastError());
+      h->launches += 2;
+    }
+    return run_stage_1d(h, Uin, nstage, dt_host, limiter_dt_dev, update_dt_dev, Uout, resW, a, b, want_outputs);
+  }
   if (h->rhsH_diag && h->mode == MODE_SUBCELL)
     CU(h, cudaMemsetAsync(h->rhsH_diag, 0, (size_t)h->K * h->Nq * h->Nc * sizeof(double), h->stream));
   if (h->entropy_bound && nstage == 1 && t == h->cfg.t0) {   // subcell.jl:32-34: global minimum of the initial condition
@@ -1242,8 +1284,8 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d %s", cfg->N, d1 ? "line" : "quad");
   if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
   if (d1 && cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation: 2D only in this build (SURVEY.md 8f-1)");
-  if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE && (d1 || !ops->VDM_inv))
-    return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture: 2D only and needs ops.VDM_inv");
+  if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE && !ops->VDM_inv)
+    return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture needs ops.VDM_inv");
   int mode;
   if (cfg->rhs_type == P2DE_RHS_LOW_ORDER_POSITIVITY) mode = MODE_LOW;
   else if (cfg->rhs_type == P2DE_RHS_FLUX_DIFF) mode = MODE_HIGH;
@@ -1251,8 +1293,6 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
     if (cfg->limiter == P2DE_LIMITER_ZHANGSHU) mode = MODE_ZHANGSHU;
     else if (cfg->limiter == P2DE_LIMITER_SUBCELL) {
       if (cfg->bound < P2DE_BOUND_POSITIVITY || cfg->bound > P2DE_BOUND_TVD_RELAXED_CELL_ENTROPY) return fail(nullptr, P2DE_ERR_ARG, "bound %d", cfg->bound);
-      if (cfg->bound != P2DE_BOUND_POSITIVITY && d1)
-        return fail(nullptr, P2DE_ERR_UNSUPPORTED, "bound %d: only PositivityBound has a 1D kernel (SURVEY.md 8f-2)", cfg->bound);
       // the smoothness indicator runs for every bound but PositivityBound (shock_capture.jl:4-12) and needs inv(VDM)
       if (cfg->bound != P2DE_BOUND_POSITIVITY && cfg->bound != P2DE_BOUND_TVD && !ops->VDM_inv)
         return fail(nullptr, P2DE_ERR_ARG, "bound %d needs ops.VDM_inv", cfg->bound);

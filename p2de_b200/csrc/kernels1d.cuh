@@ -49,6 +49,15 @@ struct Args1D {
   const double *Ival;                // [nI][3]
   double gamma, ZEROTOL, POSTOL, zeta, CFL, Jq, rxJ, blend;
   int mode, vol_flux, surf_low, surf_high, roundtrip;
+  // remaining subcell bounds and shock capturing (Solver.jl:47-74), as in the generic 2D kernel
+  int tvd;                           // TVD*Bound: rho in [min, max] of the low-order update over the low-order stencil
+  const double *rhsLpre;             // [K][Nq][3] low-order rhs of ALL elements (MODE_LOW pre-pass): the stencil crosses faces
+  int entropy_bound;                 // 0 none, 1 PositivityAndMinEntropyBound, 2 ...RelaxedMinEntropyBound (and the TVD variants)
+  int cell_entropy;                  // 0 none, 1 *CellEntropyBound, 2 *RelaxedCellEntropyBound(beta)
+  int hennemann, N;
+  double hen_a, hen_c, bound_beta;
+  const double *VDM_inv;             // [Np, Nq] column-major
+  const double *smin_dev;            // global minimum of s_modified at t0
 };
 
 struct Upd1D {
@@ -98,6 +107,33 @@ P2DE_DEV void fS1(double gm1, const Prim1 &L, const Prim1 &R, double F[3]) {    
   double f4aux = rholog / (2 * gm1 * betalog) + pa + 0.5 * rholog * unorm;
   double F1 = rholog * uavg;
   F[0] = F1; F[1] = F1 * uavg + pa; F[2] = f4aux * uavg;
+}
+P2DE_DEV double s_modified1(double gamma, const Cons1 &U) { return rhoe1(U) * pow(U.rho, -gamma); }          // :80-85
+// limiting_param_bound_rho_rhoe with a finite upper density bound (limiter_utils.jl:26-40; Urhoe = Inf gives 1)
+P2DE_DEV double limiting_param_rho_bounds1(double ZEROTOL, const Cons1 &U, const double Pv[3], double Lrho, double Lrhoe, double Urho) {
+  double l = 1.0;
+  if (U.rho + Pv[0] < Lrho) l = jl_max((Lrho - U.rho) / Pv[0], 0.0);
+  if (U.rho + Pv[0] > Urho) l = jl_min(l, jl_max((Urho - U.rho) / Pv[0], 0.0));
+  double a = Pv[0] * Pv[2] - 1.0 / 2.0 * (Pv[1] * Pv[1]);
+  double b = U.E * Pv[0] + U.rho * Pv[2] - U.m * Pv[1] - Pv[0] * Lrhoe;
+  double c = U.E * U.rho - 1.0 / 2.0 * (U.m * U.m) - U.rho * Lrhoe;
+  l = jl_min(l, rhoe_quadratic_roots(ZEROTOL, a, b, c));
+  return jl_min(l, 1.0);
+}
+// limiting_param_bound_phi (limiter_utils.jl:42-50) with the reference's bisection (nonlinear_solvers.jl: 20 halvings,
+// returns the last lower end that satisfied the predicate)
+P2DE_DEV double limiting_param_phi1(double gamma, double POSTOL, const Cons1 &U, const double Pv[3], double Lphi, double lpos) {
+  auto f = [&](double l) {
+    Cons1 W; W.rho = U.rho + l * Pv[0]; W.m = U.m + l * Pv[1]; W.E = U.E + l * Pv[2];
+    return s_modified1(gamma, W) >= Lphi - POSTOL;
+  };
+  if (f(lpos)) return lpos;
+  double x_valid = 0.0, x_invalid = lpos;
+  for (int iter = 0; iter <= 20; ++iter) {
+    double x_new = 0.5 * (x_valid + x_invalid);
+    if (f(x_new)) x_valid = x_new; else x_invalid = x_new;
+  }
+  return x_valid;
 }
 // limiter_utils.jl:26-90 (Dim1 coefficients :78-83), positivity bounds (Urho = Urhoe = Inf)
 P2DE_DEV double limiting_param_pos1(double ZEROTOL, const Cons1 &U, const double Pv[3], double Lrho, double Lrhoe) {
@@ -158,9 +194,11 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
     Cons1 ut[2], utP[2], UnodeP[2], uP_L[2], uP_H[2];
     int bc[2];
     const double *ival[2];
+    long long kPs[2]; int nodeP[2];      // low-order stencil across the faces (limiter_utils.jl:184-207): partner element / node
     for (int f = 0; f < 2; ++f) {
       int m = A.mapP32[k * 2 + f];
       long long kP = m / 2; int fP = m % 2;
+      kPs[f] = kP; nodeP[f] = T.fq2q[fP];
       Cons1 Unb[Nq];
       for (int i = 0; i < Nq; ++i) Unb[i] = load1(A.Uq + (kP * Nq + i) * 3);
       ut[f] = project_face<N1D>(T, gamma, gm1, A.roundtrip, U, f);
@@ -265,6 +303,32 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
     (void)uP_L; (void)uP_H;
 
     const double dtl = A.use_dt_dev ? dt_read(A.dt_dev) : A.dt_host;
+    // ---- smoothness indicator (shock_capture.jl:4-94), blending factor (:111-132), smoothness factor of the relaxed
+    //      bounds (subcell.jl:927-956)
+    double blend = A.blend, epsk = A.entropy_bound == 1 ? 1.0 : 0.0;
+    if (A.hennemann || A.entropy_bound == 2 || A.cell_entropy == 2) {
+      double ind[Nq], eN = 0.0, eNm1 = 0.0, etot = 0.0;
+      for (int i = 0; i < Nq; ++i) ind[i] = U[i].rho * p1(gm1, U[i]);
+      for (int m = 0; m < Nq; ++m) {
+        double coef = 0.0;
+        for (int j = 0; j < Nq; ++j) coef += A.VDM_inv[m + j * Nq] * ind[j];
+        double e = coef * coef;
+        if (m == A.N) eN += e;
+        if (m == A.N - 1) eNm1 += e;
+        etot += e;
+      }
+      const double sigma = jl_max(eN / etot, eNm1 / etot);
+      if (A.hennemann) {
+        const double TN = A.hen_a * pow(10.0, -A.hen_c * pow((double)(A.N + 1), 0.25));
+        const double s_factor = log((1 - 0.0001) / 0.0001);
+        const double al = 1.0 / (1.0 + exp(-s_factor / TN * (sigma - TN)));
+        blend = jl_max(jl_min(1.0 - al, 1.0), 0.5);
+      }
+      if (A.entropy_bound == 2 || A.cell_entropy == 2) {
+        const double kappa = 1.0, s0 = log10(pow((double)A.N, -4.0)), sk = log10(sigma);
+        epsk = sk < s0 - kappa ? 0.0 : (sk > s0 + kappa ? 1.0 : 0.5 - 0.5 * sin(3.141592653589793 * (sk - s0) / (2 * kappa)));
+      }
+    }
     if (A.mode == MODE_SUBCELL) {
       // accumulate_f_bar! (subcell.jl:144-160) and subcell_bound_limiter!(::Dim1) (:208-246)
       double fH[3], fL[3], dF[Nq + 1][3];
@@ -275,18 +339,103 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
           fL[c] = fL[c] + A.Jq * T.wq[i - 1] * rL[i - 1][c];
           dF[i][c] = fH[c] - fL[c];
         }
+      // ---- bounds over the low-order stencil {i-1, i+1} (neighbour element's face node across a face):
+      //      minimum modified entropy (subcell.jl:37-55), TVD density interval (:86-110)
+      double Lphi[Nq], Lrho_b[Nq], Urho_b[Nq];
+      for (int i = 0; i < Nq; ++i) { Lphi[i] = 0.0; Lrho_b[i] = 0.0; Urho_b[i] = INFINITY; }
+      if (A.entropy_bound) {
+        double sm[Nq], smP[2];
+        for (int i = 0; i < Nq; ++i) sm[i] = s_modified1(gamma, U[i]);
+        for (int f = 0; f < 2; ++f) smP[f] = s_modified1(gamma, load1(A.Uq + (kPs[f] * Nq + nodeP[f]) * 3));
+        const double smin = *A.smin_dev;
+        for (int i = 0; i < Nq; ++i) {
+          double lb = sm[i];
+          lb = jl_min(lb, i > 0 ? sm[i - 1] : smP[0]);
+          lb = jl_min(lb, i < Nq - 1 ? sm[i + 1] : smP[1]);
+          Lphi[i] = epsk * lb + (1 - epsk) * smin;
+        }
+      }
+      if (A.tvd) {
+        double rhoL[Nq], rhoLP[2];
+        for (int i = 0; i < Nq; ++i) rhoL[i] = U[i].rho + dtl * rL[i][0];
+        for (int f = 0; f < 2; ++f) {
+          const long long q = kPs[f] * Nq + nodeP[f];
+          rhoLP[f] = A.Uq[q * 3] + dtl * A.rhsLpre[q * 3];
+        }
+        for (int i = 0; i < Nq; ++i) {
+          const double a = i > 0 ? rhoL[i - 1] : rhoLP[0], b = i < Nq - 1 ? rhoL[i + 1] : rhoLP[1];
+          Lrho_b[i] = jl_min(jl_min(rhoL[i], a), b);
+          Urho_b[i] = jl_max(jl_max(rhoL[i], a), b);
+        }
+      }
       double lv[Nq + 1];
       for (int i = 0; i < Nq + 1; ++i) lv[i] = 1.0;
       for (int i = 0; i < Nq; ++i) {
         Cons1 uL; uL.rho = U[i].rho + dtl * rL[i][0]; uL.m = U[i].m + dtl * rL[i][1]; uL.E = U[i].E + dtl * rL[i][2];
-        double wJ = T.wq[i] * A.Jq, Lrho = A.zeta * uL.rho, Lrhoe = A.zeta * rhoe1(uL);
+        double wJ = T.wq[i] * A.Jq, Lrho = A.tvd ? Lrho_b[i] : A.zeta * uL.rho, Lrhoe = A.zeta * rhoe1(uL);
         double Pm[3], Pp[3];
         for (int c = 0; c < 3; ++c) { Pm[c] = -2 * dtl * dF[i][c] / wJ; Pp[c] = 2 * dtl * dF[i + 1][c] / wJ; }
-        lv[i] = jl_min(lv[i], limiting_param_pos1(A.ZEROTOL, uL, Pm, Lrho, Lrhoe));
-        lv[i + 1] = jl_min(lv[i + 1], limiting_param_pos1(A.ZEROTOL, uL, Pp, Lrho, Lrhoe));
+        double lm = A.tvd ? limiting_param_rho_bounds1(A.ZEROTOL, uL, Pm, Lrho, Lrhoe, Urho_b[i]) : limiting_param_pos1(A.ZEROTOL, uL, Pm, Lrho, Lrhoe);
+        double lp = A.tvd ? limiting_param_rho_bounds1(A.ZEROTOL, uL, Pp, Lrho, Lrhoe, Urho_b[i]) : limiting_param_pos1(A.ZEROTOL, uL, Pp, Lrho, Lrhoe);
+        if (A.entropy_bound) {
+          lm = limiting_param_phi1(gamma, A.POSTOL, uL, Pm, Lphi[i], lm);
+          lp = limiting_param_phi1(gamma, A.POSTOL, uL, Pp, Lphi[i], lp);
+        }
+        lv[i] = jl_min(lv[i], lm);
+        lv[i + 1] = jl_min(lv[i + 1], lp);
+      }
+      for (int i = 0; i < Nq + 1; ++i) lv[i] = jl_min(lv[i], blend);   // shock capturing (subcell.jl:243-245)
+      if (A.cell_entropy) {
+        // ---- enforce_ES_subcell!(::Dim1) (subcell.jl:458-707): entropy estimate of the element's interior subcell faces
+        //      and the greedy fix in descending (dv.dF, index) order; no interface part in 1D
+        double V[Nq][3], dv[Nq], fLr[3], fHr[3];
+        for (int i = 0; i < Nq; ++i) v_of_u1(gamma, gm1, U[i], V[i]);
+        double sBpsi = 0.0;
+        for (int f = 0; f < 2; ++f) sBpsi += (T.Br[f] * A.rxJ) * (gm1 * U[T.fq2q[f]].m);   // psi_ufun :124-132 at the face's volume node
+        double sdvfL = 0.0;
+        for (int c = 0; c < 3; ++c) { fHr[c] = BFH[0][c]; fLr[c] = BFL[0][c]; }
+        for (int si = 1; si < Nq; ++si) {
+          for (int c = 0; c < 3; ++c) { fHr[c] = fHr[c] + A.Jq * T.wq[si - 1] * rH[si - 1][c]; fLr[c] = fLr[c] + A.Jq * T.wq[si - 1] * rL[si - 1][c]; }
+          double a = 0.0, b = 0.0;
+          for (int c = 0; c < 3; ++c) { const double dvc = V[si - 1][c] - V[si][c]; a += dvc * (fHr[c] - fLr[c]); b += dvc * fLr[c]; }
+          dv[si - 1] = a; sdvfL += b;
+        }
+        const int n = Nq - 1;
+        double sum_poslim = 0.0;
+        for (int i = 0; i < n; ++i) sum_poslim += lv[i + 1] * dv[i];
+        const double rhs_es = (A.cell_entropy == 1) ? sBpsi - sdvfL : (1 - A.bound_beta * epsk) * (sBpsi - sdvfL);
+        const double tol = jl_max(0.0, sdvfL - sBpsi);
+        if (sum_poslim - rhs_es > tol) {
+          bool used[Nq];
+          for (int i = 0; i < n; ++i) used[i] = false;
+          double lhs = sum_poslim;
+          int last = -1;
+          while (lhs > rhs_es + tol) {
+            int best = -1;   // the largest remaining (dv, index) tuple: sort!(..., rev=true) on tuples, Base.isless semantics
+            for (int i = 0; i < n; ++i) {
+              if (used[i]) continue;
+              if (best < 0) { best = i; continue; }
+              const double x = dv[i], y = dv[best];
+              bool greater;
+              if (x != x) greater = !(y != y) || i > best;
+              else if (y != y) greater = false;
+              else if (x == y) greater = (signbit(y) && !signbit(x)) || (signbit(x) == signbit(y) && i > best);
+              else greater = x > y;
+              if (greater) best = i;
+            }
+            if (best < 0 || dv[best] < A.ZEROTOL) break;
+            lhs = lhs - lv[best + 1] * dv[best];
+            used[best] = true; last = best;
+          }
+          for (int i = 0; i < n; ++i)
+            if (used[i]) {
+              const double l_new = (i == last) ? jl_max((rhs_es + tol - lhs) / dv[i], 0.0) : 0.0;
+              lv[i + 1] = jl_min(lv[i + 1], l_new);
+            }
+        }
       }
       for (int i = 0; i < Nq + 1; ++i) {
-        A.lpre[k * (Nq + 1) + i] = jl_min(lv[i], A.blend);
+        A.lpre[k * (Nq + 1) + i] = lv[i];
         for (int c = 0; c < 3; ++c) A.dF[(k * (Nq + 1) + i) * 3 + c] = dF[i][c];
       }
       for (int i = 0; i < Nq; ++i) for (int c = 0; c < 3; ++c) A.rhsL[(k * Nq + i) * 3 + c] = rL[i][c];
@@ -300,7 +449,7 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
           l = jl_min(l, limiting_param_pos1(A.ZEROTOL, uL, Pv, A.zeta * uL.rho, A.zeta * rhoe1(uL)));
         }
         A.Lout[k] = l;
-        l = jl_min(l, A.blend);
+        l = jl_min(l, blend);
       }
       for (int i = 0; i < Nq; ++i)
         for (int c = 0; c < 3; ++c)

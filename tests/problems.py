@@ -162,6 +162,39 @@ def shu_osher(N=3, K=64, **kw):
     return make_param(N, K, -5.0, 5.0, dim=1, **kw), ic, bc
 
 
+# ---- Leblanc shock tube: examples/convergence/leblanc-convergence.jl:9-62 (gamma = 5/3, t0 = 0.01, T = 2/3) -------------
+def leblanc_exact(eqn, x, t):
+    """exact_sol of the reference script, vectorised: primitives (rho, u, p) at time t."""
+    g = eqn.gamma
+    x = np.asarray(x, dtype=np.float64)
+    rhoL, rhoR, pL, pR = 1.0, 1e-3, (g - 1) * 1e-1, (g - 1) * 1e-10
+    if t == 0:
+        left = x < 0.33
+        return np.where(left, rhoL, rhoR), 0 * x, np.where(left, pL, pR)
+    xi = (x - 0.33) / t
+    rhoLs, rhoRs = 5.4079335349316249e-2, 3.9999980604299963e-3
+    vs, ps = 0.62183867139173454, 0.51557792765096996e-3
+    l1, l3 = 0.49578489518897934, 0.82911836253346982
+    fan = np.clip(0.75 - 0.75 * xi, 1e-300, None)
+    rho = np.select([xi <= -1 / 3, xi <= l1, xi <= vs, xi <= l3], [rhoL, fan ** 3, rhoLs, rhoRs], rhoR)
+    u = np.select([xi <= -1 / 3, xi <= l1, xi <= l3], [0.0, 0.75 * (1 / 3 + xi), vs], 0.0)
+    p = np.select([xi <= -1 / 3, xi <= l1, xi <= l3], [pL, fan ** 5 / 15, ps], pR)
+    return rho, u, p
+
+
+def leblanc(N=2, K=100, **kw):
+    kw.setdefault("T", 2.0 / 3.0); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-3); kw.setdefault("t0", 0.01)
+    kw.setdefault("gamma", 5.0 / 3.0); kw.setdefault("eta", 0.1)
+
+    def ic(param, x):
+        return primitive_to_conservative(param.equation, leblanc_exact(param.equation, x, param.timestepping_param.t0))
+
+    def bc(param, md):
+        Ival = np.array([primitive_to_conservative(param.equation, (1.0, 0.0, (param.equation.gamma - 1) * 1e-1))])
+        return BCData(md.mapP, [1], [2 * md.K], Ival)
+    return make_param(N, K, 0.0, 1.0, dim=1, **kw), ic, bc
+
+
 def density_wave_1d(N=3, K=16, **kw):
     kw.setdefault("T", 1.0); kw.setdefault("CFL", 0.5); kw.setdefault("dt0", 1e-2)
 

@@ -276,3 +276,51 @@ def test_direct_schedule_matches_two_kernel_schedule(monkeypatch):
         for U, dts in out[1:]:
             assert np.allclose(dts, out[0][1], rtol=1e-12, atol=0)
             assert rel(U, out[0][0]) < 1e-11
+
+
+# ---- BASELINE.json config 2 on the GPU: Shu-Osher to T = 1.8 against the reference's own WENO5 data, and the Leblanc tube
+#      (examples/convergence/leblanc-convergence.jl) against its exact solution through calculate_error
+def test_1d_shu_osher_gpu_matches_reference_weno5_data():
+    """examples/1D/shu-osher.jl:70-74 overlays data/weno5_shuosher.mat on its plot; here the GPU run to T = 1.8 (N=3, K=128) is
+    held to the same number as the oracle (tests/test_oracle_1d.py): relative L1 density difference below 1.2 %."""
+    import os
+    from p2de_b200.api import State, SSP33
+    from p2de_b200.types import Solver
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "weno5_shuosher_sub.npz"))
+    param, rd, md, dd, bc, U0 = P.setup(P.shu_osher(N=3, K=128))
+    solver = Solver(param=param, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc)
+    st.set_state(U0)
+    hist = SSP33(st, solver, None)
+    assert abs(hist.thist[-1] - 1.8) < 1e-10
+    U = st.preallocation.Uq
+    x, rho = md.xq.reshape(-1), U[..., 0].reshape(-1)
+    ref = np.interp(x, g["x"], g["rho"])
+    w = (dd.ops.wq[None, :] * dd.geom.Jq).reshape(-1)
+    err = (w * np.abs(rho - ref)).sum() / (w * np.abs(ref)).sum()
+    assert err < 1.2e-2, err
+    assert rho.min() > 0.4 and st.reduce(T.REDUCE_MIN_RHOE) > 0
+    st.close()
+
+
+@pytest.mark.parametrize("limiter", [SubcellLimiter(), ZhangShuLimiter()], ids=["subcell", "zhangshu"])
+def test_1d_leblanc_gpu(limiter):
+    """Leblanc tube (density ratio 1e3, pressure ratio 1e9; examples/convergence/leblanc-convergence.jl), N=2, K=100: the
+    oracle's state after the first 40 steps, then the GPU run to T = 2/3: positivity and the L1 error against the exact
+    solution through calculate_error (the oracle reaches 0.034 summed over the three components)."""
+    from p2de_b200.api import State, calculate_error
+    from p2de_b200.types import Solver
+    param, Ug, Uo, st, orc = run_both(P.leblanc(N=2, K=100, limiter=limiter), 40)
+    assert rel(Ug, Uo) < 1e-7
+    st.close()
+    prm, rd, md, dd, bc, U0 = P.setup(P.leblanc(N=2, K=100, limiter=limiter))
+    solver = Solver(param=prm, rd=rd, md=md, discrete_data=dd)
+    st = State(solver, bc)
+    st.set_state(U0)
+    tend, dth = st.ssp33_run(prm.timestepping_param.t0)
+    assert abs(tend - prm.timestepping_param.T) < 1e-10 and len(dth) > 1000
+    U = st.preallocation.Uq
+    assert (U[..., 0] > 0).all() and st.reduce(T.REDUCE_MIN_RHOE) > 0
+    err = calculate_error(st, solver, P.leblanc_exact)
+    assert err.L1err < 0.06, err
+    st.close()

@@ -147,7 +147,12 @@ def both_rhs_1d(problem, nstage=1, dt=None):
     assert rel(pre.rhsL, orc.field("rhsL")) < 1e-12
     assert rel(pre.rhsH, orc.field("rhsH")) < 2e-10
     Nq = param.N + 1
-    return pre, orc, pre.L_local[nstage - 1][:, 0, :Nq + 1], orc.field("L_local")[nstage - 1][:, 0, :Nq + 1]
+    # element faces carry f_bar_H - f_bar_L = BF_H - BF_L = rounding noise of the projection round trip; the TVD test
+    # `rho + P < min_stencil rhoL` with P = +-1e-16 is decided by the sign of that noise (see significant_faces above)
+    fH = orc.field("f_bar_H_x").reshape(-1, 2 * Nq, 3)[:, :Nq + 1]
+    fL = orc.field("f_bar_L_x").reshape(-1, 2 * Nq, 3)[:, :Nq + 1]
+    sig = np.abs(fH - fL).max(-1) > 1e-10 * np.abs(fH).max()
+    return pre, orc, pre.L_local[nstage - 1][:, 0, :Nq + 1] * sig, orc.field("L_local")[nstage - 1][:, 0, :Nq + 1] * sig
 
 
 @pytest.mark.parametrize("N", [1, 3])

@@ -44,9 +44,13 @@ WORKLOADS = {
     # data-independence checks of the headline (same mesh and scheme as S-DMR, different data):
     "S-WAVE": dict(problem="wave2d", N=3, K=(4096, 1024), note="plateau-free smooth periodic data (tests/problems.py: wave2d), N=3 LGL, 4096x1024: "
                    "no constant elements, most node pairs off logmean's series branch (logs evaluated everywhere)"),
-    "S-DMR-developed": dict(problem="dmr", N=3, K=(4096, 1024), developed=dict(K=(512, 128), steps=8000, tile=(8, 8)),
-                            note="S-DMR mesh and boundary conditions; initial state = the double-Mach-reflection data advanced 8000 SSP-RK3 steps "
-                                 "on a 512x128 mesh and tiled 8x8 (developed shocks and reflections, tile seams add further discontinuities)"),
+    # (a "developed" double Mach reflection is not available: with the copy-out top boundary the reference's BC surface offers --
+    #  it has neither the wall nor the time-dependent exact-shock condition -- the flow where the oblique shock meets the top
+    #  boundary accelerates without bound, in the oracle as well: max wavespeed 12 -> 100 within 400 steps on 128x32.  The
+    #  long-time shock-dominated case is therefore the Sedov blast, which the reference ships and which stays stable.)
+    "S-SEDOV-developed": dict(problem="sedov", N=3, K=(4096, 1024), developed=dict(K=(512, 128), steps=3000, tile=(8, 8)),
+                              note="Sedov blast (examples/2D/sedov.jl data: background pressure 1e-5) advanced 3000 SSP-RK3 steps on a 512x128 periodic mesh "
+                                   "and tiled 8x8 seamlessly: expanding strong shocks into near-vacuum, the limiter's exact evaluation active along every front"),
     # the configuration of examples/2D/kelvin-helmholtz.jl:44-55: Gauss collocation,
     # NodewiseScaledExtrapolation, LaxFriedrichsOnProjectedVal, subcell positivity limiter
     "S-KH-gauss": dict(problem="kelvin_helmholtz", N=3, K=(2048, 512), gauss=True,
@@ -174,6 +178,8 @@ def developed_state(workload, host_np, device):
         t += st.ssp33_step(t)
     U = st.preallocation.Uq
     st.close()
+    if not (np.isfinite(t) and np.isfinite(U).all() and (U[..., 0] > 0).all()):
+        raise RuntimeError(f"{workload}: the small run did not stay finite / positive (t = {t})")
     kx, ky = dv["K"]; tx, ty = dv["tile"]
     Us = U.reshape(ky, kx, U.shape[1], U.shape[2])
     Kx = kx * tx
@@ -202,7 +208,7 @@ def run_ours(args):
             # the headline data is the reference's prescribed initial condition, which is mostly plateau: the same mesh
             # and scheme on plateau-free and on developed-shock data, with the data-dependent shortcuts counted
             out["extra"] = {}
-            for wl in ("S-WAVE", "S-DMR-developed"):
+            for wl in ("S-WAVE", "S-SEDOV-developed"):
                 try:
                     ex = measure(args, wl, world, rank, local, headline=False)
                     out["extra"][wl] = ex
@@ -302,6 +308,7 @@ def measure(args, workload, world, rank, local, headline):
         # first launches are milliseconds apart, and the early rank's clock would run while it waits for the late one)
         st.ssp33_step_async(t)
         st.profile(True)
+        launches0 = st.kernel_launch_count()
     ev0.record(stream)
     tt = t
     for _ in range(args.steps):

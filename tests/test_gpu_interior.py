@@ -126,3 +126,32 @@ def test_interior_step_keeps_all_three_stage_coefficients():
         assert (np.asarray(Lg[s] == 1.0) != np.asarray(Lo[s] == 1.0)).mean() < 1e-3
     assert (Lo < 1.0).any()
     st.close()
+
+
+def test_tiled_developed_shock_state_steps():
+    """bench.py's tiled "developed" construction at test size: the double-Mach-reflection data advanced on a small mesh, tiled 2x2
+    onto a mesh of twice the extent (strong discontinuities at the tile seams, inflow / outflow boundary conditions), then
+    30 SSP33! steps against the oracle: the limiter's exact evaluation and the non-quiet flux path run on most lines."""
+    from oracle.oracle import Oracle
+    param, rd, md, dd, bc, U0 = P.setup(P.dmr(N=3, K=(64, 16), T=1e9))
+    o = Oracle(param, dd, bc)
+    o.set_state(U0)
+    t = 0.0
+    for _ in range(190):
+        t += o.ssp33_step(t)
+    Us = o.get_state().reshape(16, 64, 16, 4)
+    big = np.ascontiguousarray(np.tile(Us, (2, 2, 1, 1)).reshape(-1, 16, 4))
+    param, solver, st, orc, _ = make_pair(P.dmr(N=3, K=(128, 32), T=1e9), keep_diagnostics=False)
+    st.set_state(big); orc.set_state(big)
+    st.debug_counters(True)
+    t_o = t_g = 0.0
+    for i in range(30):
+        dto = orc.ssp33_step(t_o); t_o += dto
+        dtg = st.ssp33_step(t_g); t_g += dtg
+        assert abs(dtg - dto) <= 1e-9 * dto, (i, dtg, dto)
+    cnt = st.debug_counters(False)
+    Ug, Uo = st.preallocation.Uq, orc.get_state()
+    assert np.isfinite(Ug).all() and (Ug[..., 0] > 0).all()
+    assert rel(Ug, Uo) < 1e-6
+    assert cnt["lines_not_easy"] > 0 and cnt["limiter_slow"] > 0 and cnt["elem_logs"] > 0
+    st.close()

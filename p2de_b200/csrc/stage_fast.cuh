@@ -124,6 +124,37 @@ P2DE_DEV void fS_rot_quiet(double half_inv_gm1, const PrimR &L, const PrimR &R, 
   F[0] = F1; F[1] = fma(F1, unavg, pa); F[2] = F1 * utavg; F[3] = f4aux * unavg;
 }
 
+// The same flux for a pair of an element in which rho and beta each vary by less than ~9 % (the "smooth" vote of the line
+// phase): no logs.  With z = da / (a_L + a_R) (= f / 2 of logmean, :307-321) and t = z^2 <= 3e-3,
+//   log(a_R / a_L) = 2 atanh(z)   =>   logmean = aavg / P(t),   P(t) = 1 + t/3 + t^2/5 + ... + t^6/13   (truncation < 1e-16)
+// for the pairs on the reference's log branch (|f| >= 1e-4); pairs with |f| < 1e-4 keep the reference's own series
+// (:315-317; it is Winters' polytropic mean, not the expansion of the log mean, so the two branches are not interchangeable).
+// The series is accurate to ~4e-16, the reference's -da / (log a_L - log a_R) loses ~1e-16 / |f| to cancellation (3e-12 at
+// |f| = 1e-4); the difference between the two is that noise.
+P2DE_DEV double logmean_series_P(double t) {
+  return fma(t, fma(t, fma(t, fma(t, fma(t, fma(t, 1.0 / 13.0, 1.0 / 11.0), 1.0 / 9.0), 1.0 / 7.0), 1.0 / 5.0), 1.0 / 3.0), 1.0);
+}
+P2DE_DEV void fS_rot_smooth(double half_inv_gm1, const PrimR &L, const PrimR &R, double F[4]) {
+  const double sa = R.rho + L.rho, da = R.rho - L.rho, sb = R.beta + L.beta, db = R.beta - L.beta;
+  const double xa = rcp_fast(sa), y = rcp_fast(sb);    // 1 / (2 aavg), 1 / (2 bavg)
+  const double za = da * xa, zb = db * y, ta = za * za, tb = zb * zb;
+  const bool ser = ta < 2.5e-9, serb = tb < 2.5e-9;    // |f| < 1e-4  <=>  z^2 < 2.5e-9
+  // rho: aavg * (reference series in v = 4 t)  or  aavg / P(t)
+  const double va = 4.0 * ta;
+  const double refa = fma(va, kSeries[0] - va * (kSeries[1] - va * kSeries[2]), 1.0);
+  const double rholog = (0.5 * sa) * (ser ? refa : rcp_fast(logmean_series_P(ta)));
+  // 1 / logmean(beta) = (reference series  or  P(t)) / bavg
+  const double vb = 4.0 * tb;
+  const double refb = fma(vb, fma(vb, kSeries[4], kSeries[3]), 1.0);
+  const double inv_betalog = (2.0 * y) * (serb ? refb : logmean_series_P(tb));
+  const double pa = 0.5 * (sa * y);
+  const double unavg = 0.5 * (L.un + R.un), utavg = 0.5 * (L.ut + R.ut);
+  const double unorm = L.un * R.un + L.ut * R.ut;
+  const double f4aux = fma(0.5 * rholog, unorm, fma(rholog * inv_betalog, half_inv_gm1, pa));
+  const double F1 = rholog * unavg;
+  F[0] = F1; F[1] = fma(F1, unavg, pa); F[2] = F1 * utavg; F[3] = f4aux * unavg;
+}
+
 // run-time indexed access to small per-line arrays inside the (rolled, rarely executed) exact limiter loop: a select chain
 // keeps the arrays in registers
 template <int NF>

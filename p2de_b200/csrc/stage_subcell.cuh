@@ -44,6 +44,9 @@ P2DE_DEV Cons2 load_cons_plus(const double *pu, const double *pw, double theta) 
 #ifndef P2DE_SUB_MIN_BLOCKS
 #define P2DE_SUB_MIN_BLOCKS 4
 #endif
+#ifndef P2DE_SUB_SMOOTH_PAIRS
+#define P2DE_SUB_SMOOTH_PAIRS 1   // warps whose elements vary by less than ~9 %: log-free two-point flux (series of the log mean)
+#endif
 #ifndef P2DE_SUB_MIN_BLOCKS_S23
 #define P2DE_SUB_MIN_BLOCKS_S23 P2DE_SUB_MIN_BLOCKS   // stages 2, 3 (their shared memory allows a fifth CTA per SM)
 #endif
@@ -293,20 +296,26 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
   // Quiet vote: if rho and beta each stay within 32 units of 2^-20 (high words) of the element's node (0, 0), they vary
   // by less than 6.2e-5 relative over the element and no pair can leave logmean's series branch (|f| < 1e-4, :307-321):
   // the pairs then take fS_rot_quiet and no log is evaluated.  Decided per warp (8 elements), all lanes voting.
-  bool quiet = false;
+  bool quiet = false, smooth = false;
   if (QUIET_PATH) {
     const int h0r = __double2hiint(q[0].rho), h0b = __double2hiint(q[0].beta);
     const int lead = (tid & 31) & ~(N1D - 1);      // the element's thread with line 0: its node a = 0 is node (0, 0)
     const int rr0 = __shfl_sync(0xffffffffu, h0r, lead), rb0 = __shfl_sync(0xffffffffu, h0b, lead);
-    bool far = false;
+    // second threshold ("smooth"): within 0x6000 units of node (0, 0), i.e. any two nodes differ by less than 9.4 %, so
+    // |z| = |da| / (a_L + a_R) < 0.05 for every pair and fS_rot_smooth's series applies (no logs either)
+    bool far = false, far2 = false;
 #pragma unroll
-    for (int a = 0; a < N1D; ++a)
-      far = far | ((unsigned)(__double2hiint(q[a].rho) - rr0 + 32) > 64u) | ((unsigned)(__double2hiint(q[a].beta) - rb0 + 32) > 64u);
+    for (int a = 0; a < N1D; ++a) {
+      const int er = __double2hiint(q[a].rho) - rr0, eb = __double2hiint(q[a].beta) - rb0;
+      far = far | ((unsigned)(er + 32) > 64u) | ((unsigned)(eb + 32) > 64u);
+      far2 = far2 | ((unsigned)(er + 0x6000) > 0xC000u) | ((unsigned)(eb + 0x6000) > 0xC000u);
+    }
     const unsigned fm = __ballot_sync(0xffffffffu, far);
     quiet = fm == 0u;
+    smooth = P2DE_SUB_SMOOTH_PAIRS && !quiet && __ballot_sync(0xffffffffu, far2) == 0u;
     if (A.dbg && d == 0 && line == 0 && active) {
       atomicAdd(A.dbg + DBG_ELEM, 1ull);
-      if (!quiet) atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull);
+      if (!quiet && !smooth) atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull);
     }
   } else if (A.dbg && d == 0 && line == 0 && active) { atomicAdd(A.dbg + DBG_ELEM, 1ull); atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull); }
   if (quiet) {
@@ -314,6 +323,15 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
       constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
       double F[4];
       fS_rot_quiet(A.half_inv_gm1, q[i], q[j], F);
+      const double Sv = T.SHt[d][i][j][line];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }
+    });
+  } else if (smooth) {
+    PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
+      constexpr int j = decltype(jc)::value, i = decltype(ic)::value;
+      double F[4];
+      fS_rot_smooth(A.half_inv_gm1, q[i], q[j], F);
       const double Sv = T.SHt[d][i][j][line];
 #pragma unroll
       for (int c = 0; c < 4; ++c) { G[i][c] = fma(-Sv, F[c], G[i][c]); G[j][c] = fma(Sv, F[c], G[j][c]); }

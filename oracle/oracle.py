@@ -18,7 +18,8 @@ from p2de_b200.abi import BCDataC, Config, GeometryC, OperatorsC, PackedProblem 
 
 _LIBS = {}
 _DEFAULT = "ref"
-_SO = {"ref": "libp2de_oracle.so", "native": "libp2de_oracle_native.so", "fma": "libp2de_oracle_fma.so"}
+_SO = {"ref": "libp2de_oracle.so", "native": "libp2de_oracle_native.so", "fma": "libp2de_oracle_fma.so",
+       "series": "libp2de_oracle_series.so"}
 
 
 def build(force: bool = False, variant: str = "ref") -> str:
@@ -26,6 +27,8 @@ def build(force: bool = False, variant: str = "ref") -> str:
     "ref"    portable -O2, -ffp-contract=off: THE checker (Julia does not contract a*b+c);
     "fma"    same source with -ffp-contract=fast -mfma: a legal re-association of the same formulas, used by tests to
              measure how far the reference formulation itself moves under rounding (tolerance probe);
+    "series" the portable build with logmean's log branch evaluated by a cancellation-free series where it converges:
+             second tolerance probe (how much of a difference is the rounding noise of -da / (log aL - log aR) itself);
     "native" -O3 -march=native, -ffp-contract=off: bench.py's CPU arm, compiled on the machine that runs it."""
     so = os.path.join(_HERE, _SO[variant])
     src = os.path.join(_HERE, "p2de_oracle.cpp")

@@ -141,6 +141,19 @@ struct Phys {
     double da = aR - aL, aavg = 0.5 * (aR + aL);
     double f = da / aavg, v = f * f;
     if (std::fabs(f) < 1e-4) return aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857)));
+#ifdef P2DE_ORACLE_LOGMEAN_SERIES
+    // TOLERANCE PROBE ONLY (libp2de_oracle_series.so, oracle/Makefile): the same mean without the cancellation of
+    // log(aL) - log(aR): log(aR / aL) = 2 atanh(z), z = da / (aL + aR), so logmean = aavg / (1 + z^2/3 + z^4/5 + ...).
+    // For |z| < 0.055 the truncated series is exact to ~4e-16, while the line below loses ~1e-16 / |f|.  The difference
+    // between the two builds is the reference formulation's own rounding noise.
+    {
+      double z = da / (aR + aL), t = z * z;
+      if (t < 3.0e-3) {
+        double Pt = 1.0 + t * (1.0 / 3.0 + t * (1.0 / 5.0 + t * (1.0 / 7.0 + t * (1.0 / 9.0 + t * (1.0 / 11.0 + t * (1.0 / 13.0))))));
+        return aavg / Pt;
+      }
+    }
+#endif
     return -da / (logL - logR);
   }
   // :196-249

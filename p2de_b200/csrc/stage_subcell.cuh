@@ -76,8 +76,6 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
   // A-form exchange (see the header): the limiter's dt multiplies everything the kernel writes
   constexpr bool AFORM = KIND == KIND_S23 || KIND == KIND_S1;
   constexpr bool DIAG = KIND == KIND_RT;
-  // quiet vote: an element's N1D line threads of one direction are adjacent lanes of one warp
-  constexpr bool QUIET_PATH = N1D == 4 && HALF % 32 == 0;
   extern __shared__ double sm[];
   Tables2D<N1D> &T = *reinterpret_cast<Tables2D<N1D> *>(sm);
   double *nodes = sm + TBL;                                            // [4][S] rho, m1, m2, E at swizzled positions
@@ -293,31 +291,30 @@ __device__ __forceinline__ void stage_subcell_impl(const StageArgs &A, const Mes
     publish(N1D - 1, Uc, GLc, Fc1, Gadj1, true, (lam_prev + 0.0) + lamF1);
   }
   // ---- flux differencing along this line, flux_differencing.jl:164-211 (pairs j<i, j outer).
-  // Quiet vote: if rho and beta each stay within 32 units of 2^-20 (high words) of the element's node (0, 0), they vary
-  // by less than 6.2e-5 relative over the element and no pair can leave logmean's series branch (|f| < 1e-4, :307-321):
-  // the pairs then take fS_rot_quiet and no log is evaluated.  Decided per warp (8 elements), all lanes voting.
+  // Which form of the two-point flux the line's pairs need is decided from the line's own nodes (its pairs are all it
+  // evaluates): if rho and beta each stay within 32 units of 2^-20 (high words) of the line's first node they vary by less
+  // than 6.2e-5 relative and no pair can leave logmean's series branch (|f| < 1e-4, :307-321): "quiet", fS_rot_quiet; within
+  // 0x6000 units any two nodes differ by less than 9.4 %, so |z| = |da| / (a_L + a_R) < 0.05 for every pair and the series
+  // of fS_rot_smooth applies: "smooth".  Neither evaluates a log.  The choice is made per warp (all its lanes vote), so
+  // the three variants never diverge inside a warp.
   bool quiet = false, smooth = false;
-  if (QUIET_PATH) {
-    const int h0r = __double2hiint(q[0].rho), h0b = __double2hiint(q[0].beta);
-    const int lead = (tid & 31) & ~(N1D - 1);      // the element's thread with line 0: its node a = 0 is node (0, 0)
-    const int rr0 = __shfl_sync(0xffffffffu, h0r, lead), rb0 = __shfl_sync(0xffffffffu, h0b, lead);
-    // second threshold ("smooth"): within 0x6000 units of node (0, 0), i.e. any two nodes differ by less than 9.4 %, so
-    // |z| = |da| / (a_L + a_R) < 0.05 for every pair and fS_rot_smooth's series applies (no logs either)
+  {
+    const int rr0 = __double2hiint(q[0].rho), rb0 = __double2hiint(q[0].beta);
     bool far = false, far2 = false;
 #pragma unroll
-    for (int a = 0; a < N1D; ++a) {
+    for (int a = 1; a < N1D; ++a) {
       const int er = __double2hiint(q[a].rho) - rr0, eb = __double2hiint(q[a].beta) - rb0;
       far = far | ((unsigned)(er + 32) > 64u) | ((unsigned)(eb + 32) > 64u);
       far2 = far2 | ((unsigned)(er + 0x6000) > 0xC000u) | ((unsigned)(eb + 0x6000) > 0xC000u);
     }
-    const unsigned fm = __ballot_sync(0xffffffffu, far);
-    quiet = fm == 0u;
-    smooth = P2DE_SUB_SMOOTH_PAIRS && !quiet && __ballot_sync(0xffffffffu, far2) == 0u;
+    const unsigned am = __activemask();   // (the CTA's last warp may be partial when 2 N1D EPB is not a multiple of 32)
+    quiet = P2DE_FAST_QUIET_PAIRS && __ballot_sync(am, far) == 0u;
+    smooth = P2DE_SUB_SMOOTH_PAIRS && !quiet && __ballot_sync(am, far2) == 0u;
     if (A.dbg && d == 0 && line == 0 && active) {
       atomicAdd(A.dbg + DBG_ELEM, 1ull);
       if (!quiet && !smooth) atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull);
     }
-  } else if (A.dbg && d == 0 && line == 0 && active) { atomicAdd(A.dbg + DBG_ELEM, 1ull); atomicAdd(A.dbg + DBG_ELEM_LOGS, 1ull); }
+  }
   if (quiet) {
     PairLoop<N1D, 0, 1>::run([&](auto jc, auto ic) {
       constexpr int j = decltype(jc)::value, i = decltype(ic)::value;

@@ -392,13 +392,18 @@ def measure(args, workload, world, rank, local, headline):
                 "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd, "counters": counters,
                 "between_launches_ms_per_step": gap_ms / args.steps,
                 "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}
+    tr("e2e serial")
     e2e_loop([st], [stream], [host], 2)
-    initial_state(param, rd, ic, host.numpy())
+    if not w.get("developed"):
+        initial_state(param, rd, ic, host.numpy())
     serial_ms = timed_e2e([st], [stream], [host], e2e_steps)
+    tr("e2e serial done")
     # two more handles + streams + pinned buffers for the pipelined variant (one job = ~2 copy times + 1 compute
     # time on its own stream, so three jobs in flight keep both copy directions busy)
     states, streams, hosts = [st], [stream], [host]
-    for _ in range(2):
+    # (single GPU only: with several ranks the three handles would be three NCCL communicators working concurrently on
+    #  different streams, whose kernels the GPUs may start in different orders -- a known way to deadlock NCCL)
+    for _ in range(2 if world == 1 else 0):
         sx = torch.cuda.Stream()
         s2 = State(solver, bc, device=local, structured_bc=periodic)
         s2.set_stream(sx.cuda_stream)
@@ -411,12 +416,16 @@ def measure(args, workload, world, rank, local, headline):
         h2 = torch.empty_like(host).pin_memory()
         h2.copy_(host)
         states.append(s2); streams.append(sx); hosts.append(h2)
-    e2e_loop(states, streams, hosts, 3)
-    torch.cuda.synchronize()
-    for hx in hosts[:-1]:
-        hx.copy_(hosts[-1])
-    e2e_ms = timed_e2e(states, streams, hosts, e2e_steps)
-    e2e_value = 3.0 * dof_per_stage * e2e_steps / (e2e_ms * 1e-3)
+    if world == 1:
+        e2e_loop(states, streams, hosts, 3)
+        torch.cuda.synchronize()
+        for hx in hosts[:-1]:
+            hx.copy_(hosts[-1])
+        e2e_ms = timed_e2e(states, streams, hosts, e2e_steps)
+        e2e_value = 3.0 * dof_per_stage * e2e_steps / (e2e_ms * 1e-3)
+    else:
+        e2e_ms, e2e_value = None, None
+    tr("e2e done")
     serial_value = 3.0 * dof_per_stage * e2e_steps / (serial_ms * 1e-3)
     for s2 in states[1:]:
         s2.close()
@@ -473,7 +482,7 @@ def measure(args, workload, world, rank, local, headline):
         "e2e": {"value": serial_value, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                 "steps": e2e_steps, "ms_per_step": serial_ms / e2e_steps,
                 "mode": "serial: one handle, one stream, copy in -> 3 stages -> copy out per step",
-                "pipelined_value": e2e_value, "pipelined_ms_per_step": e2e_ms / e2e_steps,
+                "pipelined_value": e2e_value, "pipelined_ms_per_step": (e2e_ms / e2e_steps) if e2e_ms else None,
                 "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others"},
         "gpu_launches": int(launches), "clocks": clocks, "counters": counters,
         "between_launches_ms_per_step": gap_ms / args.steps,

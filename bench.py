@@ -326,10 +326,19 @@ def measure(args, workload, world, rank, local, headline):
     gap_ms, n_gap = st.profile_get(100)       # device time between consecutive hot-path launches (exchanges, collectives, bubbles)
     st.profile(False)
     clocks = sampler.stop()
+    per_rank = None
     if world > 1:
         tm = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         ms = float(tm.item())
+        # every rank's own kernel time and its waiting time: the ranks run in lock step (three exchanges and one
+        # all-reduce per step), so the slowest GPU of the box sets the pace and the others' waiting shows up between launches
+        mine = torch.tensor([stage_ms / (3.0 * args.steps), gap_ms / args.steps],
+                            dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"stage_kernels_ms_per_stage": [round(float(a[0]), 4) for a in allr],
+                    "between_launches_ms_per_step": [round(float(a[1]), 4) for a in allr]}
     dof_per_stage = sz.K * sz.Nq * world
     value = 3.0 * dof_per_stage * args.steps / (ms * 1e-3)
     # data-dependent shortcuts taken, counted by the kernels themselves during one more (untimed) step
@@ -390,7 +399,7 @@ def measure(args, workload, world, rank, local, headline):
     if args.no_e2e:      # kernel A/B runs only (tools/ab_variants.sh): not a bench line the driver reads
         return {"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
                 "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd, "counters": counters,
-                "between_launches_ms_per_step": gap_ms / args.steps,
+                "between_launches_ms_per_step": gap_ms / args.steps, "per_rank": per_rank,
                 "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}
     tr("e2e serial")
     e2e_loop([st], [stream], [host], 2)
@@ -485,7 +494,7 @@ def measure(args, workload, world, rank, local, headline):
                 "pipelined_value": e2e_value, "pipelined_ms_per_step": (e2e_ms / e2e_steps) if e2e_ms else None,
                 "pipelining": "3 handles on 3 streams used in turn: the H2D / D2H copies of one step overlap the compute and copies of the others"},
         "gpu_launches": int(launches), "clocks": clocks, "counters": counters,
-        "between_launches_ms_per_step": gap_ms / args.steps,
+        "between_launches_ms_per_step": gap_ms / args.steps, "per_rank": per_rank,
         "source_hash": source_hash(),
     }
     if world > 1 and not args.no_multi_gpu_check:

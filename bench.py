@@ -353,13 +353,16 @@ def measure(args, workload, world, rank, local, headline):
                         "interior_cta_frac": c["cta_interior"] / max(c["cta_interior"] + c["cta_general"], 1), "raw": c}
     peak, peak_src = peaks()
     A = algorithmic_bytes_per_dof(param.N, param.rhs_limiter.code)
-    stage_total_ms = (stage_ms + upd_ms + proj_ms) / max(n_stage, 1)          # all kernels of one stage, device time
+    # all kernels of one RK stage, device time (per RK stage, not per launch: with several ranks a stage is two row-range
+    # launches of the same kernel, boundary rows first)
+    n_rk = 3 * args.steps
+    stage_total_ms = (stage_ms + upd_ms + proj_ms) / n_rk
     achieved = A * sz.K * sz.Nq / (stage_total_ms * 1e-3) / 1e9 if n_stage else None
     if not headline:
         mr, mre = st.reduce(1), st.reduce(2)
         st.close()
         del host
-        return {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
+        return {"value": value, "unit": UNIT, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / n_rk,
                 "roofline_frac": (achieved / peak) if achieved else None, "gpu_launches": int(launches), "counters": counters,
                 "description": w["note"], "developed": dev_info, "min_rho": mr, "min_rhoe": mre}
 
@@ -397,7 +400,7 @@ def measure(args, workload, world, rank, local, headline):
 
     e2e_steps = max(3, min(args.steps, 9))
     if args.no_e2e:      # kernel A/B runs only (tools/ab_variants.sh): not a bench line the driver reads
-        return {"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / max(n_stage, 1),
+        return {"value": value, "ms_per_step": ms / args.steps, "stage_kernel_ms": stage_ms / n_rk,
                 "update_kernel_ms": upd_ms / max(n_upd, 1), "n_stage": n_stage, "n_upd": n_upd, "counters": counters,
                 "between_launches_ms_per_step": gap_ms / args.steps, "per_rank": per_rank,
                 "gpu_launches": int(launches), "clocks": clocks, "lib": os.environ.get("P2DE_B200_LIB", "in-tree")}
@@ -470,20 +473,21 @@ def measure(args, workload, world, rank, local, headline):
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
                      "traffic_note": traffic_note,
                      "kernel": "all kernels of one RK stage (subcell family: one stage_subcell_s1/s2/s3 launch; generic path: + projection / update kernels)", "algorithmic_bytes_per_dof_update": A,
-                     "stage_kernel_ms": stage_ms / max(n_stage, 1), "update_kernel_ms": upd_ms / max(n_upd, 1),
+                     "stage_kernel_ms": stage_ms / n_rk, "stage_kernel_launches_per_stage": n_stage / n_rk,
+                     "update_kernel_ms": upd_ms / max(n_upd, 1),
                      "stage_kernel_share": stage_ms / max(stage_ms + upd_ms + proj_ms, 1e-30),
                      "projection_kernel_ms": (proj_ms / n_proj) if n_proj else None},
         # second view of the same stage: the stage kernel is bound by the FP64 CUDA-core pipe, not by HBM.
         # flops per DOF-update counted by ncu (DFMA = 2), peak = DFMA micro-benchmark on this GPU type
         # (tools/fp64_peak.cu, profiles/r1_fp64_peak.json)
         "roofline_fp64": ({"bound": "fp64", "unit": "TFLOP/s",
-                           "achieved": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3) / 1e12,
+                           "achieved": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / n_rk * 1e-3) / 1e12,
                            "peak": fp64_peak["dfma_tflops"],
-                           "frac": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3) / 1e12 / fp64_peak["dfma_tflops"],
-                           "pipe_frac": fp64["lane_ops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / max(n_stage, 1) * 1e-3)
+                           "frac": fp64["flops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / n_rk * 1e-3) / 1e12 / fp64_peak["dfma_tflops"],
+                           "pipe_frac": fp64["lane_ops_per_dof_update"] * sz.K * sz.Nq / (stage_ms / n_rk * 1e-3)
                                         / (fp64_peak["dadd_per_clk_sm"] * fp64_peak["sms"] * fp64_peak["clock_mhz"] * 1e6),
                            "kernel": "stage_subcell_s1/s2/s3", "flops_per_dof_update": fp64["flops_per_dof_update"],
-                           "source": "ncu thread-instruction counts (profiles/r1_traffic.json) and tools/fp64_peak.cu (profiles/r1_fp64_peak.json)"}
+                           "source": "ncu thread-instruction counts (profiles/r2_traffic.json) and tools/fp64_peak.cu (profiles/r1_fp64_peak.json)"}
                           if (fp64 and fp64_peak and n_stage) else None),
         # headline e2e = ONE handle on ONE stream: host->device copy of the state, the step, device->host copy, strictly in
         # sequence like a time loop that needs step n's output before step n+1 (PCIe-bound: 4.3 GB per step).  The pipelined

@@ -10,7 +10,11 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libp2de_b200.so")
 SOURCES = ["capi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-split-compile", "0",   # the kernels of the one translation unit are compiled in parallel (same code, 2.5x faster build)
+              # ptxas compiles the kernels of the one translation unit in parallel.  NOT nvcc's own `-split-compile 0`: that also
+              # splits the NVVM optimiser (cicc), whose output for this file is then not reproducible -- the same command gives one
+              # of two different PTX files from run to run (different inlining / unswitching, 24..144 B of stack in the stage
+              # kernels); with cicc unsplit the PTX and the SASS of every kernel are identical across builds.
+              "-Xptxas", "-split-compile=0",
               "-diag-suppress", "177",
               "-Xcompiler", "-fPIC", "-shared", "-ldl"]
 

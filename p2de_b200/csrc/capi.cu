@@ -767,6 +767,7 @@ int build_tables1d(p2de_handle *h, const p2de_operators *o) {
     if (T.fq2q[f] < 0 || T.fq2q[f] >= Nq) return fail(h, P2DE_ERR_ARG, "fq2q[%d] out of range", f);
     for (int j = 0; j < Nq; ++j) {
       T.Vf[f][j] = o->Vf[f + (size_t)j * 2];
+      T.Vf_low[f][j] = o->Vf_low ? o->Vf_low[f + (size_t)j * 2] : (j == T.fq2q[f] ? 1.0 : 0.0);
       if (T.Vf[f][j] != (j == T.fq2q[f] ? 1.0 : 0.0)) gather = false;
     }
   }
@@ -813,12 +814,16 @@ int run_stage_1d(p2de_handle *h, const double *Uin, int nstage, double dt_host, 
   A.hennemann = h->cfg.shockcapture == P2DE_SHOCKCAPTURE_HENNEMANN; A.N = h->cfg.N;
   A.hen_a = h->cfg.hennemann_a; A.hen_c = h->cfg.hennemann_c; A.bound_beta = h->cfg.bound_beta;
   A.VDM_inv = h->VDM_inv; A.smin_dev = reinterpret_cast<const double *>(h->smin_bits);
+  A.nodewise = h->nodewise ? 1 : 0; A.gauss = h->cfg.basis == P2DE_BASIS_GAUSS; A.eta = h->cfg.eta;
+  A.theta_local = h->nodewise ? h->theta_local_dev + (size_t)h->K * 2 * (nstage - 1) : nullptr;
+  A.theta = h->nodewise ? h->theta_dev + (size_t)h->K * (nstage - 1) : nullptr;
   if (h->tvd) {
     // TVD bounds (subcell.jl:86-110): rho + dt rhsL[1] of the stencil nodes across the element faces needs the neighbours'
     // finished low-order rhs: a MODE_LOW pre-pass of the same kernel writes it for all elements
     Args1D P = A;
     P.mode = MODE_LOW; P.rhsU = h->rhsLpre; P.nstage = 2;   // nstage != 1: no CFL reduction in the pre-pass
     P.rhsH_diag = nullptr; P.rhsL_diag = nullptr; P.tvd = 0; P.entropy_bound = 0; P.cell_entropy = 0; P.hennemann = 0;
+    P.theta_local = nullptr; P.theta = nullptr;
     Upd1D none{};
     int rc = 0;
     switch (h->N1D) {
@@ -850,7 +855,6 @@ int run_stage_1d(p2de_handle *h, const double *Uin, int nstage, double dt_host, 
 int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *geom, const p2de_bcdata *bc) {
   const int N1D = h->N1D, Nq = h->Nq;
   const long long K = h->K;
-  if (h->cfg.proj_limiter != P2DE_PROJLIM_NONE) return fail(h, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation (SURVEY.md 8f-1)");
   if (geom->uniform) { h->Jq = geom->J_const; h->Jcons = geom->J_const; h->rxJ1 = geom->GJ_const[0]; }
   else {
     if (!geom->Jq || !geom->GJh[0]) return fail(h, P2DE_ERR_ARG, "geometry arrays missing");
@@ -911,6 +915,13 @@ int create_1d(p2de_handle *h, const p2de_operators *ops, const p2de_geometry *ge
   if (h->cfg.keep_diagnostics) {
     if ((rc = dev_alloc(h, &h->rhsH_diag, nU)) || (rc = dev_alloc(h, &h->rhsL_diag, nU))) return rc;
     CU(h, cudaMemset(h->rhsH_diag, 0, nU * sizeof(double))); CU(h, cudaMemset(h->rhsL_diag, 0, nU * sizeof(double)));
+  }
+  if (h->nodewise) {   // theta_local [Ns][K][2], theta [Ns][K]: zeros until a stage writes its slot (init.jl:22-23)
+    if (h->cfg.basis == P2DE_BASIS_GAUSS && !ops->Vf_low) return fail(h, P2DE_ERR_ARG, "NodewiseScaledExtrapolation needs ops.Vf_low");
+    const size_t nth = (size_t)K * 2 * h->Ns, nt = (size_t)K * h->Ns;
+    if ((rc = dev_alloc(h, &h->theta_local_dev, nth)) || (rc = dev_alloc(h, &h->theta_dev, nt))) return rc;
+    CU(h, cudaMemset(h->theta_local_dev, 0, nth * sizeof(double)));
+    CU(h, cudaMemset(h->theta_dev, 0, nt * sizeof(double)));
   }
   h->fast = false;
   return 0;
@@ -1283,7 +1294,6 @@ int32_t p2de_create(const p2de_config *cfg, const p2de_operators *ops, const p2d
          : (cfg->Nq != N1D * N1D || cfg->Nfp != 4 * N1D || cfg->Nh != cfg->Nq + cfg->Nfp || cfg->Np != cfg->Nq))
     return fail(nullptr, P2DE_ERR_ARG, "sizes inconsistent with a degree-%d %s", cfg->N, d1 ? "line" : "quad");
   if (cfg->K <= 0) return fail(nullptr, P2DE_ERR_ARG, "K must be positive");
-  if (d1 && cfg->proj_limiter != P2DE_PROJLIM_NONE) return fail(nullptr, P2DE_ERR_UNSUPPORTED, "NodewiseScaledExtrapolation: 2D only in this build (SURVEY.md 8f-1)");
   if (cfg->shockcapture != P2DE_SHOCKCAPTURE_NONE && !ops->VDM_inv)
     return fail(nullptr, P2DE_ERR_UNSUPPORTED, "HennemannShockCapture needs ops.VDM_inv");
   int mode;

@@ -27,6 +27,7 @@ struct Tables1D {
   double S0[Nq][Nq];      // low-order S0
   double Br[2];
   double Vf[2][Nq];
+  double Vf_low[2][Nq];   // nearest-node gather (init.jl:181-213); blended with Vf by NodewiseScaledExtrapolation
   double MinvVhT[Nq][Nh];
   double MinvVfT[Nq][2];
   double wq[Nq];
@@ -58,6 +59,10 @@ struct Args1D {
   double hen_a, hen_c, bound_beta;
   const double *VDM_inv;             // [Np, Nq] column-major
   const double *smin_dev;            // global minimum of s_modified at t0
+  // NodewiseScaledExtrapolation (filter.jl:6-130): theta per face node, this stage's slots [K][2] / [K] (null: not stored)
+  int nodewise, gauss;
+  double eta;
+  double *theta_local, *theta;
 };
 
 struct Upd1D {
@@ -165,18 +170,57 @@ P2DE_DEV double find_alpha1(double POSTOL, const Cons1 &ui, const Cons1 &ut) {  
 
 P2DE_DEV Cons1 load1(const double *p) { Cons1 U; U.rho = p[0]; U.m = p[1]; U.E = p[2]; return U; }
 
-// entropy-projected state of element `Uel` at face f (rhs.jl:84-94, theta = 1)
+// entropy-projected state of element `Uel` at face f (rhs.jl:84-94): u(sum_j (th Vf + (1 - th) Vf_low)[f][j] v_j); th = 1
+// without NodewiseScaledExtrapolation
 template <int N1D>
-P2DE_DEV Cons1 project_face(const Tables1D<N1D> &T, double gamma, double gm1, int roundtrip, const Cons1 Uel[N1D], int f) {
+P2DE_DEV Cons1 project_face(const Tables1D<N1D> &T, double gamma, double gm1, int roundtrip, const Cons1 Uel[N1D], int f,
+                            int nodewise = 0, double th = 1.0) {
   if (T.vf_is_gather && !roundtrip) return Uel[T.fq2q[f]];
   double acc[3] = {0.0, 0.0, 0.0};
   for (int j = 0; j < N1D; ++j) {
     double V[3];
     v_of_u1(gamma, gm1, Uel[j], V);
-    double w = T.Vf[f][j];
+    double w = nodewise ? th * T.Vf[f][j] + (1 - th) * T.Vf_low[f][j] : T.Vf[f][j];
     acc[0] += w * V[0]; acc[1] += w * V[1]; acc[2] += w * V[2];
   }
   return u_of_v1(gamma, gm1, acc);
+}
+
+// compute_entropyproj_limiting_param!(::GaussCollocation) for one face node (filter.jl:6-15,26-58): the largest theta in
+// [0, 1] (1, or the valid end of 21 bisection steps, nonlinear_solvers.jl:3-20) whose blended extrapolation of the entropy
+// variables keeps v3, rho and rho e inside the bounds relative to the plain extrapolation (check_bound_on_face_node :84-98,
+// update_limited_entropyproj_vars_on_face_node! :110-130)
+template <int N1D>
+P2DE_DEV double theta_face1(const Tables1D<N1D> &T, double gamma, double gm1, double POSTOL, double zeta, double eta,
+                            const Cons1 Uel[N1D], int f) {
+  double V[N1D][3], Uf[3] = {0.0, 0.0, 0.0}, VUf[3] = {0.0, 0.0, 0.0};
+  for (int j = 0; j < N1D; ++j) {
+    v_of_u1(gamma, gm1, Uel[j], V[j]);
+    const double w = T.Vf[f][j];
+    Uf[0] += w * Uel[j].rho; Uf[1] += w * Uel[j].m; Uf[2] += w * Uel[j].E;
+    VUf[0] += w * V[j][0]; VUf[1] += w * V[j][1]; VUf[2] += w * V[j][2];
+  }
+  Cons1 Ufc; Ufc.rho = Uf[0]; Ufc.m = Uf[1]; Ufc.E = Uf[2];
+  const double rhoef = rhoe1(Ufc);
+  auto ok = [&](double th) {
+    double vt[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < N1D; ++j) {
+      const double w = th * T.Vf[f][j] + (1 - th) * T.Vf_low[f][j];
+      vt[0] += w * V[j][0]; vt[1] += w * V[j][1]; vt[2] += w * V[j][2];
+    }
+    if (!(vt[2] < -POSTOL)) return false;
+    const Cons1 ut = u_of_v1(gamma, gm1, vt);
+    const double rhoe = rhoe1(ut);
+    return vt[2] < jl_min(zeta * VUf[2], -POSTOL) && ut.rho > jl_max((1 - eta) * Uf[0], POSTOL) && ut.rho < (1 + eta) * Uf[0] &&
+           rhoe > jl_max((1 - eta) * rhoef, POSTOL) && rhoe < (1 + eta) * rhoef;
+  };
+  if (ok(1.0)) return 1.0;
+  double x_valid = 0.0, x_invalid = 1.0;
+  for (int it = 0; it <= 20; ++it) {
+    const double x_new = 0.5 * (x_valid + x_invalid);
+    if (ok(x_new)) x_valid = x_new; else x_invalid = x_new;
+  }
+  return x_valid;
 }
 
 template <int N1D>
@@ -195,18 +239,31 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
     int bc[2];
     const double *ival[2];
     long long kPs[2]; int nodeP[2];      // low-order stencil across the faces (limiter_utils.jl:184-207): partner element / node
+    // NodewiseScaledExtrapolation: theta of the own faces and (recomputed from the neighbour's nodes with the same arithmetic,
+    // hence the same bits as the neighbour's own value) of the partner faces; Lobatto: 1 (filter.jl:18-20)
+    const bool nw = A.nodewise && A.gauss;
+    double th[2] = {1.0, 1.0};
     for (int f = 0; f < 2; ++f) {
       int m = A.mapP32[k * 2 + f];
       long long kP = m / 2; int fP = m % 2;
       kPs[f] = kP; nodeP[f] = T.fq2q[fP];
       Cons1 Unb[Nq];
       for (int i = 0; i < Nq; ++i) Unb[i] = load1(A.Uq + (kP * Nq + i) * 3);
-      ut[f] = project_face<N1D>(T, gamma, gm1, A.roundtrip, U, f);
-      utP[f] = project_face<N1D>(T, gamma, gm1, A.roundtrip, Unb, fP);
+      double thP = 1.0;
+      if (nw) {
+        th[f] = theta_face1<N1D>(T, gamma, gm1, A.POSTOL, A.zeta, A.eta, U, f);
+        thP = theta_face1<N1D>(T, gamma, gm1, A.POSTOL, A.zeta, A.eta, Unb, fP);
+      }
+      ut[f] = project_face<N1D>(T, gamma, gm1, A.roundtrip, U, f, nw, th[f]);
+      utP[f] = project_face<N1D>(T, gamma, gm1, A.roundtrip, Unb, fP, nw, thP);
       UnodeP[f] = Unb[T.fq2q[fP]];
       int fl = A.bcflag ? A.bcflag[k * 2 + f] : 0;
       bc[f] = fl > 0 ? 1 : (fl < 0 ? 2 : 0);
       ival[f] = fl > 0 ? A.Ival + 3ll * (fl - 1) : nullptr;
+    }
+    if (A.nodewise && A.theta_local) {
+      A.theta_local[k * 2 + 0] = th[0]; A.theta_local[k * 2 + 1] = th[1];
+      if (A.gauss && A.theta) A.theta[k] = ((0.0 + th[0]) + th[1]) / 2;   // filter.jl:57 (the Lobatto method never writes theta)
     }
     double rL[Nq][3], rH[Nq][3], BFL[2][3], BFH[2][3];
     for (int i = 0; i < Nq; ++i) for (int c = 0; c < 3; ++c) { rL[i][c] = 0.0; rH[i][c] = 0.0; }
@@ -292,11 +349,23 @@ stage1d_kernel(const Args1D A, const Tables1D<N1D> T) {
         const double uf[3] = {ut[f].rho, ut[f].m, ut[f].E}, up[3] = {uP.rho, uP.m, uP.E};
         for (int c = 0; c < 3; ++c) BFH[f][c] = B * fs[c] - LFc * (up[c] - uf[c]);
       }
+      // assemble_rhs! (flux_differencing.jl:274-361); an element with some theta < 1 lifts with the limited face matrix
+      // Vf_new = theta Vf + (1 - theta) Vf_low: M^-1 Vh^T -> (1/wq) [I Vf_new^T], M^-1 Vf^T -> (1/wq) Vf_new^T (:288-319)
+      const bool limited = nw && jl_min(th[0], th[1]) < 1.0;
       for (int i = 0; i < Nq; ++i)
         for (int c = 0; c < 3; ++c) {
           double a = 0.0, b = 0.0;
-          for (int h = 0; h < Nh; ++h) a += T.MinvVhT[i][h] * QF[h][c];
-          for (int f = 0; f < 2; ++f) b += T.MinvVfT[i][f] * BFH[f][c];
+          if (!limited) {
+            for (int h = 0; h < Nh; ++h) a += T.MinvVhT[i][h] * QF[h][c];
+            for (int f = 0; f < 2; ++f) b += T.MinvVfT[i][f] * BFH[f][c];
+          } else {
+            for (int h = 0; h < Nh; ++h) {
+              const double vht = h < Nq ? (h == i ? 1.0 : 0.0)
+                                        : th[h - Nq] * T.Vf[h - Nq][i] + (1 - th[h - Nq]) * T.Vf_low[h - Nq][i];
+              a += ((1 / T.wq[i]) * vht) * QF[h][c];
+            }
+            for (int f = 0; f < 2; ++f) b += ((1 / T.wq[i]) * (th[f] * T.Vf[f][i] + (1 - th[f]) * T.Vf_low[f][i])) * BFH[f][c];
+          }
           rH[i][c] = -(a + b) / A.Jq;
         }
     }

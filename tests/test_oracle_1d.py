@@ -58,3 +58,29 @@ def test_1d_periodic_conservation_and_symmetric_coefficients():
     L = orc.field("L_local")[2][:, 0, :]          # last stage, [K, Nq+N1D]; first Nq+1 entries are used
     Nq = dd.sizes.Nq
     assert np.array_equal(L[:, 0], np.roll(L[:, Nq], 1))    # face shared by elements k-1 and k (subcell.jl:405-416)
+
+
+@pytest.mark.parametrize("limiter", [SubcellLimiter(), ZhangShuLimiter()], ids=["subcell", "zhangshu"])
+def test_sod_gauss_nodewise_scaled_extrapolation(limiter):
+    """Gauss nodes with NodewiseScaledExtrapolation (filter.jl:6-130) in 1D: the projection limiter bites on some face nodes
+    (theta in [0, 1), 21 bisection steps => multiples of 2^-21), theta[k] is the mean of the element's two face values, and the
+    run reaches the same plateau as without the projection limiter."""
+    from p2de_b200 import NodewiseScaledExtrapolation
+    prob = P.sod(N=3, K=200, limiter=limiter, basis=GaussCollocation(), entropyproj_limiter=NodewiseScaledExtrapolation())
+    param, rd, md, dd, bc, U0 = P.setup(prob)
+    orc = Oracle(param, dd, bc, threads=4)
+    orc.set_state(U0)
+    t, bit = 0.0, 0
+    while t < 0.2 - 1e-12:
+        t += orc.ssp33_step(t)
+        th = orc.field("theta_local").reshape(3, -1, 2)
+        assert ((th >= 0.0) & (th <= 1.0)).all()
+        assert np.array_equal(th * 2.0 ** 21, np.round(th * 2.0 ** 21))
+        assert np.abs(orc.field("theta").reshape(3, -1) - th.mean(axis=2)).max() < 1e-15
+        bit += int((th < 1.0).sum())
+    assert bit > 0
+    U = orc.get_state()
+    x, rho = md.xq.reshape(-1), U[..., 0].reshape(-1)
+    plateau = rho[(x > 0.72) & (x < 0.82)]
+    assert abs(plateau.mean() - 0.26557) < 5e-4 and plateau.std() < 5e-3
+    assert rho.min() > 0.11 and orc.reduce(2) > 0

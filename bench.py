@@ -153,7 +153,7 @@ def initial_state(param, rd, ic, out):
 
 
 def source_hash():
-    """sha256 over the kernel sources: profiles/*_traffic.json is only quoted for the code it was captured from."""
+    """sha256 over the kernel sources (every file of csrc/): printed in the bench line so that records can be matched to code."""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "p2de_b200", "csrc")
@@ -161,6 +161,42 @@ def source_hash():
         with open(os.path.join(d, f), "rb") as fh:
             h.update(f.encode()); h.update(fh.read())
     return h.hexdigest()[:16]
+
+
+def kernel_sass_hashes(lib, names):
+    """{mangled name: sha256[:16] of its SASS} for the named kernels of a built library (cuobjdump -sass -fun), or None.
+
+    profiles/r2_traffic.json is an ncu capture of three kernels; it is quoted only while the machine code of exactly those
+    kernels in the library this run loaded is the one a build of the captured sources gives (the hash over all of csrc/
+    also changes when an unrelated kernel does).  (tools/kernel_sass_hash.py compares whole libraries the same way; its hashes are taken
+    over the full dump's slightly different framing of a function and are not interchangeable with these.)"""
+    import hashlib
+    import re
+    import shutil
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        return None
+    res = {}
+    for want in names:
+        try:
+            out = subprocess.run([exe, "-sass", "-fun", want, lib], capture_output=True, text=True, timeout=60).stdout
+        except Exception:
+            return None
+        name, body = None, []
+        for line in out.splitlines():
+            m = re.match(r"\s*Function : (\S+)", line)
+            if m:
+                if name == want:
+                    break
+                name, body = m.group(1), []
+            elif line.strip().startswith(".......") and name == want:
+                break
+            elif name == want:
+                body.append(line.rstrip())
+        if name != want or not body:
+            return None
+        res[want] = hashlib.sha256("\n".join(body).encode()).hexdigest()[:16]
+    return res
 
 
 def developed_state(workload, host_np, device):
@@ -450,12 +486,19 @@ def measure(args, workload, world, rank, local, headline):
         with open(tpath) as f:
             tall = json.load(f)
         tj = tall.get(workload, {})
-        if tall.get("source_hash") == source_hash():
+        want = tall.get("kernel_sass", {})
+        from p2de_b200.lib import SO_PATH
+        have = kernel_sass_hashes(SO_PATH, sorted(want)) if want else None
+        if tall.get("source_hash") == source_hash() or (have is not None and have == want):
             traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
             traffic_note = ("DRAM bytes per stage (dram__bytes_read.sum + dram__bytes_write.sum of the three stage kernels of one step / 3) from one "
-                            "ncu --set full capture of these kernel sources (profiles/r2_traffic.json, source hash checked)")
+                            "ncu --set full capture (profiles/r2_traffic.json); quoted because "
+                            + ("the kernel sources are the captured ones (source hash checked)" if tall.get("source_hash") == source_hash() else
+                               "the SASS of stage_subcell_s1/s2/s3<4,8> in the library this run loaded is identical to a build of the captured sources "
+                               "(cuobjdump hashes checked against the file's kernel_sass; other kernels of csrc/ have changed since)"))
         else:
-            traffic_note = "profiles/r2_traffic.json was captured from other kernel sources (hash mismatch): not quoted"
+            traffic_note = ("profiles/r2_traffic.json was captured from other kernel code (source hash and kernel SASS hashes both differ"
+                            + (", cuobjdump unavailable" if (want and have is None) else "") + "): not quoted")
     fp64_peak = None
     ppath = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
     if os.path.exists(ppath):

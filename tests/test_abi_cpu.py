@@ -91,3 +91,18 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle." not in txt and "import oracle" not in txt and "p2de_oracle" not in txt, f
+
+
+def test_ncu_capture_is_of_the_kernels_this_library_holds():
+    """profiles/r2_traffic.json (DRAM traffic, FP64 instruction counts of the three stage kernels) is quoted by bench.py only while
+    the SASS of exactly those kernels in the built library is what the captured sources compile to; this pins that it is."""
+    import json
+    import shutil
+    import bench
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+        want = json.load(f)["kernel_sass"]
+    assert len(want) == 3
+    plib.load()
+    assert bench.kernel_sass_hashes(plib.SO_PATH, sorted(want)) == want

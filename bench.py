@@ -487,24 +487,27 @@ def measure(args, workload, world, rank, local, headline):
     # DRAM traffic and FP64 instruction counts come from one ncu --set full capture (profiles/r2_traffic.json, written by
     # tools/summarize_ncu.py); they are only quoted for the kernel sources they were captured from (source_hash)
     traffic, fp64, traffic_note = None, None, "no ncu capture of these kernel sources in profiles/ (traffic: null)"
-    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            tall = json.load(f)
-        tj = tall.get(workload, {})
-        want = tall.get("kernel_sass", {})
-        from p2de_b200.lib import SO_PATH
-        have = kernel_sass_hashes(SO_PATH, sorted(want)) if want else None
-        if tall.get("source_hash") == source_hash() or (have is not None and have == want):
-            traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
-            traffic_note = ("DRAM bytes per stage (dram__bytes_read.sum + dram__bytes_write.sum of the three stage kernels of one step / 3) from one "
-                            "ncu --set full capture (profiles/r2_traffic.json); quoted because "
-                            + ("the kernel sources are the captured ones (source hash checked)" if tall.get("source_hash") == source_hash() else
-                               "the SASS of stage_subcell_s1/s2/s3<4,8> in the library this run loaded is identical to a build of the captured sources "
-                               "(cuobjdump hashes checked against the file's kernel_sass; other kernels of csrc/ have changed since)"))
-        else:
-            traffic_note = ("profiles/r2_traffic.json was captured from other kernel code (source hash and kernel SASS hashes both differ"
-                            + (", cuobjdump unavailable" if (want and have is None) else "") + "): not quoted")
+    try:
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tall = json.load(f)
+            tj = tall.get(workload, {})
+            want = tall.get("kernel_sass", {})
+            from p2de_b200.lib import SO_PATH
+            have = kernel_sass_hashes(SO_PATH, sorted(want)) if want else None
+            if tall.get("source_hash") == source_hash() or (have is not None and have == want):
+                traffic, fp64 = tj.get("per_stage_total_bytes"), tj.get("fp64")
+                traffic_note = ("DRAM bytes per stage (dram__bytes_read.sum + dram__bytes_write.sum of the three stage kernels of one step / 3) from one "
+                                "ncu --set full capture (profiles/r2_traffic.json); quoted because "
+                                + ("the kernel sources are the captured ones (source hash checked)" if tall.get("source_hash") == source_hash() else
+                                   "the SASS of stage_subcell_s1/s2/s3<4,8> in the library this run loaded is identical to a build of the captured sources "
+                                   "(cuobjdump hashes checked against the file's kernel_sass; other kernels of csrc/ have changed since)"))
+            else:
+                traffic_note = ("profiles/r2_traffic.json was captured from other kernel code (source hash and kernel SASS hashes both differ"
+                                + (", cuobjdump unavailable" if (want and have is None) else "") + "): not quoted")
+    except Exception as e:      # evidence look-up only: it must never cost the measured line
+        traffic, fp64, traffic_note = None, None, f"profiles/r2_traffic.json could not be matched to the loaded library ({e!r}): not quoted"
     fp64_peak = None
     ppath = os.path.join(ROOT, "profiles", "r1_fp64_peak.json")
     if os.path.exists(ppath):

@@ -41,6 +41,8 @@ WORKLOADS = {
     "S-DMR-small": dict(problem="dmr", N=3, K=(512, 128), note="S-DMR at 512x128"),
     "S-DMR-mid": dict(problem="dmr", N=3, K=(1024, 512), note="S-DMR at 1024x512 (profiling size)"),
     "S-KH": dict(problem="kelvin_helmholtz", N=4, K=(4096, 512), note="Kelvin-Helmholtz, N=4 LGL, 4096x512 per GPU, periodic"),
+    "S-VORTEX": dict(problem="vortex", N=3, K=(2048, 2048), note="isentropic vortex (test/test_smoke.jl data), N=3 LGL, 2048x2048, periodic: smooth, the limiter never engages "
+                     "(SURVEY.md 8d)"),
     # data-independence checks of the headline (same mesh and scheme as S-DMR, different data):
     "S-WAVE": dict(problem="wave2d", N=3, K=(4096, 1024), note="plateau-free smooth periodic data (tests/problems.py: wave2d), N=3 LGL, 4096x1024: "
                    "no constant elements, most node pairs off logmean's series branch (logs evaluated everywhere)"),

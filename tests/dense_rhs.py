@@ -1,0 +1,273 @@
+"""A SECOND, independently written restatement of one `rhs!` of the reference (2D compressible Euler), used only to cross-check
+the C++ oracle (tests/test_oracle_crosscheck.py).  It shares no code and no structure with oracle/p2de_oracle.cpp:
+
+* dense operators and plain numpy, vectorised over elements: the flux-differencing volume term is the full Nh x Nh Hadamard sum
+  `QF1_i = sum_j Sxyh_db[i, j] * fS(u_i, u_j)` (flux_differencing.jl:164-211 visits the non-zeros of the same matrix and adds the
+  skew-symmetric partner), the assembly is the dense `M^-1 Vh^T QF1 + M^-1 Vf^T BF` (flux_differencing.jl:274-361), face data are
+  gathered through the caller's linear `mapP`, boundary conditions through `mapI / mapO / Ival`;
+* no line structure, no tensor-product knowledge, no special case for Lobatto nodes.
+
+Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!` including the CFL dt and `find_alpha`
+(low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361).
+Not covered: the limiters (they have no dense formulation to restate differently).
+
+Test infrastructure; nothing under p2de_b200/ imports it."""
+import math
+
+import numpy as np
+
+from p2de_b200 import types as T
+
+_mlog = np.frompyfunc(math.log, 1, 1)
+_mexp = np.frompyfunc(math.exp, 1, 1)
+_mpow = np.frompyfunc(math.pow, 2, 1)
+
+
+def LOG(x):
+    """libm's log, element by element.  numpy's vectorised log differs from libm's in the last bit for some arguments, and
+    logmean's `-da / (logL - logR)` amplifies one ulp of a logarithm by 1 / |da / a| (up to 1e4), the near-cancelling sum of
+    S_ij f_ij by another ~1e2: with np.log this restatement and the C++ oracle agree to 2e-11 on a developed Kelvin-Helmholtz
+    state, with the same libm logarithm to 2e-13 (the reference formulation's own sensitivity)."""
+    return _mlog(np.asarray(x, dtype=float)).astype(float)
+
+
+def EXP(x):
+    return _mexp(np.asarray(x, dtype=float)).astype(float)
+
+
+def POW(x, y):
+    """libm's pow; a negative base gives NaN (math.pow would raise), as in the oracle and the CUDA path."""
+    x = np.asarray(x, dtype=float)
+    with np.errstate(invalid="ignore"):
+        safe = np.where(x < 0, np.nan, x)
+    return _mpow(safe, y).astype(float)
+
+
+def flux_options(rhs):
+    """(low-order surface flux, high-order surface flux, volume flux) codes of a LowOrderPositivity / FluxDiffRHS / LimitedDG."""
+    if rhs.code == T.RHS_LOW_ORDER_POSITIVITY:
+        return rhs.surface_flux.code, T.SURFFLUX_LF_PROJECTED, T.VOLFLUX_CHANDRASHEKAR
+    if rhs.code == T.RHS_FLUX_DIFF:
+        return T.SURFFLUX_LF_NODAL, rhs.surface_flux.code, rhs.volume_flux.code
+    return rhs.low_order_surface_flux.code, rhs.high_order_surface_flux.code, rhs.high_order_volume_flux.code
+
+
+# ---- compressible_Navier_Stokes.jl (Dim2); U[..., 4]
+def pfun(g, U):
+    return (g - 1.0) * (U[..., 3] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) / U[..., 0])
+
+
+def betafun(g, U):
+    return U[..., 0] / (2 * pfun(g, U))
+
+
+def wavespeed(g, U, n):
+    """wavespeed_estimate(::Dim2, U, n) :48-62: the 1D estimate of (rho, n . m, E)."""
+    mn = n[..., 0] * U[..., 1] + n[..., 1] * U[..., 2]
+    p = (g - 1.0) * (U[..., 3] - 0.5 * mn ** 2 / U[..., 0])
+    return np.abs(mn / U[..., 0]) + np.sqrt(g * p / U[..., 0])
+
+
+def v_ufun(g, U):
+    p = pfun(g, U)
+    s = LOG(p / POW(U[..., 0], g))
+    return np.stack([(g + 1 - s) - (g - 1) * U[..., 3] / p, U[..., 1] * (g - 1) / p, U[..., 2] * (g - 1) / p,
+                     -U[..., 0] * (g - 1) / p], axis=-1)
+
+
+def u_vfun(g, V):
+    q = V[..., 1] ** 2 + V[..., 2] ** 2
+    s = g - V[..., 0] + q / (2 * V[..., 3])
+    rhoeV = POW((g - 1) / POW(-V[..., 3], g), 1 / (g - 1)) * EXP(-s / (g - 1))
+    return np.stack([-rhoeV * V[..., 3], rhoeV * V[..., 1], rhoeV * V[..., 2], rhoeV * (1 - q / (2 * V[..., 3]))], axis=-1)
+
+
+def fluxes(g, U):
+    """-> [..., 2, 4]"""
+    rho, m1, m2, E = (U[..., c] for c in range(4))
+    p = pfun(g, U)
+    u, v = m1 / rho, m2 / rho
+    fx = np.stack([m1, m1 * u + p, rho * u * v, u * (E + p)], axis=-1)
+    fy = np.stack([m2, rho * u * v, m2 * v + p, v * (E + p)], axis=-1)
+    return np.stack([fx, fy], axis=-2)
+
+
+def logmean(aL, aR, logL, logR):
+    da = aR - aL
+    aavg = 0.5 * (aR + aL)
+    f = da / aavg
+    v = f * f
+    series = aavg * (1 + v * (-0.2 - v * (0.0512 - v * 0.026038857142857)))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        general = -da / (logL - logR)
+    return np.where(np.abs(f) < 1e-4, series, general)
+
+
+def fS(g, rhoL, uL, vL, bL, rlL, blL, rhoR, uR, vR, bR, rlR, blR):
+    """fS(::Dim2) :238-266 -> [..., 2, 4]"""
+    rholog = logmean(rhoL, rhoR, rlL, rlR)
+    betalog = logmean(bL, bR, blL, blR)
+    rhoavg, uavg, vavg = 0.5 * (rhoL + rhoR), 0.5 * (uL + uR), 0.5 * (vL + vR)
+    unorm = uL * uR + vL * vR
+    pa = rhoavg / (bL + bR)
+    f4aux = rholog / (2 * (g - 1) * betalog) + pa + 0.5 * rholog * unorm
+    Fx1 = rholog * uavg
+    Fx3 = Fx1 * vavg
+    Fy1 = rholog * vavg
+    fx = np.stack([Fx1, Fx1 * uavg + pa, Fx3, f4aux * uavg], axis=-1)
+    fy = np.stack([Fy1, Fx3, Fy1 * vavg + pa, f4aux * vavg], axis=-1)
+    return np.stack([fx, fy], axis=-2)
+
+
+def find_alpha(POSTOL, ui, ut):
+    """low_order_graph_viscosity.jl:299-327, elementwise over leading axes."""
+    def ok(al):
+        s = al[..., None] * ui - ut
+        with np.errstate(divide="ignore", invalid="ignore"):
+            rhoe = s[..., 3] - 0.5 * (s[..., 1] ** 2 + s[..., 2] ** 2) / s[..., 0]
+        return (s[..., 0] > POSTOL) & (rhoe > POSTOL)
+    aL = np.zeros(ui.shape[:-1])
+    aR = np.ones(ui.shape[:-1])
+    for _ in range(1100):
+        bad = ~ok(aR)
+        if not bad.any():
+            break
+        aR = np.where(bad, 2 * aR, aR)
+    for _ in range(50):
+        aM = (aL + aR) / 2
+        good = ok(aM)
+        aR = np.where(good, aM, aR)
+        aL = np.where(good, aL, aM)
+    return aR
+
+
+def dense_rhs(param, dd, bc, Uq, t, nstage=1):
+    """One rhs! without the limiter.  Returns dict(rhsL, rhsH, rhsxyL, rhsxyH [K, Nq, 2, 4], dt, u_tilde_f)."""
+    g = param.equation.gamma
+    sz, ops, geom = dd.sizes, dd.ops, dd.geom
+    K, Nq, Nfp, Nh = sz.K, sz.Nq, sz.Nfp, sz.Nh
+    N1D = param.N + 1
+    POSTOL = param.global_constants.POSTOL
+    tp = param.timestepping_param
+    fq2q = np.asarray(ops.fq2q) - 1
+    rxJ, sxJ, ryJ, syJ = (np.asarray(a, dtype=float) for a in geom.GJh)        # [K, Nh]
+    low_flux, high_flux, vol_flux = flux_options(param.rhs)
+    low_proj = low_flux == T.SURFFLUX_LF_PROJECTED
+    mapP = np.asarray(bc.mapP).reshape(K * Nfp) - 1                            # linear index into [K, Nfp]
+    mapI = np.asarray(bc.mapI, dtype=np.int64).reshape(-1) - 1
+    mapO = np.asarray(bc.mapO, dtype=np.int64).reshape(-1) - 1
+    Ival = np.asarray(bc.Ival, dtype=float).reshape(-1, 4)
+
+    # ---- entropy projection, theta = 1 (rhs.jl:59-133)
+    vq = v_ufun(g, Uq)                                                         # [K, Nq, 4]
+    vf = np.einsum("fq,kqc->kfc", ops.Vf, vq)
+    utf = u_vfun(g, vf)                                                        # [K, Nfp, 4]
+    u_tilde = np.concatenate([Uq, utf], axis=1)                                # [K, Nh, 4]
+
+    # physical boundary matrix entries and normals at the face nodes (rhs_utils.jl:13-39)
+    Br, Bs = (np.asarray(b, dtype=float) for b in ops.Brs)
+    Bxy = np.stack([rxJ[:, Nq:] * Br + sxJ[:, Nq:] * Bs, ryJ[:, Nq:] * Br + syJ[:, Nq:] * Bs], axis=-1)   # [K, Nfp, 2]
+    nnorm = np.linalg.norm(Bxy, axis=-1)
+    nf = Bxy / nnorm[..., None]
+    xface = np.arange(Nfp) < 2 * N1D                                           # apply_LF_dissipation_to_BF :84-91
+
+    # =================== low order (low_order_graph_viscosity.jl)
+    Uf = utf if low_proj else Uq[:, fq2q]                                      # update_face_values! :44-65
+    flux_q = fluxes(g, Uq)                                                     # [K, Nq, 2, 4]
+    flux_f = fluxes(g, Uf)
+    ws_f = wavespeed(g, Uf, nf)
+    uP = Uf.reshape(K * Nfp, 4)[mapP].copy()                                   # get_uP_and_enforce_BC! :87-118
+    if len(mapI):
+        uP[mapI] = Ival
+    if len(mapO):
+        uP[mapO] = Uq[mapO // Nfp, fq2q[mapO % Nfp]]
+    uP = uP.reshape(K, Nfp, 4)
+    Q0F1 = np.zeros((K, Nq, 2, 4))
+    lam = np.zeros((K, Nq, Nq))
+    Sr0, Ss0 = ops.Srs0
+    for (i1, j1) in ops.Srs0_nnz:                                              # accumulate_low_order_rhs_volume! :131-165
+        i, j = i1 - 1, j1 - 1
+        Sx = rxJ[:, i] * Sr0[i, j] + sxJ[:, i] * Ss0[i, j]
+        Sy = ryJ[:, i] * Sr0[i, j] + syJ[:, i] * Ss0[i, j]
+        Sxy = np.stack([Sx, Sy], axis=-1)                                      # [K, 2]
+        nn = np.linalg.norm(Sxy, axis=-1)
+        nij = Sxy / nn[:, None]
+        lam_ij = nn * np.maximum(wavespeed(g, Uq[:, i], nij), wavespeed(g, Uq[:, j], -nij))
+        lam[:, i, j] = lam[:, j, i] = lam_ij
+        F = 0.5 * (flux_q[:, i] + flux_q[:, j])                                # [K, 2, 4]
+        visc = lam_ij[:, None] * (Uq[:, j] - Uq[:, i])                         # graph_viscosity(::Dim2) :118-132
+        D = np.zeros((K, 2, 4))
+        isx = np.abs(Sx) > 1e-10
+        D[isx, 0] = visc[isx]
+        D[~isx, 1] = visc[~isx]
+        SF = 2.0 * Sxy[:, :, None] * F - D
+        Q0F1[:, i] += SF
+        Q0F1[:, j] -= SF
+    rhsxyL = -Q0F1
+    lamB = 0.5 * nnorm * np.maximum(ws_f, ws_f.reshape(K * Nfp)[mapP].reshape(K, Nfp))     # :167-195
+    fstar_L = 0.5 * (flux_f + fluxes(g, uP))
+    BF_L = Bxy[..., None] * fstar_L                                            # [K, Nfp, 2, 4]
+    lf = lamB[..., None] * (uP - Uf)
+    BF_L[:, xface, 0] -= lf[:, xface]
+    BF_L[:, ~xface, 1] -= lf[:, ~xface]
+    for f in range(Nfp):
+        rhsxyL[:, fq2q[f]] -= BF_L[:, f]
+    wJ = np.asarray(geom.Jq, dtype=float) * ops.wq[None, :]                    # scale_low_order_rhs_by_mass! :197-211
+    rhsxyL = rhsxyL / wJ[:, :, None, None]
+    rhsL = rhsxyL.sum(axis=2)
+    dt = None
+    if nstage == 1:                                                            # calculate_lambda_and_low_order_CFL! :213-281
+        lam_i = lam.sum(axis=2)
+        if low_proj:
+            alpha = find_alpha(POSTOL, Uq[:, fq2q], utf)
+            lamB_cfl = alpha * lamB + 0.5 * nnorm * ws_f
+        else:
+            lamB_cfl = lamB
+        for i in range(Nq):
+            for f1 in ops.q2fq[i]:
+                lam_i[:, i] += lamB_cfl[:, f1 - 1]
+        dt = min(min(tp.CFL * tp.dt0, tp.T - t), float((tp.CFL * 0.5 * wJ / lam_i).min()))
+
+    # =================== high order (flux_differencing.jl)
+    beta = betafun(g, u_tilde)                                                 # calculate_primitive_variables! :39-72
+    rholog, betalog = LOG(u_tilde[..., 0]), LOG(beta)
+    uu, vv = u_tilde[..., 1] / u_tilde[..., 0], u_tilde[..., 2] / u_tilde[..., 0]
+    lam_f = wavespeed(g, utf, nf)                                              # calculate_interface_dissipation_coeff! :92-116
+    LFc = 0.5 * nnorm * np.maximum(lam_f, lam_f.reshape(K * Nfp)[mapP].reshape(K, Nfp))
+    uPh = utf.reshape(K * Nfp, 4)[mapP].copy()
+    LFc = LFc.reshape(K * Nfp)
+    if len(mapI):                                                              # enforce_BC! :118-151
+        LFc[mapI] = 0.0
+        uPh[mapI] = Ival
+    if len(mapO):
+        LFc[mapO] = 0.0
+        uPh[mapO] = Uq[mapO // Nfp, fq2q[mapO % Nfp]]
+    LFc = LFc.reshape(K, Nfp)
+    uPh = uPh.reshape(K, Nfp, 4)
+    Srh, Ssh = ops.Srsh_db
+    Sxh = rxJ[:, :, None] * Srh[None] + sxJ[:, :, None] * Ssh[None]            # Sx(::Dim2) :49-54: geometry at row i
+    Syh = ryJ[:, :, None] * Srh[None] + syJ[:, :, None] * Ssh[None]            # [K, Nh, Nh]
+    vol_central = vol_flux == T.VOLFLUX_CENTRAL
+    if vol_central:                                                            # eval_high_order_volume_flux(::CentralFlux) :217-221
+        fh = fluxes(g, u_tilde)                                                # [K, Nh, 2, 4]
+        Fij = 0.5 * (fh[:, :, None] + fh[:, None, :])                          # [K, Nh, Nh, 2, 4]
+    else:
+        L = lambda a: a[:, :, None]
+        R = lambda a: a[:, None, :]
+        Fij = fS(g, L(u_tilde[..., 0]), L(uu), L(vv), L(beta), L(rholog), L(betalog),
+                 R(u_tilde[..., 0]), R(uu), R(vv), R(beta), R(rholog), R(betalog))
+    QF1 = np.stack([np.einsum("kij,kijc->kic", Sxh, Fij[..., 0, :]), np.einsum("kij,kijc->kic", Syh, Fij[..., 1, :])], axis=2)   # [K, Nh, 2, 4]
+    surf_chandra = high_flux == T.SURFFLUX_CHANDRASHEKAR_PROJECTED
+    if surf_chandra:                                                           # ChandrashekarOnProjectedVal :232-243
+        bP = betafun(g, uPh)
+        fstar_H = fS(g, utf[..., 0], utf[..., 1] / utf[..., 0], utf[..., 2] / utf[..., 0], beta[:, Nq:], rholog[:, Nq:], betalog[:, Nq:],
+                     uPh[..., 0], uPh[..., 1] / uPh[..., 0], uPh[..., 2] / uPh[..., 0], bP, LOG(uPh[..., 0]), LOG(bP))
+    else:
+        fstar_H = 0.5 * (fluxes(g, utf) + fluxes(g, uPh))
+    BF_H = Bxy[..., None] * fstar_H
+    lfh = LFc[..., None] * (uPh - utf)
+    BF_H[:, xface, 0] -= lfh[:, xface]
+    BF_H[:, ~xface, 1] -= lfh[:, ~xface]
+    rhsxyH = -(np.einsum("qh,khdc->kqdc", ops.MinvVhT, QF1) + np.einsum("qf,kfdc->kqdc", ops.MinvVfT, BF_H)) \
+        / np.asarray(geom.Jq, dtype=float)[:, :, None, None]                   # assemble_rhs! :331-361
+    return {"rhsL": rhsL, "rhsxyL": rhsxyL, "rhsH": rhsxyH.sum(axis=2), "rhsxyH": rhsxyH, "dt": dt, "u_tilde_f": utf}

@@ -8,8 +8,9 @@ the C++ oracle (tests/test_oracle_crosscheck.py).  It shares no code and no stru
 * no line structure, no tensor-product knowledge, no special case for Lobatto nodes.
 
 Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!` including the CFL dt and `find_alpha`
-(low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361).
-Not covered: the limiters (they have no dense formulation to restate differently).
+(low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361),
+and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with PositivityBound as whole-array operations with the
+interface symmetrisation through `mapP` (`dense_limited_rhs`).  Not covered: the other nine subcell bounds, shock capturing, 1D.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -270,4 +271,96 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1):
     BF_H[:, ~xface, 1] -= lfh[:, ~xface]
     rhsxyH = -(np.einsum("qh,khdc->kqdc", ops.MinvVhT, QF1) + np.einsum("qf,kfdc->kqdc", ops.MinvVfT, BF_H)) \
         / np.asarray(geom.Jq, dtype=float)[:, :, None, None]                   # assemble_rhs! :331-361
-    return {"rhsL": rhsL, "rhsxyL": rhsxyL, "rhsH": rhsxyH.sum(axis=2), "rhsxyH": rhsxyH, "dt": dt, "u_tilde_f": utf}
+    return {"rhsL": rhsL, "rhsxyL": rhsxyL, "rhsH": rhsxyH.sum(axis=2), "rhsxyH": rhsxyH, "dt": dt, "u_tilde_f": utf,
+            "BF_L": BF_L, "BF_H": BF_H, "wJ": wJ}
+
+
+# ---- limiter_utils.jl:26-95, vectorised (IEEE semantics kept: a == 0 gives infinite / NaN roots, which fail every comparison)
+def rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe):
+    a = Pv[..., 0] * Pv[..., 3] - 0.5 * (Pv[..., 1] ** 2 + Pv[..., 2] ** 2)
+    b = U[..., 3] * Pv[..., 0] + U[..., 0] * Pv[..., 3] - U[..., 1] * Pv[..., 1] - U[..., 2] * Pv[..., 2] - Pv[..., 0] * Lrhoe
+    c = U[..., 3] * U[..., 0] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) - U[..., 0] * Lrhoe
+    disc = b * b - 4 * a * c
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sq = np.sqrt(np.where(disc >= 0, disc, 0.0))
+        r1 = (-b + sq) / (2 * a)
+        r2 = (-b - sq) / (2 * a)
+        l = np.ones_like(a)
+        both = (r1 > ZEROTOL) & (r2 > ZEROTOL)
+        only1 = ~both & (r1 > ZEROTOL) & (r2 < -ZEROTOL)
+        only2 = ~both & ~only1 & (r2 > ZEROTOL) & (r1 < -ZEROTOL)
+        l = np.where(both, np.minimum(r1, r2), l)       # (finite here: both compare greater than ZEROTOL)
+        l = np.where(only1, r1, l)
+        l = np.where(only2, r2, l)
+    return np.where(disc >= 0, l, 1.0)
+
+
+def limiting_param_rho_rhoe(ZEROTOL, U, Pv, Lrho, Lrhoe):
+    """limiting_param_bound_rho_rhoe with Urho = Urhoe = Inf (PositivityBound, Zhang-Shu)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        l = np.where(U[..., 0] + Pv[..., 0] < Lrho, np.maximum((Lrho - U[..., 0]) / Pv[..., 0], 0.0), 1.0)
+    return np.minimum(np.minimum(l, rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe)), 1.0)
+
+
+def rhoe_ufun(U):
+    return U[..., 3] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) / U[..., 0]
+
+
+def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1):
+    """rhs!(::LimitedDG) with NoShockCapture: dense_rhs + apply_rhs_limiter! (Zhang-Shu: zhangshu.jl:4-45; subcell with
+    PositivityBound: subcell.jl:163-349, 418-456, 841-924), vectorised over elements and subcell faces, neighbours through mapP.
+    `dt` is the dt the limiter sees (the caller's, rhs.jl:46,52).  Adds rhsU and L [K] or Lx [K, N1D, N1D+1], Ly [K, N1D+1, N1D]."""
+    d = dense_rhs(param, dd, bc, Uq, t, nstage)
+    zeta, ZEROTOL = param.limiting_param.zeta, param.global_constants.ZEROTOL
+    sz = dd.sizes
+    K, Nq, Nfp = sz.K, sz.Nq, sz.Nfp
+    n = param.N + 1
+    uL = Uq + dt * d["rhsL"]
+    if param.rhs_limiter.code == T.LIMITER_ZHANGSHU:
+        Pv = dt * (d["rhsH"] - d["rhsL"])
+        l = limiting_param_rho_rhoe(ZEROTOL, uL, Pv, zeta * uL[..., 0], zeta * rhoe_ufun(uL)).min(axis=1)
+        d["L"] = l
+        d["rhsU"] = (1 - l)[:, None, None] * d["rhsL"] + l[:, None, None] * d["rhsH"]
+        return d
+    wJ = d["wJ"].reshape(K, n, n)                                     # [K, jq, iq]
+    uLg = uL.reshape(K, n, n, 4)
+    rH, rL = d["rhsxyH"].reshape(K, n, n, 2, 4), d["rhsxyL"].reshape(K, n, n, 2, 4)
+    fb = {}
+    for name, r, BF in (("H", rH, d["BF_H"]), ("L", rL, d["BF_L"])):  # accumulate_f_bar! :163-206 (running sums, in this order)
+        fx = np.zeros((K, n, n + 1, 4))                               # [K, sj, si]
+        fx[:, :, 0] = BF[:, 0:n, 0]
+        for si in range(1, n + 1):
+            fx[:, :, si] = fx[:, :, si - 1] + wJ[:, :, si - 1, None] * r[:, :, si - 1, 0]
+        fy = np.zeros((K, n + 1, n, 4))                               # [K, sj, si]
+        fy[:, 0] = BF[:, 2 * n:3 * n, 1]
+        for sj in range(1, n + 1):
+            fy[:, sj] = fy[:, sj - 1] + wJ[:, sj - 1, :, None] * r[:, sj - 1, :, 1]
+        fb[name] = (fx, fy)
+    dfx, dfy = fb["H"][0] - fb["L"][0], fb["H"][1] - fb["L"][1]
+    Lrho, Lrhoe = zeta * uLg[..., 0], zeta * rhoe_ufun(uLg)
+    Lx, Ly = np.ones((K, n, n + 1)), np.ones((K, n + 1, n))          # subcell_bound_limiter! :248-349
+    # x: subcell face si is the LEFT face of node si (P = -4 dt df / wJ) and the RIGHT face of node si - 1 (P = +4 dt df / wJ)
+    Lx[:, :, :n] = np.minimum(Lx[:, :, :n], limiting_param_rho_rhoe(ZEROTOL, uLg, -4 * dt * dfx[:, :, :n] / wJ[..., None], Lrho, Lrhoe))
+    Lx[:, :, 1:] = np.minimum(Lx[:, :, 1:], limiting_param_rho_rhoe(ZEROTOL, uLg, 4 * dt * dfx[:, :, 1:] / wJ[..., None], Lrho, Lrhoe))
+    Ly[:, :n] = np.minimum(Ly[:, :n], limiting_param_rho_rhoe(ZEROTOL, uLg, -4 * dt * dfy[:, :n] / wJ[..., None], Lrho, Lrhoe))
+    Ly[:, 1:] = np.minimum(Ly[:, 1:], limiting_param_rho_rhoe(ZEROTOL, uLg, 4 * dt * dfy[:, 1:] / wJ[..., None], Lrho, Lrhoe))
+    # symmetrize_limiting_parameters! :418-456, partner faces through mapP (limiter_utils.jl:122-181)
+    mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
+    Lx0, Ly0 = Lx.copy(), Ly.copy()
+    kk = np.arange(K)[:, None]
+    line = np.arange(n)[None, :]
+    for e, pos in ((0, 0), (1, n)):
+        P = mapP[:, e * n:(e + 1) * n]                                # x faces: face nodes e n + sj
+        kP, iP = P // Nfp, P % Nfp
+        Lx[kk, line, pos] = np.minimum(Lx0[kk, line, pos], Lx0[kP, iP % n, np.where(iP // n == 0, 0, n)])
+        P = mapP[:, (2 + e) * n:(3 + e) * n]                          # y faces: face nodes (2 + e) n + si
+        kP, iP = P // Nfp, P % Nfp
+        Ly[kk, pos, line] = np.minimum(Ly0[kk, pos, line], Ly0[kP, np.where(iP // n == 2, 0, n), iP % n])
+    flx = Lx[..., None] * fb["H"][0] + (1 - Lx[..., None]) * fb["L"][0]     # accumulate_f_bar_limited! :841-876
+    fly = Ly[..., None] * fb["H"][1] + (1 - Ly[..., None]) * fb["L"][1]
+    rx = (flx[:, :, 1:] - flx[:, :, :-1]) / wJ[..., None]             # apply_subcell_limiter! :894-924
+    ry = (fly[:, 1:] - fly[:, :-1]) / wJ[..., None]
+    d["rhsU"] = (rx + ry).reshape(K, Nq, 4)
+    d["Lx"], d["Ly"] = Lx, Ly
+    return d
+

@@ -11,9 +11,9 @@ import pytest
 import problems as P
 from dense_rhs import dense_rhs
 from oracle.oracle import Oracle
-from p2de_b200 import (CentralFlux, ChandrashekarFlux, ChandrashekarOnProjectedVal, ESLimitedLowOrderPos, FluxDiffRHS,
+from p2de_b200 import (CentralFlux, ChandrashekarFlux, ChandrashekarOnProjectedVal, ESLimitedLowOrderPos, FluxDiffRHS,  # noqa: F401
                        GaussCollocation, LaxFriedrichsOnNodalVal, LaxFriedrichsOnProjectedVal, LimitedDG, LowOrderPositivity,
-                       StdDGLimitedLowOrderPos)
+                       StdDGLimitedLowOrderPos, ZhangShuLimiter)
 
 PROJ = LaxFriedrichsOnProjectedVal()
 
@@ -112,3 +112,55 @@ def test_the_dense_restatement_is_not_trivially_satisfied():
     d = dense_rhs(param, bad, bc, U0, tp.t0, 1)
     assert rel(d["rhsH"], orc.field("rhsH")) > 1e-9
     assert rel(d["rhsL"], orc.field("rhsL")) < 1e-12
+
+
+LIMITED = {
+    "sedov-N3-subcell": (lambda: P.sedov(N=3, K=(8, 8)), 6),
+    "sedov-N2-zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 6),
+    "dmr-N3-subcell": (lambda: P.dmr(N=3, K=(16, 4)), 5),
+    "dmr-N2-zhangshu": (lambda: P.dmr(N=2, K=(16, 4), limiter=ZhangShuLimiter()), 4),
+    "vortex-N3-subcell-smoke": (lambda: P.vortex(N=3, K=(5, 5)), 0),
+    "vortex-N4-subcell": (lambda: P.vortex(N=4, K=(4, 4), T=10.0), 2),
+    "kh-N1-subcell": (lambda: P.kelvin_helmholtz(N=1, K=(8, 8)), 4),
+    "kh-N3-gauss-subcell": (lambda: P.kelvin_helmholtz(N=3, K=(5, 5), basis=GaussCollocation(), rhs=ESLimitedLowOrderPos(PROJ, PROJ)), 4),
+    "front-N2-gauss-subcell-inflow-outflow": (lambda: front(2, (12, 4), basis=GaussCollocation(), rhs=ESLimitedLowOrderPos(PROJ, PROJ)), 3),
+    "kh-N2-gauss-zhangshu": (lambda: P.kelvin_helmholtz(N=2, K=(6, 6), basis=GaussCollocation(), limiter=ZhangShuLimiter(),
+                                                        rhs=ESLimitedLowOrderPos(PROJ, PROJ)), 3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LIMITED))
+def test_oracle_limiters_agree_with_the_dense_restatement(name):
+    """rhs!(::LimitedDG) including apply_rhs_limiter!: Zhang-Shu (zhangshu.jl:4-45) and the subcell limiter with PositivityBound
+    (accumulate_f_bar!, subcell_bound_limiter!, symmetrize_limiting_parameters!, accumulate_f_bar_limited!, apply_subcell_limiter!;
+    subcell.jl:163-349, 418-456, 841-924) restated with whole-array numpy operations and mapP gathers: coefficients to 1e-12 with
+    identical {l == 1} sets, rhsU to 1e-12, for every stage index (the limiter sees the caller's dt, rhs.jl:46,52)."""
+    from dense_rhs import dense_limited_rhs
+    make, nsteps = LIMITED[name]
+    param, rd, md, dd, bc, U0 = P.setup(make())
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, n = dd.sizes.K, param.N + 1
+    active = 0
+    for nstage in (1, 2, 3):
+        dt_in = tp.CFL * tp.dt0
+        orc.rhs(t, dt_in, nstage)
+        d = dense_limited_rhs(param, dd, bc, U, t, dt_in, nstage)
+        assert rel(d["rhsU"], orc.field("rhsU")) < 1e-12, (name, nstage)
+        if "L" in d:
+            pairs = [(d["L"], orc.field("L").reshape(3, K)[nstage - 1])]
+        else:
+            Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]      # Julia [Nq + N1D, Nd, K, Ns]
+            pairs = [(d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))]
+        for mine, ref in pairs:
+            assert np.abs(mine - ref).max() < 1e-12, (name, nstage)
+            assert np.array_equal(mine == 1.0, ref == 1.0), (name, nstage)
+            active += int((ref < 1.0).sum())
+    if name.startswith(("sedov", "dmr-N3", "vortex-N3")):
+        assert active > 0, "the case was chosen because the limiter engages"

@@ -10,7 +10,9 @@ the C++ oracle (tests/test_oracle_crosscheck.py).  It shares no code and no stru
 Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!` including the CFL dt and `find_alpha`
 (low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361),
 and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with PositivityBound as whole-array operations with the
-interface symmetrisation through `mapP` (`dense_limited_rhs`).  Not covered: the other nine subcell bounds, shock capturing, 1D.
+interface symmetrisation through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
+filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319).  Not covered: the other nine
+subcell bounds, shock capturing, 1D.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -142,8 +144,44 @@ def find_alpha(POSTOL, ui, ut):
     return aR
 
 
-def dense_rhs(param, dd, bc, Uq, t, nstage=1):
-    """One rhs! without the limiter.  Returns dict(rhsL, rhsH, rhsxyL, rhsxyH [K, Nq, 2, 4], dt, u_tilde_f)."""
+def dense_theta(param, dd, Uq):
+    """compute_entropyproj_limiting_param!(::GaussCollocation) with NodewiseScaledExtrapolation (filter.jl:6-130): per face node the
+    largest theta in [0, 1] (21-step bisection, nonlinear_solvers.jl:3-20) for which u(v_tilde_f(theta)) stays within the bounds of
+    :84-98; all face nodes of all elements at once.  -> theta_local [K, Nfp]"""
+    g = param.equation.gamma
+    ops = dd.ops
+    eps, zeta, eta = param.global_constants.POSTOL, param.limiting_param.zeta, param.limiting_param.eta
+    vq = v_ufun(g, Uq)
+    Uf = np.einsum("fq,kqc->kfc", ops.Vf, Uq)                                  # calc_face_values! :26-41
+    VUf = np.einsum("fq,kqc->kfc", ops.Vf, vq)
+    rhoef = rhoe_ufun(Uf)
+    hi, lo = np.einsum("fq,kqc->kfc", ops.Vf, vq), np.einsum("fq,kqc->kfc", ops.Vf_low, vq)
+
+    def ok(th):
+        # (theta Vf + (1 - theta) Vf_low) vq accumulated node by node in the reference; the two extrapolations are linear in vq
+        W = th[..., None] * np.asarray(ops.Vf)[None] + (1 - th[..., None]) * np.asarray(ops.Vf_low)[None]      # [K, Nfp, Nq]
+        vt = np.einsum("kfq,kqc->kfc", W, vq)
+        well = vt[..., 3] < -eps
+        with np.errstate(all="ignore"):
+            ut = u_vfun(g, np.where(well[..., None], vt, np.array([0.0, 0.0, 0.0, -1.0])))
+            rhoe = rhoe_ufun(ut)
+            good = (vt[..., 3] < np.minimum(zeta * VUf[..., 3], -eps)) & (ut[..., 0] > np.maximum((1 - eta) * Uf[..., 0], eps)) & \
+                (ut[..., 0] < (1 + eta) * Uf[..., 0]) & (rhoe > np.maximum((1 - eta) * rhoef, eps)) & (rhoe < (1 + eta) * rhoef)
+        return well & good
+    one = ok(np.ones(Uf.shape[:2]))
+    xv, xi = np.zeros(Uf.shape[:2]), np.ones(Uf.shape[:2])
+    for _ in range(21):
+        xn = 0.5 * (xv + xi)
+        good = ok(xn)
+        xv = np.where(good, xn, xv)
+        xi = np.where(good, xi, xn)
+    return np.where(one, 1.0, xv)
+
+
+def dense_rhs(param, dd, bc, Uq, t, nstage=1, theta_local=None):
+    """One rhs! without the limiter.  Returns dict(rhsL, rhsH, rhsxyL, rhsxyH [K, Nq, 2, 4], dt, u_tilde_f, ...).
+    `theta_local` [K, Nfp]: the projection-limiting parameters to use (NodewiseScaledExtrapolation); None = computed here when
+    the configuration has that limiter, 1 otherwise."""
     g = param.equation.gamma
     sz, ops, geom = dd.sizes, dd.ops, dd.geom
     K, Nq, Nfp, Nh = sz.K, sz.Nq, sz.Nfp, sz.Nh
@@ -161,7 +199,10 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1):
 
     # ---- entropy projection, theta = 1 (rhs.jl:59-133)
     vq = v_ufun(g, Uq)                                                         # [K, Nq, 4]
-    vf = np.einsum("fq,kqc->kfc", ops.Vf, vq)
+    if theta_local is None:
+        theta_local = dense_theta(param, dd, Uq) if param.entropyproj_limiter.code == T.PROJLIM_NODEWISE else np.ones((K, Nfp))
+    Vf_new = theta_local[..., None] * np.asarray(ops.Vf)[None] + (1 - theta_local[..., None]) * np.asarray(ops.Vf_low)[None]   # [K, Nfp, Nq]
+    vf = np.einsum("kfq,kqc->kfc", Vf_new, vq)                                 # entropy_projection_face_node! :84-94
     utf = u_vfun(g, vf)                                                        # [K, Nfp, 4]
     u_tilde = np.concatenate([Uq, utf], axis=1)                                # [K, Nh, 4]
 
@@ -269,10 +310,14 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1):
     lfh = LFc[..., None] * (uPh - utf)
     BF_H[:, xface, 0] -= lfh[:, xface]
     BF_H[:, ~xface, 1] -= lfh[:, ~xface]
-    rhsxyH = -(np.einsum("qh,khdc->kqdc", ops.MinvVhT, QF1) + np.einsum("qf,kfdc->kqdc", ops.MinvVfT, BF_H)) \
-        / np.asarray(geom.Jq, dtype=float)[:, :, None, None]                   # assemble_rhs! :331-361
+    if (theta_local == 1.0).all():
+        proj = np.einsum("qh,khdc->kqdc", ops.MinvVhT, QF1) + np.einsum("qf,kfdc->kqdc", ops.MinvVfT, BF_H)
+    else:   # project_flux_difference_to_quad!(::ScaledExtrapolation) :288-319: M^-1 [I Vf_new^T] with the limited Vf_new
+        proj = (QF1[:, :Nq] + np.einsum("kfq,kfdc->kqdc", Vf_new, QF1[:, Nq:]) + np.einsum("kfq,kfdc->kqdc", Vf_new, BF_H)) \
+            / np.asarray(ops.wq)[None, :, None, None]
+    rhsxyH = -proj / np.asarray(geom.Jq, dtype=float)[:, :, None, None]        # assemble_rhs! :331-361
     return {"rhsL": rhsL, "rhsxyL": rhsxyL, "rhsH": rhsxyH.sum(axis=2), "rhsxyH": rhsxyH, "dt": dt, "u_tilde_f": utf,
-            "BF_L": BF_L, "BF_H": BF_H, "wJ": wJ}
+            "BF_L": BF_L, "BF_H": BF_H, "wJ": wJ, "theta_local": theta_local}
 
 
 # ---- limiter_utils.jl:26-95, vectorised (IEEE semantics kept: a == 0 gives infinite / NaN roots, which fail every comparison)
@@ -306,11 +351,11 @@ def rhoe_ufun(U):
     return U[..., 3] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) / U[..., 0]
 
 
-def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1):
+def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None):
     """rhs!(::LimitedDG) with NoShockCapture: dense_rhs + apply_rhs_limiter! (Zhang-Shu: zhangshu.jl:4-45; subcell with
     PositivityBound: subcell.jl:163-349, 418-456, 841-924), vectorised over elements and subcell faces, neighbours through mapP.
     `dt` is the dt the limiter sees (the caller's, rhs.jl:46,52).  Adds rhsU and L [K] or Lx [K, N1D, N1D+1], Ly [K, N1D+1, N1D]."""
-    d = dense_rhs(param, dd, bc, Uq, t, nstage)
+    d = dense_rhs(param, dd, bc, Uq, t, nstage, theta_local)
     zeta, ZEROTOL = param.limiting_param.zeta, param.global_constants.ZEROTOL
     sz = dd.sizes
     K, Nq, Nfp = sz.K, sz.Nq, sz.Nfp

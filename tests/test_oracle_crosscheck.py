@@ -164,3 +164,54 @@ def test_oracle_limiters_agree_with_the_dense_restatement(name):
             active += int((ref < 1.0).sum())
     if name.startswith(("sedov", "dmr-N3", "vortex-N3")):
         assert active > 0, "the case was chosen because the limiter engages"
+
+
+NW = dict(basis=GaussCollocation(), rhs=ESLimitedLowOrderPos(PROJ, PROJ))
+NODEWISE = {
+    "kh-N3": (lambda nw: P.kelvin_helmholtz(N=3, K=(6, 6), **nw), 10),            # examples/2D/kelvin-helmholtz.jl:44-55
+    "kh-N2": (lambda nw: P.kelvin_helmholtz(N=2, K=(8, 8), **nw), 10),
+    "sedov-N3": (lambda nw: P.sedov(N=3, K=(8, 8), **nw), 8),                     # examples/2D/sedov.jl
+    "dmr-N3-inflow-outflow": (lambda nw: P.dmr(N=3, K=(16, 4), **nw), 6),
+    "vortex-N3-underresolved": (lambda nw: P.vortex(N=3, K=(3, 3), T=10.0, **nw), 2),
+    "vortex-N4-underresolved": (lambda nw: P.vortex(N=4, K=(3, 3), T=10.0, **nw), 2),
+}
+
+
+@pytest.mark.parametrize("name", sorted(NODEWISE))
+def test_oracle_nodewise_projection_limiter_agrees_with_the_dense_restatement(name):
+    """The configuration of every shipped 2D example (Gauss collocation + NodewiseScaledExtrapolation + LaxFriedrichsOnProjectedVal +
+    subcell limiter): theta per face node (filter.jl:6-130; broken at the reference's HEAD by argument shadowing, oracle deviation
+    D4, so BOTH restatements follow the evident intent), the projection with theta (rhs.jl:113-133), find_alpha on the limited face
+    state, the limited face matrix in assemble_rhs! (flux_differencing.jl:288-319) and the limiter on top."""
+    from dense_rhs import dense_limited_rhs, dense_theta
+    from p2de_b200 import NodewiseScaledExtrapolation
+    make, nsteps = NODEWISE[name]
+    param, rd, md, dd, bc, U0 = P.setup(make(dict(NW, entropyproj_limiter=NodewiseScaledExtrapolation())))
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, n = dd.sizes.K, param.N + 1
+    for nstage in (1, 3):
+        dt_in = tp.CFL * tp.dt0
+        dt_o = orc.rhs(t, dt_in, nstage)
+        th_o = orc.field("theta_local").reshape(3, K, 4 * n)[nstage - 1]
+        if name not in ("kh-N2", "vortex-N4-underresolved"):
+            assert (th_o < 1.0).any(), "the case was chosen because the projection limiter engages"
+        th = dense_theta(param, dd, U)
+        # a bisection result is a multiple of 2^-21: the two agree exactly unless a bound test sits on a rounding boundary
+        assert np.abs(th - th_o).max() <= 2.0 ** -20 and (th == th_o).mean() > 0.99, name
+        assert np.array_equal(th == 1.0, th_o == 1.0)
+        assert np.abs(orc.field("theta").reshape(3, K)[nstage - 1] - th_o.sum(axis=1) / (4 * n)).max() < 1e-15      # filter.jl:57
+        d = dense_limited_rhs(param, dd, bc, U, t, dt_in, nstage, theta_local=th_o)
+        for f in ("rhsL", "rhsH", "rhsU"):
+            assert rel(d[f], orc.field(f)) < 1e-12, (name, nstage, f)
+        if nstage == 1:
+            assert abs(d["dt"] - dt_o) <= 1e-13 * dt_o
+        Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]
+        for mine, ref in ((d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))):
+            assert np.abs(mine - ref).max() < 1e-12 and np.array_equal(mine == 1.0, ref == 1.0), (name, nstage)

@@ -11,8 +11,8 @@ Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!
 (low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361),
 and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with PositivityBound as whole-array operations with the
 interface symmetrisation through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
-filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319).  Not covered: the other nine
-subcell bounds, shock capturing, 1D.
+filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  Not covered: the other nine subcell bounds
+and shock capturing.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -409,3 +409,185 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None):
     d["Lx"], d["Ly"] = Lx, Ly
     return d
 
+
+
+# ============================================================================================== 1D (Dim1), U[..., 3]
+def p1(g, U):
+    return (g - 1.0) * (U[..., 2] - 0.5 * U[..., 1] ** 2 / U[..., 0])
+
+
+def ws1(g, U):
+    return np.abs(U[..., 1] / U[..., 0]) + np.sqrt(g * p1(g, U) / U[..., 0])
+
+
+def flux1(g, U):
+    p = p1(g, U)
+    u = U[..., 1] / U[..., 0]
+    return np.stack([U[..., 1], U[..., 1] * u + p, u * (U[..., 2] + p)], axis=-1)
+
+
+def v_u1(g, U):
+    p = p1(g, U)
+    s = LOG(p / POW(U[..., 0], g))
+    return np.stack([(g + 1 - s) - (g - 1) * U[..., 2] / p, U[..., 1] * (g - 1) / p, -U[..., 0] * (g - 1) / p], axis=-1)
+
+
+def u_v1(g, V):
+    s = g - V[..., 0] + V[..., 1] ** 2 / (2 * V[..., 2])
+    rhoeV = POW((g - 1) / POW(-V[..., 2], g), 1 / (g - 1)) * EXP(-s / (g - 1))
+    return np.stack([-rhoeV * V[..., 2], rhoeV * V[..., 1], rhoeV * (1 - V[..., 1] ** 2 / (2 * V[..., 2]))], axis=-1)
+
+
+def fS1(g, rhoL, uL, bL, rlL, blL, rhoR, uR, bR, rlR, blR):
+    rholog, betalog = logmean(rhoL, rhoR, rlL, rlR), logmean(bL, bR, blL, blR)
+    rhoavg, uavg = 0.5 * (rhoL + rhoR), 0.5 * (uL + uR)
+    pa = rhoavg / (bL + bR)
+    f4aux = rholog / (2 * (g - 1) * betalog) + pa + 0.5 * rholog * (uL * uR)
+    F1 = rholog * uavg
+    return np.stack([F1, F1 * uavg + pa, f4aux * uavg], axis=-1)
+
+
+def rhoe1(U):
+    return U[..., 2] - 0.5 * U[..., 1] ** 2 / U[..., 0]
+
+
+def quad1(ZEROTOL, U, Pv, Lrhoe):
+    """rhoe_quadratic_solve with rhoe_quadratic_coefficients(::Dim1), limiter_utils.jl:52-83."""
+    a = Pv[..., 0] * Pv[..., 2] - 0.5 * Pv[..., 1] ** 2
+    b = U[..., 2] * Pv[..., 0] + U[..., 0] * Pv[..., 2] - U[..., 1] * Pv[..., 1] - Pv[..., 0] * Lrhoe
+    c = U[..., 2] * U[..., 0] - 0.5 * U[..., 1] ** 2 - U[..., 0] * Lrhoe
+    disc = b * b - 4 * a * c
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sq = np.sqrt(np.where(disc >= 0, disc, 0.0))
+        r1, r2 = (-b + sq) / (2 * a), (-b - sq) / (2 * a)
+        both = (r1 > ZEROTOL) & (r2 > ZEROTOL)
+        only1 = ~both & (r1 > ZEROTOL) & (r2 < -ZEROTOL)
+        only2 = ~both & ~only1 & (r2 > ZEROTOL) & (r1 < -ZEROTOL)
+        l = np.where(both, np.minimum(r1, r2), np.where(only1, r1, np.where(only2, r2, 1.0)))
+    return np.where(disc >= 0, l, 1.0)
+
+
+def lim1(ZEROTOL, U, Pv, Lrho, Lrhoe):
+    with np.errstate(divide="ignore", invalid="ignore"):
+        l = np.where(U[..., 0] + Pv[..., 0] < Lrho, np.maximum((Lrho - U[..., 0]) / Pv[..., 0], 0.0), 1.0)
+    return np.minimum(np.minimum(l, quad1(ZEROTOL, U, Pv, Lrhoe)), 1.0)
+
+
+def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1):
+    """rhs!(::LimitedDG) in 1D with NoEntropyProjectionLimiter, NoShockCapture, PositivityBound / Zhang-Shu: the same dense
+    restatement for Dim1 (the Dim1 methods of the files cited above; Bx(::Dim1) as evidently intended, rhs_utils.jl:13-19 passes its
+    arguments in the wrong order; the subcell symmetrisation pairs element k's first face with element k-1's last, periodically,
+    whatever the boundary conditions, subcell.jl:405-416)."""
+    g = param.equation.gamma
+    sz, ops, geom = dd.sizes, dd.ops, dd.geom
+    K, Nq, Nh = sz.K, sz.Nq, sz.Nh
+    tp = param.timestepping_param
+    zeta, ZEROTOL, POSTOL = param.limiting_param.zeta, param.global_constants.ZEROTOL, param.global_constants.POSTOL
+    fq2q = np.asarray(ops.fq2q) - 1
+    rxJ = np.asarray(geom.GJh[0], dtype=float)                                 # [K, Nh]
+    low_flux, high_flux, vol_flux = flux_options(param.rhs)
+    mapP = np.asarray(bc.mapP).reshape(K * 2) - 1
+    mapI = np.asarray(bc.mapI, dtype=np.int64).reshape(-1) - 1
+    mapO = np.asarray(bc.mapO, dtype=np.int64).reshape(-1) - 1
+    Ival = np.asarray(bc.Ival, dtype=float).reshape(-1, 3)
+    vq = v_u1(g, Uq)
+    utf = u_v1(g, np.einsum("fq,kqc->kfc", ops.Vf, vq))
+    u_tilde = np.concatenate([Uq, utf], axis=1)
+    Bx = rxJ[:, Nq:] * np.asarray(ops.Brs[0], dtype=float)                      # [K, 2]
+    nn = np.abs(Bx)
+    # ---- low order
+    Uf = utf if low_flux == T.SURFFLUX_LF_PROJECTED else Uq[:, fq2q]
+    fq_, ff_ = flux1(g, Uq), flux1(g, Uf)
+    wsf = ws1(g, Uf)
+    uP = Uf.reshape(K * 2, 3)[mapP].copy()
+    if len(mapI):
+        uP[mapI] = Ival
+    if len(mapO):
+        uP[mapO] = Uq[mapO // 2, fq2q[mapO % 2]]
+    uP = uP.reshape(K, 2, 3)
+    S0 = ops.Srs0[0]
+    Q0 = np.zeros((K, Nq, 3))
+    lam = np.zeros((K, Nq, Nq))
+    for (i1, j1) in ops.Srs0_nnz:
+        i, j = i1 - 1, j1 - 1
+        S = rxJ[:, i] * S0[i, j]
+        lij = np.abs(S) * np.maximum(ws1(g, Uq[:, i]), ws1(g, Uq[:, j]))
+        lam[:, i, j] = lam[:, j, i] = lij
+        SF = 2.0 * S[:, None] * (0.5 * (fq_[:, i] + fq_[:, j])) - lij[:, None] * (Uq[:, j] - Uq[:, i])
+        Q0[:, i] += SF
+        Q0[:, j] -= SF
+    rL = -Q0
+    lamB = 0.5 * nn * np.maximum(wsf, wsf.reshape(K * 2)[mapP].reshape(K, 2))
+    BF_L = Bx[..., None] * (0.5 * (ff_ + flux1(g, uP))) - lamB[..., None] * (uP - Uf)
+    for f in range(2):
+        rL[:, fq2q[f]] -= BF_L[:, f]
+    wJ = np.asarray(geom.Jq, dtype=float) * np.asarray(ops.wq)[None, :]
+    rhsL = rL / wJ[..., None]
+    d = {"rhsL": rhsL}
+    if nstage == 1:
+        lam_i = lam.sum(axis=2)
+        lamB_cfl = lamB
+        if low_flux == T.SURFFLUX_LF_PROJECTED:
+            ui, ut = Uq[:, fq2q], utf
+            pad = lambda a: np.concatenate([a[..., :2], np.zeros_like(a[..., :1]), a[..., 2:]], axis=-1)   # (rho, m, 0, E) for the 2D helper
+            lamB_cfl = find_alpha(POSTOL, pad(ui), pad(ut)) * lamB + 0.5 * nn * wsf
+        for i in range(Nq):
+            for f1 in ops.q2fq[i]:
+                lam_i[:, i] += lamB_cfl[:, f1 - 1]
+        d["dt"] = min(min(tp.CFL * tp.dt0, tp.T - t), float((tp.CFL * 0.5 * wJ / lam_i).min()))
+    # ---- high order
+    beta = u_tilde[..., 0] / (2 * p1(g, u_tilde))
+    rl, bl = LOG(u_tilde[..., 0]), LOG(beta)
+    uu = u_tilde[..., 1] / u_tilde[..., 0]
+    lamf = ws1(g, utf)
+    LFc = (0.5 * nn * np.maximum(lamf, lamf.reshape(K * 2)[mapP].reshape(K, 2))).reshape(K * 2)
+    uPh = utf.reshape(K * 2, 3)[mapP].copy()
+    if len(mapI):
+        LFc[mapI] = 0.0
+        uPh[mapI] = Ival
+    if len(mapO):
+        LFc[mapO] = 0.0
+        uPh[mapO] = Uq[mapO // 2, fq2q[mapO % 2]]
+    LFc, uPh = LFc.reshape(K, 2), uPh.reshape(K, 2, 3)
+    Sh = rxJ[:, :, None] * np.asarray(ops.Srsh_db[0])[None]
+    if vol_flux == T.VOLFLUX_CENTRAL:
+        fh = flux1(g, u_tilde)
+        Fij = 0.5 * (fh[:, :, None] + fh[:, None, :])
+    else:
+        L = lambda a: a[:, :, None]
+        R = lambda a: a[:, None, :]
+        Fij = fS1(g, L(u_tilde[..., 0]), L(uu), L(beta), L(rl), L(bl), R(u_tilde[..., 0]), R(uu), R(beta), R(rl), R(bl))
+    QF1 = np.einsum("kij,kijc->kic", Sh, Fij)
+    if high_flux == T.SURFFLUX_CHANDRASHEKAR_PROJECTED:
+        bP = uPh[..., 0] / (2 * p1(g, uPh))
+        fstar = fS1(g, utf[..., 0], utf[..., 1] / utf[..., 0], beta[:, Nq:], rl[:, Nq:], bl[:, Nq:],
+                    uPh[..., 0], uPh[..., 1] / uPh[..., 0], bP, LOG(uPh[..., 0]), LOG(bP))
+    else:
+        fstar = 0.5 * (flux1(g, utf) + flux1(g, uPh))
+    BF_H = Bx[..., None] * fstar - LFc[..., None] * (uPh - utf)
+    rhsH = -(np.einsum("qh,khc->kqc", ops.MinvVhT, QF1) + np.einsum("qf,kfc->kqc", ops.MinvVfT, BF_H)) / np.asarray(geom.Jq, dtype=float)[..., None]
+    d["rhsH"] = rhsH
+    # ---- limiter
+    uL = Uq + dt * rhsL
+    if param.rhs_limiter.code == T.LIMITER_ZHANGSHU:
+        l = lim1(ZEROTOL, uL, dt * (rhsH - rhsL), zeta * uL[..., 0], zeta * rhoe1(uL)).min(axis=1)
+        d["L"], d["rhsU"] = l, (1 - l)[:, None, None] * rhsL + l[:, None, None] * rhsH
+        return d
+    fH, fL = np.zeros((K, Nq + 1, 3)), np.zeros((K, Nq + 1, 3))       # accumulate_f_bar!(::Dim1) :144-161
+    fH[:, 0], fL[:, 0] = BF_H[:, 0], BF_L[:, 0]
+    for i in range(1, Nq + 1):
+        fH[:, i] = fH[:, i - 1] + wJ[:, i - 1, None] * rhsH[:, i - 1]
+        fL[:, i] = fL[:, i - 1] + wJ[:, i - 1, None] * rhsL[:, i - 1]
+    df = fH - fL
+    Lrho, Lrhoe = zeta * uL[..., 0], zeta * rhoe1(uL)
+    Ll = np.ones((K, Nq + 1))                                         # subcell_bound_limiter!(::Dim1) :208-246
+    Ll[:, :Nq] = np.minimum(Ll[:, :Nq], lim1(ZEROTOL, uL, -2 * dt * df[:, :Nq] / wJ[..., None], Lrho, Lrhoe))
+    Ll[:, 1:] = np.minimum(Ll[:, 1:], lim1(ZEROTOL, uL, 2 * dt * df[:, 1:] / wJ[..., None], Lrho, Lrhoe))
+    first, last = Ll[:, 0].copy(), Ll[:, Nq].copy()                   # symmetrize_limiting_parameters!(::Dim1) :405-416
+    l = np.minimum(first, np.roll(last, 1))
+    Ll[:, 0] = l
+    Ll[:, Nq] = np.roll(l, -1)
+    flim = Ll[..., None] * fH + (1 - Ll[..., None]) * fL
+    d["rhsU"] = (flim[:, 1:] - flim[:, :-1]) / wJ[..., None]
+    d["Ll"] = Ll
+    return d

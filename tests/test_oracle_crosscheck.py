@@ -215,3 +215,49 @@ def test_oracle_nodewise_projection_limiter_agrees_with_the_dense_restatement(na
         Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]
         for mine, ref in ((d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))):
             assert np.abs(mine - ref).max() < 1e-12 and np.array_equal(mine == 1.0, ref == 1.0), (name, nstage)
+
+
+ONE_D = {
+    "sod-N3-early": (lambda: P.sod(N=3, K=40), 2, True),                      # BASELINE.json configs[0] (at 40 elements)
+    "sod-N3": (lambda: P.sod(N=3, K=40), 30, False),
+    "sod-N2-zhangshu": (lambda: P.sod(N=2, K=50, limiter=ZhangShuLimiter()), 30, False),
+    "sod-N1": (lambda: P.sod(N=1, K=64), 10, False),
+    "sod-N4-gauss-projected": (lambda: P.sod(N=4, K=32, basis=GaussCollocation(), rhs=ESLimitedLowOrderPos(PROJ, PROJ)), 10, False),
+    "sod-N3-chandrashekar-surface": (lambda: P.sod(N=3, K=40, rhs=ESLimitedLowOrderPos(LaxFriedrichsOnNodalVal(), ChandrashekarOnProjectedVal())), 10, False),
+    "shu-osher-N3": (lambda: P.shu_osher(N=3, K=64), 40, False),              # configs[1]
+    "leblanc-N2": (lambda: P.leblanc(N=2, K=100), 3, True),                   # configs[1], examples/convergence/leblanc-convergence.jl
+    "leblanc-N3-initial": (lambda: P.leblanc(N=3, K=50), 0, True),
+    "density-wave-N3-periodic": (lambda: P.density_wave_1d(N=3, K=16), 5, False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ONE_D))
+def test_oracle_1d_agrees_with_the_dense_restatement(name):
+    """The Dim1 methods (SURVEY.md 8f-3): rhsL, rhsH, dt, the limiter's coefficients and rhsU of one rhs!(::LimitedDG)."""
+    from dense_rhs import dense_limited_rhs_1d
+    make, nsteps, expect_active = ONE_D[name]
+    param, rd, md, dd, bc, U0 = P.setup(make())
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, Nq = dd.sizes.K, dd.sizes.Nq
+    for nstage in (1, 2, 3):
+        dt_in = tp.CFL * tp.dt0
+        dt_o = orc.rhs(t, dt_in, nstage)
+        d = dense_limited_rhs_1d(param, dd, bc, U, t, dt_in, nstage)
+        for f in ("rhsL", "rhsH", "rhsU"):
+            assert rel(d[f], orc.field(f)) < 1e-12, (name, nstage, f)
+        if nstage == 1:
+            assert abs(d["dt"] - dt_o) <= 1e-13 * dt_o
+        if "L" in d:
+            mine, ref = d["L"], orc.field("L").reshape(3, K)[nstage - 1]
+        else:       # L_local is allocated [Nq + N1D, Nd, K, Ns] in 1D as well (init.jl); the first Nq + 1 entries are the subcell faces
+            mine, ref = d["Ll"], orc.field("L_local").reshape(3, K, -1)[nstage - 1][:, :Nq + 1]
+        assert np.abs(mine - ref).max() < 1e-12 and np.array_equal(mine == 1.0, ref == 1.0), (name, nstage)
+        if expect_active:
+            assert (ref < 1.0).any()

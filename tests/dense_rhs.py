@@ -9,10 +9,11 @@ the C++ oracle (tests/test_oracle_crosscheck.py).  It shares no code and no stru
 
 Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!` including the CFL dt and `find_alpha`
 (low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361),
-and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with PositivityBound as whole-array operations with the
-interface symmetrisation through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
-filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  Not covered: the other nine subcell bounds
-and shock capturing.
+and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with the positivity, minimum-entropy (plain / relaxed) and
+TVD bounds and their combinations, with or without Hennemann shock capturing, as whole-array operations with the interface
+symmetrisation and the low-order stencils through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
+filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  Not covered: the four cell-entropy bounds
+(`enforce_ES_subcell!`, a serial greedy algorithm with no second form to write it in) and those bounds in 1D.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -340,35 +341,143 @@ def rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe):
     return np.where(disc >= 0, l, 1.0)
 
 
-def limiting_param_rho_rhoe(ZEROTOL, U, Pv, Lrho, Lrhoe):
-    """limiting_param_bound_rho_rhoe with Urho = Urhoe = Inf (PositivityBound, Zhang-Shu)."""
-    with np.errstate(divide="ignore", invalid="ignore"):
-        l = np.where(U[..., 0] + Pv[..., 0] < Lrho, np.maximum((Lrho - U[..., 0]) / Pv[..., 0], 0.0), 1.0)
-    return np.minimum(np.minimum(l, rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe)), 1.0)
-
-
 def rhoe_ufun(U):
     return U[..., 3] - 0.5 * (U[..., 1] ** 2 + U[..., 2] ** 2) / U[..., 0]
 
 
-def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None):
-    """rhs!(::LimitedDG) with NoShockCapture: dense_rhs + apply_rhs_limiter! (Zhang-Shu: zhangshu.jl:4-45; subcell with
-    PositivityBound: subcell.jl:163-349, 418-456, 841-924), vectorised over elements and subcell faces, neighbours through mapP.
-    `dt` is the dt the limiter sees (the caller's, rhs.jl:46,52).  Adds rhsU and L [K] or Lx [K, N1D, N1D+1], Ly [K, N1D+1, N1D]."""
+def limiting_param_bounds(ZEROTOL, U, Pv, Lrho, Lrhoe, Urho=None):
+    """limiting_param_bound_rho_rhoe (limiter_utils.jl:26-40) with an optional finite upper density bound (TVD bounds); Urhoe = Inf."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        l = np.where(U[..., 0] + Pv[..., 0] < Lrho, np.maximum((Lrho - U[..., 0]) / Pv[..., 0], 0.0), 1.0)
+        if Urho is not None:
+            l = np.where(U[..., 0] + Pv[..., 0] > Urho, np.minimum(l, np.maximum((Urho - U[..., 0]) / Pv[..., 0], 0.0)), l)
+    return np.minimum(np.minimum(l, rhoe_quadratic_solve(ZEROTOL, U, Pv, Lrhoe)), 1.0)
+
+
+def s_modified(g, U):
+    """s_modified_ufun :80-85 (a negative density gives NaN, which fails the bound test)."""
+    return rhoe_ufun(U) * POW(U[..., 0], -g)
+
+
+def limiting_param_phi(g, POSTOL, U, Pv, Lphi, lpos):
+    """limiting_param_bound_phi (limiter_utils.jl:42-50): bisection(f, 0, lpos), nonlinear_solvers.jl:3-20, all entries at once."""
+    def f(l):
+        with np.errstate(all="ignore"):
+            return s_modified(g, U + l[..., None] * Pv) >= Lphi - POSTOL
+    top = f(lpos)
+    xv, xi = np.zeros_like(lpos), lpos.copy()
+    for _ in range(21):
+        xn = 0.5 * (xv + xi)
+        good = f(xn)
+        xv = np.where(good, xn, xv)
+        xi = np.where(good, xi, xn)
+    return np.where(top, lpos, xv)
+
+
+def smoothness_indicator(param, dd, Uq):
+    """initialize_smoothness_indicator!(::Dim2) shock_capture.jl:47-94: modal energies of rho p in the two highest modes."""
+    g, N = param.equation.gamma, param.N
+    modal = np.einsum("mq,kq->km", dd.ops.VDM_inv, Uq[..., 0] * pfun(g, Uq))
+    e = (modal ** 2).reshape(-1, N + 1, N + 1)                                 # [K, j, i]
+    ii, jj = np.meshgrid(np.arange(N + 1), np.arange(N + 1))
+    eN = np.where((ii == N) | (jj == N), e, 0.0).reshape(len(e), -1)
+    eNm1 = np.where((ii == N - 1) | (jj == N - 1), e, 0.0).reshape(len(e), -1)
+    tot = e.reshape(len(e), -1)
+    sN, sNm1, st = np.zeros(len(e)), np.zeros(len(e)), np.zeros(len(e))
+    for m in range(tot.shape[1]):                                              # the reference's accumulation order
+        sN, sNm1, st = sN + eN[:, m], sNm1 + eNm1[:, m], st + tot[:, m]
+    return np.maximum(sN / st, sNm1 / st)
+
+
+def stencil_neighbours(dd, bc, n):
+    """low_order_stencil(::Dim2) limiter_utils.jl:222-231 for every node: (k, node) of the left / right / bottom / top stencil
+    node, across element faces through q2fq, mapP and fq2q (quad_index_to_quad_index_P :197-210).  -> kN, qN [K, Nq, 4]"""
+    K, Nq, Nfp = dd.sizes.K, dd.sizes.Nq, dd.sizes.Nfp
+    mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
+    fq2q = np.asarray(dd.ops.fq2q) - 1
+    kN = np.empty((K, Nq, 4), dtype=np.int64)
+    qN = np.empty((K, Nq, 4), dtype=np.int64)
+    kk = np.arange(K)
+    for q in range(Nq):
+        i, j = q % n, q // n
+        faces = [f - 1 for f in dd.ops.q2fq[q]]
+        for s_, (inside, qin, direction) in enumerate(((i - 1 >= 0, q - 1, 0), (i + 1 <= n - 1, q + 1, 0),
+                                                       (j - 1 >= 0, q - n, 1), (j + 1 <= n - 1, q + n, 1))):
+            if inside:
+                kN[:, q, s_], qN[:, q, s_] = kk, qin
+            else:
+                f = faces[0] if len(faces) == 1 else faces[direction]
+                P = mapP[:, f]
+                kN[:, q, s_], qN[:, q, s_] = P // Nfp, fq2q[P % Nfp]
+    return kN, qN
+
+
+def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin=None):
+    """rhs!(::LimitedDG): dense_rhs + apply_rhs_limiter! (limiter.jl:8-56) -- Zhang-Shu (zhangshu.jl:4-45) or the subcell limiter
+    (subcell.jl:4-349, 418-456, 841-924) with PositivityBound, the minimum-entropy bounds (plain / relaxed), the TVD bounds and their
+    combinations, with or without HennemannShockCapture (shock_capture.jl) -- as whole-array operations, neighbours through mapP.
+    `dt` is the dt the limiter sees (the caller's, rhs.jl:46,52); `smin` the minimum of s_modified over the initial condition
+    (subcell.jl:31-34: recorded at t == t0, nstage == 1).  The cell-entropy bounds are not restated here.
+    Adds rhsU and L [K] or Lx [K, N1D, N1D+1], Ly [K, N1D+1, N1D]."""
     d = dense_rhs(param, dd, bc, Uq, t, nstage, theta_local)
-    zeta, ZEROTOL = param.limiting_param.zeta, param.global_constants.ZEROTOL
+    g = param.equation.gamma
+    zeta, ZEROTOL, POSTOL = param.limiting_param.zeta, param.global_constants.ZEROTOL, param.global_constants.POSTOL
     sz = dd.sizes
     K, Nq, Nfp = sz.K, sz.Nq, sz.Nfp
     n = param.N + 1
+    lim = param.rhs_limiter
+    subcell = lim.code == T.LIMITER_SUBCELL
+    bcode = lim.bound.code if subcell else T.BOUND_POSITIVITY
+    if bcode in (T.BOUND_POS_CELL_ENTROPY, T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY):
+        raise NotImplementedError("cell-entropy bounds")
+    tvd = bcode >= T.BOUND_TVD
+    minent = bcode in (T.BOUND_POS_MIN_ENTROPY, T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
+    relaxed = bcode in (T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
+    hen = lim.shockcapture.code == T.SHOCKCAPTURE_HENNEMANN
+    blend = np.ones(K)
+    if hen or relaxed:
+        sigma = smoothness_indicator(param, dd, Uq)
+    if hen:                                                                    # update_blending_factor! shock_capture.jl:111-132
+        TN = lim.shockcapture.a * 10 ** (-lim.shockcapture.c * (param.N + 1) ** 0.25)
+        s_factor = math.log((1 - 0.0001) / 0.0001)
+        blend = np.maximum(np.minimum(1.0 - 1.0 / (1.0 + EXP(-s_factor / TN * (sigma - TN))), 1.0), 0.5)
+    d["blending_factor"] = blend
     uL = Uq + dt * d["rhsL"]
-    if param.rhs_limiter.code == T.LIMITER_ZHANGSHU:
+    if not subcell:
         Pv = dt * (d["rhsH"] - d["rhsL"])
-        l = limiting_param_rho_rhoe(ZEROTOL, uL, Pv, zeta * uL[..., 0], zeta * rhoe_ufun(uL)).min(axis=1)
-        d["L"] = l
+        L = limiting_param_bounds(ZEROTOL, uL, Pv, zeta * uL[..., 0], zeta * rhoe_ufun(uL)).min(axis=1)
+        l = np.minimum(L, blend)
+        d["L"] = L
         d["rhsU"] = (1 - l)[:, None, None] * d["rhsL"] + l[:, None, None] * d["rhsH"]
         return d
+    if minent or tvd:
+        kN, qN = stencil_neighbours(dd, bc, n)
+    Lphi = None
+    if minent:                                                                 # initialize_entropy_bounds! subcell.jl:14-75
+        sm = s_modified(g, Uq)
+        lb = np.minimum(sm, sm[kN, qN].min(axis=2))
+        if relaxed:                                                            # update_smoothness_factor! :937-956
+            s0, sk = math.log10(float(param.N) ** -4), np.log10(sigma)
+            epsk = np.where(sk < s0 - 1.0, 0.0, np.where(sk > s0 + 1.0, 1.0, 0.5 - 0.5 * np.sin(math.pi * (sk - s0) / 2.0)))
+        else:
+            epsk = np.ones(K)
+        Lphi = (epsk[:, None] * lb + (1 - epsk[:, None]) * smin).reshape(K, n, n)
+        d["lbound_s_modified"] = Lphi.reshape(K, Nq)
     wJ = d["wJ"].reshape(K, n, n)                                     # [K, jq, iq]
     uLg = uL.reshape(K, n, n, 4)
+    Lrho, Urho = zeta * uLg[..., 0], None
+    if tvd:                                                                    # initialize_TVD_bounds! :112-141
+        rhoL = Uq[..., 0] + dt * d["rhsL"][..., 0]
+        nb = rhoL[kN, qN]
+        Lrho = np.minimum(rhoL, nb.min(axis=2)).reshape(K, n, n)
+        Urho = np.maximum(rhoL, nb.max(axis=2)).reshape(K, n, n)
+    Lrhoe = zeta * rhoe_ufun(uLg)
+
+    def coef(Pv):                                                              # limiting_param limiter_utils.jl:4-24
+        l = limiting_param_bounds(ZEROTOL, uLg, Pv, Lrho, Lrhoe, Urho)
+        if minent:
+            l = limiting_param_phi(g, POSTOL, uLg, Pv, Lphi, l)
+        return l
     rH, rL = d["rhsxyH"].reshape(K, n, n, 2, 4), d["rhsxyL"].reshape(K, n, n, 2, 4)
     fb = {}
     for name, r, BF in (("H", rH, d["BF_H"]), ("L", rL, d["BF_L"])):  # accumulate_f_bar! :163-206 (running sums, in this order)
@@ -382,13 +491,13 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None):
             fy[:, sj] = fy[:, sj - 1] + wJ[:, sj - 1, :, None] * r[:, sj - 1, :, 1]
         fb[name] = (fx, fy)
     dfx, dfy = fb["H"][0] - fb["L"][0], fb["H"][1] - fb["L"][1]
-    Lrho, Lrhoe = zeta * uLg[..., 0], zeta * rhoe_ufun(uLg)
     Lx, Ly = np.ones((K, n, n + 1)), np.ones((K, n + 1, n))          # subcell_bound_limiter! :248-349
     # x: subcell face si is the LEFT face of node si (P = -4 dt df / wJ) and the RIGHT face of node si - 1 (P = +4 dt df / wJ)
-    Lx[:, :, :n] = np.minimum(Lx[:, :, :n], limiting_param_rho_rhoe(ZEROTOL, uLg, -4 * dt * dfx[:, :, :n] / wJ[..., None], Lrho, Lrhoe))
-    Lx[:, :, 1:] = np.minimum(Lx[:, :, 1:], limiting_param_rho_rhoe(ZEROTOL, uLg, 4 * dt * dfx[:, :, 1:] / wJ[..., None], Lrho, Lrhoe))
-    Ly[:, :n] = np.minimum(Ly[:, :n], limiting_param_rho_rhoe(ZEROTOL, uLg, -4 * dt * dfy[:, :n] / wJ[..., None], Lrho, Lrhoe))
-    Ly[:, 1:] = np.minimum(Ly[:, 1:], limiting_param_rho_rhoe(ZEROTOL, uLg, 4 * dt * dfy[:, 1:] / wJ[..., None], Lrho, Lrhoe))
+    Lx[:, :, :n] = np.minimum(Lx[:, :, :n], coef(-4 * dt * dfx[:, :, :n] / wJ[..., None]))
+    Lx[:, :, 1:] = np.minimum(Lx[:, :, 1:], coef(4 * dt * dfx[:, :, 1:] / wJ[..., None]))
+    Ly[:, :n] = np.minimum(Ly[:, :n], coef(-4 * dt * dfy[:, :n] / wJ[..., None]))
+    Ly[:, 1:] = np.minimum(Ly[:, 1:], coef(4 * dt * dfy[:, 1:] / wJ[..., None]))
+    Lx, Ly = np.minimum(Lx, blend[:, None, None]), np.minimum(Ly, blend[:, None, None])       # "Apply shock capturing" :344-347
     # symmetrize_limiting_parameters! :418-456, partner faces through mapP (limiter_utils.jl:122-181)
     mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
     Lx0, Ly0 = Lx.copy(), Ly.copy()
@@ -408,7 +517,6 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None):
     d["rhsU"] = (rx + ry).reshape(K, Nq, 4)
     d["Lx"], d["Ly"] = Lx, Ly
     return d
-
 
 
 # ============================================================================================== 1D (Dim1), U[..., 3]

@@ -261,3 +261,60 @@ def test_oracle_1d_agrees_with_the_dense_restatement(name):
         assert np.abs(mine - ref).max() < 1e-12 and np.array_equal(mine == 1.0, ref == 1.0), (name, nstage)
         if expect_active:
             assert (ref < 1.0).any()
+
+
+def _variants():
+    from p2de_b200 import (HennemannShockCapture, PositivityAndMinEntropyBound, PositivityAndRelaxedMinEntropyBound, PositivityBound,
+                           SubcellLimiter, TVDAndMinEntropyBound, TVDAndRelaxedMinEntropyBound, TVDBound)
+    return {
+        "subcell-hennemann": SubcellLimiter(bound=PositivityBound(), shockcapture=HennemannShockCapture()),      # test/test_smoke.jl:44-52
+        "subcell-minentropy": SubcellLimiter(bound=PositivityAndMinEntropyBound()),
+        "subcell-relaxed-minentropy": SubcellLimiter(bound=PositivityAndRelaxedMinEntropyBound()),
+        "zhangshu-hennemann": ZhangShuLimiter(shockcapture=HennemannShockCapture()),
+        "subcell-tvd": SubcellLimiter(bound=TVDBound()),
+        "subcell-tvd-minentropy": SubcellLimiter(bound=TVDAndMinEntropyBound()),
+        "subcell-tvd-relaxed-minentropy-hennemann": SubcellLimiter(bound=TVDAndRelaxedMinEntropyBound(), shockcapture=HennemannShockCapture()),
+    }
+
+
+BOUND_PROBLEMS = {
+    "kh-N3": (lambda lim: P.kelvin_helmholtz(N=3, K=(6, 6), limiter=lim), 4),
+    "sedov-N3": (lambda lim: P.sedov(N=3, K=(8, 8), limiter=lim), 6),
+    "dmr-N2": (lambda lim: P.dmr(N=2, K=(16, 4), limiter=lim), 4),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(_variants()))
+@pytest.mark.parametrize("problem", sorted(BOUND_PROBLEMS))
+def test_oracle_bounds_and_shock_capturing_agree_with_the_dense_restatement(problem, variant):
+    """minimum-entropy bounds (stencil minimum across element faces, relaxation towards the global minimum at t0,
+    21-step bisection on s_modified; subcell.jl:14-75, limiter_utils.jl:42-50), TVD bounds (density of the low-order update over
+    the stencil; subcell.jl:112-141, 359-368), the modal smoothness indicator with Hennemann's blending factor and the smoothness
+    factor of the relaxed bounds (shock_capture.jl:47-132, subcell.jl:937-956), on non-isentropic states the oracle has advanced."""
+    from dense_rhs import dense_limited_rhs, s_modified
+    make, nsteps = BOUND_PROBLEMS[problem]
+    param, rd, md, dd, bc, U0 = P.setup(make(_variants()[variant]))
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    smin = float(s_modified(param.equation.gamma, U0).min())          # what the first stage at t0 records (subcell.jl:31-34)
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, n = dd.sizes.K, param.N + 1
+    for nstage in (1, 2):
+        dt_in = tp.CFL * tp.dt0
+        orc.rhs(t, dt_in, nstage)
+        d = dense_limited_rhs(param, dd, bc, U, t, dt_in, nstage, smin=smin)
+        assert rel(d["rhsU"], orc.field("rhsU")) < 1e-12, (problem, variant, nstage)
+        if "L" in d:
+            pairs = [(d["L"], orc.field("L").reshape(3, K)[nstage - 1])]
+        else:
+            Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]
+            pairs = [(d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))]
+            assert (Lo < 1.0).any(), "the bound was chosen because it engages on this state"
+        for mine, ref in pairs:
+            # (a bisection result may flip by one step, 2^-21 of its bracket, where its predicate sits on a rounding boundary)
+            assert (np.abs(mine - ref) > 1e-12).mean() < 0.01 and np.abs(mine - ref).max() < 1e-5, (problem, variant, nstage)

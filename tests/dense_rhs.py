@@ -12,8 +12,9 @@ Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!
 and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with the positivity, minimum-entropy (plain / relaxed) and
 TVD bounds and their combinations, with or without Hennemann shock capturing, as whole-array operations with the interface
 symmetrisation and the low-order stencils through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
-filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  Not covered: the four cell-entropy bounds
-(`enforce_ES_subcell!`, a serial greedy algorithm with no second form to write it in) and those bounds in 1D.
+filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  The four cell-entropy bounds on Lobatto
+nodes are restated element by element (`es_volume`).  Not covered: the interface part of the cell-entropy bounds on Gauss nodes
+(order-dependent in the reference itself, oracle deviation D5) and the bounds other than PositivityBound in 1D.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -412,12 +413,79 @@ def stencil_neighbours(dd, bc, n):
     return kN, qN
 
 
+def smooth_factor(param, sigma):
+    """update_smoothness_factor! of the relaxed bounds, subcell.jl:937-956."""
+    s0, sk = math.log10(float(param.N) ** -4), np.log10(sigma)
+    return np.where(sk < s0 - 1.0, 0.0, np.where(sk > s0 + 1.0, 1.0, 0.5 - 0.5 * np.sin(math.pi * (sk - s0) / 2.0)))
+
+
+def es_volume(param, dd, Uq, d, fb, Lx, Ly, epsk, bound):
+    """enforce_ES_subcell! on Lobatto nodes = initialize_ES_subcell_limiting! + enforce_ES_subcell_volume! (subcell.jl:508-565,
+    630-743; the interface part is a no-op there, :755-757): per element and direction, if the entropy production estimate of the
+    positivity-limited interior subcell fluxes exceeds its budget, the faces with the largest production are switched off in
+    descending (value, index) order, the last one partially.  Element by element (the greedy step is inherently serial); Lx, Ly are
+    updated in place."""
+    g, ZEROTOL = param.equation.gamma, param.global_constants.ZEROTOL
+    K, Nq, Nfp = dd.sizes.K, dd.sizes.Nq, dd.sizes.Nfp
+    n = param.N + 1
+    ops, geom = dd.ops, dd.geom
+    fq2q = np.asarray(ops.fq2q) - 1
+    rxJ, sxJ, ryJ, syJ = (np.asarray(a, dtype=float) for a in geom.GJh)
+    Br, Bs = (np.asarray(b, dtype=float) for b in ops.Brs)
+    Bxy = np.stack([rxJ[:, Nq:] * Br + sxJ[:, Nq:] * Bs, ryJ[:, Nq:] * Br + syJ[:, Nq:] * Bs], axis=-1)
+    vq = v_ufun(g, Uq).reshape(K, n, n, 4)                                     # [K, j, i]
+    psif = (g - 1.0) * Uq[:, fq2q][..., 1:3]                                   # psi_ufun :126-129 at the face nodes' volume nodes
+    relaxed = bound.code in (T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
+    for k in range(K):
+        sB = np.zeros(2)
+        for f in range(Nfp):
+            sB = sB + Bxy[k, f] * psif[k, f]
+        for dirn in (0, 1):
+            fH, fL = fb["H"][dirn][k], fb["L"][dirn][k]                        # x: [sj, si, 4]; y: [sj, si, 4]
+            L = Lx[k] if dirn == 0 else Ly[k]
+            faces = []                                                         # (flat index in the reference's dvdf order, sj, si)
+            if dirn == 0:
+                for sj in range(n):
+                    for si in range(1, n):
+                        faces.append(((si - 1) + sj * (n - 1), sj, si, vq[k, sj, si - 1] - vq[k, sj, si]))
+                visit = faces                                                  # sums run sj outer, si inner (:653-658)
+            else:
+                for sj in range(1, n):
+                    for si in range(n):
+                        faces.append((si + (sj - 1) * n, sj, si, vq[k, sj - 1, si] - vq[k, sj, si]))
+                visit = sorted(faces, key=lambda r: (r[2], r[1]))              # sums run si outer, sj inner (:663-668)
+            dvdf = {r[0]: float(np.sum(r[3] * (fH[r[1], r[2]] - fL[r[1], r[2]]))) for r in faces}
+            sdvfL, spos = 0.0, 0.0
+            for r in visit:
+                sdvfL += float(np.sum(r[3] * fL[r[1], r[2]]))
+            for r in visit:
+                spos += L[r[1], r[2]] * dvdf[r[0]]
+            budget = sB[dirn] - sdvfL
+            rhs_ = (1 - bound.beta * epsk[k]) * budget if relaxed else budget  # rhs_es :746-753
+            tol = max(0.0, sdvfL - sB[dirn])
+            if not (spos - rhs_ > tol):
+                continue
+            where = {r[0]: (r[1], r[2]) for r in faces}
+            order = sorted(dvdf, key=lambda e: (dvdf[e], e), reverse=True)     # sort!(..., rev=true) on (value, index) tuples
+            lhs, taken = spos, []
+            for e in order:
+                if not lhs > rhs_ + tol:
+                    break
+                if dvdf[e] < ZEROTOL:
+                    break
+                lhs = lhs - L[where[e]] * dvdf[e]
+                taken.append(e)
+            for m, e in enumerate(taken):
+                l_new = max((rhs_ + tol - lhs) / dvdf[e], 0.0) if m == len(taken) - 1 else 0.0
+                L[where[e]] = min(L[where[e]], l_new)
+
+
 def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin=None):
     """rhs!(::LimitedDG): dense_rhs + apply_rhs_limiter! (limiter.jl:8-56) -- Zhang-Shu (zhangshu.jl:4-45) or the subcell limiter
     (subcell.jl:4-349, 418-456, 841-924) with PositivityBound, the minimum-entropy bounds (plain / relaxed), the TVD bounds and their
     combinations, with or without HennemannShockCapture (shock_capture.jl) -- as whole-array operations, neighbours through mapP.
     `dt` is the dt the limiter sees (the caller's, rhs.jl:46,52); `smin` the minimum of s_modified over the initial condition
-    (subcell.jl:31-34: recorded at t == t0, nstage == 1).  The cell-entropy bounds are not restated here.
+    (subcell.jl:31-34: recorded at t == t0, nstage == 1).  Cell-entropy bounds: Lobatto nodes only (`es_volume`).
     Adds rhsU and L [K] or Lx [K, N1D, N1D+1], Ly [K, N1D+1, N1D]."""
     d = dense_rhs(param, dd, bc, Uq, t, nstage, theta_local)
     g = param.equation.gamma
@@ -428,14 +496,16 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin
     lim = param.rhs_limiter
     subcell = lim.code == T.LIMITER_SUBCELL
     bcode = lim.bound.code if subcell else T.BOUND_POSITIVITY
-    if bcode in (T.BOUND_POS_CELL_ENTROPY, T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY):
-        raise NotImplementedError("cell-entropy bounds")
+    cell = bcode in (T.BOUND_POS_CELL_ENTROPY, T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
+    relaxed_cell = bcode in (T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
+    if cell and param.approximation_basis.code == T.BASIS_GAUSS:
+        raise NotImplementedError("cell-entropy bounds on Gauss nodes (enforce_ES_subcell_interface!, subcell.jl:759-805)")
     tvd = bcode >= T.BOUND_TVD
     minent = bcode in (T.BOUND_POS_MIN_ENTROPY, T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
     relaxed = bcode in (T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
     hen = lim.shockcapture.code == T.SHOCKCAPTURE_HENNEMANN
     blend = np.ones(K)
-    if hen or relaxed:
+    if hen or relaxed or relaxed_cell:
         sigma = smoothness_indicator(param, dd, Uq)
     if hen:                                                                    # update_blending_factor! shock_capture.jl:111-132
         TN = lim.shockcapture.a * 10 ** (-lim.shockcapture.c * (param.N + 1) ** 0.25)
@@ -456,11 +526,7 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin
     if minent:                                                                 # initialize_entropy_bounds! subcell.jl:14-75
         sm = s_modified(g, Uq)
         lb = np.minimum(sm, sm[kN, qN].min(axis=2))
-        if relaxed:                                                            # update_smoothness_factor! :937-956
-            s0, sk = math.log10(float(param.N) ** -4), np.log10(sigma)
-            epsk = np.where(sk < s0 - 1.0, 0.0, np.where(sk > s0 + 1.0, 1.0, 0.5 - 0.5 * np.sin(math.pi * (sk - s0) / 2.0)))
-        else:
-            epsk = np.ones(K)
+        epsk = smooth_factor(param, sigma) if relaxed else np.ones(K)
         Lphi = (epsk[:, None] * lb + (1 - epsk[:, None]) * smin).reshape(K, n, n)
         d["lbound_s_modified"] = Lphi.reshape(K, Nq)
     wJ = d["wJ"].reshape(K, n, n)                                     # [K, jq, iq]
@@ -498,6 +564,8 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin
     Ly[:, :n] = np.minimum(Ly[:, :n], coef(-4 * dt * dfy[:, :n] / wJ[..., None]))
     Ly[:, 1:] = np.minimum(Ly[:, 1:], coef(4 * dt * dfy[:, 1:] / wJ[..., None]))
     Lx, Ly = np.minimum(Lx, blend[:, None, None]), np.minimum(Ly, blend[:, None, None])       # "Apply shock capturing" :344-347
+    if cell:
+        es_volume(param, dd, Uq, d, fb, Lx, Ly, smooth_factor(param, sigma) if relaxed_cell else np.zeros(K), lim.bound)
     # symmetrize_limiting_parameters! :418-456, partner faces through mapP (limiter_utils.jl:122-181)
     mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
     Lx0, Ly0 = Lx.copy(), Ly.copy()

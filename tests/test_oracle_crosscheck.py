@@ -318,3 +318,47 @@ def test_oracle_bounds_and_shock_capturing_agree_with_the_dense_restatement(prob
         for mine, ref in pairs:
             # (a bisection result may flip by one step, 2^-21 of its bracket, where its predicate sits on a rounding boundary)
             assert (np.abs(mine - ref) > 1e-12).mean() < 0.01 and np.abs(mine - ref).max() < 1e-5, (problem, variant, nstage)
+
+
+def _cell_variants():
+    from p2de_b200 import (HennemannShockCapture, PositivityAndCellEntropyBound, PositivityAndRelaxedCellEntropyBound, SubcellLimiter,
+                           TVDAndCellEntropyBound, TVDAndRelaxedCellEntropyBound)
+    return {
+        "cell-entropy": SubcellLimiter(bound=PositivityAndCellEntropyBound()),
+        "relaxed-cell-entropy": SubcellLimiter(bound=PositivityAndRelaxedCellEntropyBound()),
+        "tvd-cell-entropy": SubcellLimiter(bound=TVDAndCellEntropyBound()),
+        "tvd-relaxed-cell-entropy-beta0.3-hennemann": SubcellLimiter(bound=TVDAndRelaxedCellEntropyBound(beta=0.3), shockcapture=HennemannShockCapture()),
+    }
+
+
+CELL_PROBLEMS = dict(BOUND_PROBLEMS, **{"wave-N4": (lambda lim: P.wave2d(N=4, K=(4, 4), limiter=lim), 3)})
+
+
+@pytest.mark.parametrize("variant", sorted(_cell_variants()))
+@pytest.mark.parametrize("problem", sorted(CELL_PROBLEMS))
+def test_oracle_cell_entropy_bounds_agree_with_the_dense_restatement(problem, variant):
+    """The four cell-entropy bounds on Lobatto nodes (enforce_ES_subcell!: subcell.jl:462-466, 508-565, 630-753): entropy-production
+    estimate per element and direction, greedy switch-off of the interior subcell faces in descending (value, index) order, the last
+    one partially; written here with dictionaries and Python's sort instead of the oracle's in-place selection."""
+    from dense_rhs import dense_limited_rhs
+    make, nsteps = CELL_PROBLEMS[problem]
+    param, rd, md, dd, bc, U0 = P.setup(make(_cell_variants()[variant]))
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, n = dd.sizes.K, param.N + 1
+    for nstage in (1, 3):
+        dt_in = tp.CFL * tp.dt0
+        orc.rhs(t, dt_in, nstage)
+        d = dense_limited_rhs(param, dd, bc, U, t, dt_in, nstage)
+        assert rel(d["rhsU"], orc.field("rhsU")) < 1e-12, (problem, variant, nstage)
+        Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]
+        assert (Lo < 1.0).any()
+        for mine, ref in ((d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))):
+            assert np.abs(mine - ref).max() < 1e-12, (problem, variant, nstage)
+            assert np.array_equal(mine == 0.0, ref == 0.0)          # the faces the greedy step switched off completely

@@ -767,3 +767,21 @@ def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1):
     d["rhsU"] = (flim[:, 1:] - flim[:, :-1]) / wJ[..., None]
     d["Ll"] = Ll
     return d
+
+
+def dense_ssp33_step(param, dd, bc, Uq, t, smin=None):
+    """One iteration of the loop in SSP33! (timestepping/SSPRK33.jl:28-40) on top of the dense rhs!: dt capped by CFL dt0 and
+    T - t, stage 1 returns the CFL dt but its limiter has seen the cap (rhs.jl:46,52), three stages with the SSP combinations.
+    2D, LimitedDG.  -> (U_new, dt)"""
+    tp = param.timestepping_param
+    dt = min(tp.CFL * tp.dt0, tp.T - t)
+    resW = Uq
+    d = dense_limited_rhs(param, dd, bc, Uq, t, dt, 1, smin=smin)
+    dt = d["dt"]
+    U = resW + dt * d["rhsU"]
+    d = dense_limited_rhs(param, dd, bc, U, t, dt, 2, smin=smin)
+    resZ = U + dt * d["rhsU"]
+    U = 3 / 4 * resW + 1 / 4 * resZ
+    d = dense_limited_rhs(param, dd, bc, U, t, dt, 3, smin=smin)
+    resZ = U + dt * d["rhsU"]
+    return 1 / 3 * resW + 2 / 3 * resZ, dt

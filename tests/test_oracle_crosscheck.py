@@ -362,3 +362,38 @@ def test_oracle_cell_entropy_bounds_agree_with_the_dense_restatement(problem, va
         for mine, ref in ((d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))):
             assert np.abs(mine - ref).max() < 1e-12, (problem, variant, nstage)
             assert np.array_equal(mine == 0.0, ref == 0.0)          # the faces the greedy step switched off completely
+
+
+STEPS = {
+    "vortex-N3-smoke": (lambda: P.vortex(N=3, K=(5, 5)), 2),                                       # test/test_smoke.jl to its T = 2e-2
+    "dmr-N3": (lambda: P.dmr(N=3, K=(16, 4)), 6),
+    "sedov-N2-zhangshu": (lambda: P.sedov(N=2, K=(8, 8), limiter=ZhangShuLimiter()), 6),
+    "kh-N3-gauss-nodewise": (lambda: P.kelvin_helmholtz(N=3, K=(5, 5), **dict(NW, entropyproj_limiter=_nodewise())), 6),
+    "sedov-N3-minentropy": (lambda: P.sedov(N=3, K=(8, 8), limiter=_variants()["subcell-minentropy"]), 5),
+}
+
+
+def _nodewise():
+    from p2de_b200 import NodewiseScaledExtrapolation
+    return NodewiseScaledExtrapolation()
+
+
+@pytest.mark.parametrize("name", sorted(STEPS))
+def test_oracle_time_loop_agrees_with_the_dense_restatement(name):
+    """SSP33! (SSPRK33.jl:28-40) for several steps: the dt rule (cap, CFL dt from stage 1, the stage-1 limiter seeing the cap), the
+    three SSP combinations and everything underneath, both restatements advancing their own state from the same initial data."""
+    from dense_rhs import dense_ssp33_step, s_modified
+    make, nsteps = STEPS[name]
+    param, rd, md, dd, bc, U0 = P.setup(make())
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    smin = float(s_modified(param.equation.gamma, U0).min())
+    t, U = param.timestepping_param.t0, U0
+    for _ in range(nsteps):
+        dt_o = orc.ssp33_step(t)
+        U, dt = dense_ssp33_step(param, dd, bc, U, t, smin=smin)
+        assert abs(dt - dt_o) <= 1e-12 * dt_o, (name, dt, dt_o)
+        t += dt_o
+    Uo = orc.get_state()
+    assert rel(U, Uo) < 1e-11, name
+    assert np.array_equal(np.sign(U[..., 0]), np.sign(Uo[..., 0]))

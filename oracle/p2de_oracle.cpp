@@ -34,6 +34,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <limits>
 #include <string>
 #include <vector>
@@ -204,7 +205,9 @@ double bisection(F f, double x_valid, double x_invalid) {
 // Wall-clock per phase, under the reference's TimerOutputs labels (rhs.jl:6-51, limiter.jl:9-51,
 // SSPRK33.jl:29): what `@timeit_debug timer "..."` would report.  Read with oracle_phase_times.
 struct PhaseTimers {
-  std::vector<std::pair<std::string, double>> acc;
+  // (a deque: scopes nest -- "rhs calculation" is open while "apply positivity limiter" registers its label -- and each open
+  //  scope keeps a reference to its slot, which a growing std::vector would leave dangling)
+  std::deque<std::pair<std::string, double>> acc;
   double &slot(const char *name) {
     for (auto &p : acc) if (p.first == name) return p.second;
     acc.emplace_back(name, 0.0);

@@ -649,7 +649,36 @@ def lim1(ZEROTOL, U, Pv, Lrho, Lrhoe):
     return np.minimum(np.minimum(l, quad1(ZEROTOL, U, Pv, Lrhoe)), 1.0)
 
 
-def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1):
+def dense_theta_1d(param, dd, Uq):
+    """NodewiseScaledExtrapolation on 1D Gauss nodes: filter.jl:6-130 is dimension-generic (Vf, Vf_low of the line element)."""
+    g = param.equation.gamma
+    ops = dd.ops
+    eps, zeta, eta = param.global_constants.POSTOL, param.limiting_param.zeta, param.limiting_param.eta
+    vq = v_u1(g, Uq)
+    Uf = np.einsum("fq,kqc->kfc", ops.Vf, Uq)
+    VUf = np.einsum("fq,kqc->kfc", ops.Vf, vq)
+    rhoef = rhoe1(Uf)
+
+    def ok(th):
+        W = th[..., None] * np.asarray(ops.Vf)[None] + (1 - th[..., None]) * np.asarray(ops.Vf_low)[None]
+        vt = np.einsum("kfq,kqc->kfc", W, vq)
+        well = vt[..., 2] < -eps
+        with np.errstate(all="ignore"):
+            ut = u_v1(g, np.where(well[..., None], vt, np.array([0.0, 0.0, -1.0])))
+            rhoe = rhoe1(ut)
+            good = (vt[..., 2] < np.minimum(zeta * VUf[..., 2], -eps)) & (ut[..., 0] > np.maximum((1 - eta) * Uf[..., 0], eps)) & \
+                (ut[..., 0] < (1 + eta) * Uf[..., 0]) & (rhoe > np.maximum((1 - eta) * rhoef, eps)) & (rhoe < (1 + eta) * rhoef)
+        return well & good
+    one = ok(np.ones(Uf.shape[:2]))
+    xv, xi = np.zeros(Uf.shape[:2]), np.ones(Uf.shape[:2])
+    for _ in range(21):
+        xn = 0.5 * (xv + xi)
+        good = ok(xn)
+        xv, xi = np.where(good, xn, xv), np.where(good, xi, xn)
+    return np.where(one, 1.0, xv)
+
+
+def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin=None):
     """rhs!(::LimitedDG) in 1D with NoEntropyProjectionLimiter, NoShockCapture, PositivityBound / Zhang-Shu: the same dense
     restatement for Dim1 (the Dim1 methods of the files cited above; Bx(::Dim1) as evidently intended, rhs_utils.jl:13-19 passes its
     arguments in the wrong order; the subcell symmetrisation pairs element k's first face with element k-1's last, periodically,
@@ -667,7 +696,10 @@ def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1):
     mapO = np.asarray(bc.mapO, dtype=np.int64).reshape(-1) - 1
     Ival = np.asarray(bc.Ival, dtype=float).reshape(-1, 3)
     vq = v_u1(g, Uq)
-    utf = u_v1(g, np.einsum("fq,kqc->kfc", ops.Vf, vq))
+    if theta_local is None:
+        theta_local = dense_theta_1d(param, dd, Uq) if param.entropyproj_limiter.code == T.PROJLIM_NODEWISE else np.ones((K, 2))
+    Vf_new = theta_local[..., None] * np.asarray(ops.Vf)[None] + (1 - theta_local[..., None]) * np.asarray(ops.Vf_low)[None]
+    utf = u_v1(g, np.einsum("kfq,kqc->kfc", Vf_new, vq))
     u_tilde = np.concatenate([Uq, utf], axis=1)
     Bx = rxJ[:, Nq:] * np.asarray(ops.Brs[0], dtype=float)                      # [K, 2]
     nn = np.abs(Bx)
@@ -741,24 +773,119 @@ def dense_limited_rhs_1d(param, dd, bc, Uq, t, dt, nstage=1):
     else:
         fstar = 0.5 * (flux1(g, utf) + flux1(g, uPh))
     BF_H = Bx[..., None] * fstar - LFc[..., None] * (uPh - utf)
-    rhsH = -(np.einsum("qh,khc->kqc", ops.MinvVhT, QF1) + np.einsum("qf,kfc->kqc", ops.MinvVfT, BF_H)) / np.asarray(geom.Jq, dtype=float)[..., None]
-    d["rhsH"] = rhsH
+    if (theta_local == 1.0).all():
+        proj = np.einsum("qh,khc->kqc", ops.MinvVhT, QF1) + np.einsum("qf,kfc->kqc", ops.MinvVfT, BF_H)
+    else:       # the limited face matrix, flux_differencing.jl:288-319
+        proj = (QF1[:, :Nq] + np.einsum("kfq,kfc->kqc", Vf_new, QF1[:, Nq:]) + np.einsum("kfq,kfc->kqc", Vf_new, BF_H)) / np.asarray(ops.wq)[None, :, None]
+    rhsH = -proj / np.asarray(geom.Jq, dtype=float)[..., None]
+    d["rhsH"], d["theta_local"] = rhsH, theta_local
     # ---- limiter
+    lim = param.rhs_limiter
+    subcell = lim.code == T.LIMITER_SUBCELL
+    bcode = lim.bound.code if subcell else T.BOUND_POSITIVITY
+    cell = bcode in (T.BOUND_POS_CELL_ENTROPY, T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
+    relaxed_cell = bcode in (T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
+    tvd = bcode >= T.BOUND_TVD
+    minent = bcode in (T.BOUND_POS_MIN_ENTROPY, T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
+    relaxed = bcode in (T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
+    hen = lim.shockcapture.code == T.SHOCKCAPTURE_HENNEMANN
+    blend = np.ones(K)
+    if hen or relaxed or relaxed_cell:                                # initialize_smoothness_indicator!(::Dim1) shock_capture.jl:14-45
+        modal = np.einsum("mq,kq->km", ops.VDM_inv, Uq[..., 0] * p1(g, Uq))
+        e = modal ** 2
+        tot = np.zeros(K)
+        for m in range(e.shape[1]):
+            tot = tot + e[:, m]
+        sigma = np.maximum(e[:, param.N] / tot, e[:, param.N - 1] / tot)
+    if hen:
+        TN = lim.shockcapture.a * 10 ** (-lim.shockcapture.c * (param.N + 1) ** 0.25)
+        blend = np.maximum(np.minimum(1.0 - 1.0 / (1.0 + EXP(-math.log((1 - 0.0001) / 0.0001) / TN * (sigma - TN))), 1.0), 0.5)
     uL = Uq + dt * rhsL
-    if param.rhs_limiter.code == T.LIMITER_ZHANGSHU:
-        l = lim1(ZEROTOL, uL, dt * (rhsH - rhsL), zeta * uL[..., 0], zeta * rhoe1(uL)).min(axis=1)
-        d["L"], d["rhsU"] = l, (1 - l)[:, None, None] * rhsL + l[:, None, None] * rhsH
+    if not subcell:
+        L = lim1(ZEROTOL, uL, dt * (rhsH - rhsL), zeta * uL[..., 0], zeta * rhoe1(uL)).min(axis=1)
+        l = np.minimum(L, blend)
+        d["L"], d["rhsU"] = L, (1 - l)[:, None, None] * rhsL + l[:, None, None] * rhsH
         return d
+    if minent or tvd:                                                 # low_order_stencil(::Dim1) limiter_utils.jl:212-220
+        mp = np.asarray(bc.mapP).reshape(K, 2) - 1
+        kN, qN = np.empty((K, Nq, 2), dtype=np.int64), np.empty((K, Nq, 2), dtype=np.int64)
+        for q in range(Nq):
+            for s_, (inside, qin) in enumerate(((q - 1 >= 0, q - 1), (q + 1 <= Nq - 1, q + 1))):
+                if inside:
+                    kN[:, q, s_], qN[:, q, s_] = np.arange(K), qin
+                else:
+                    P = mp[:, ops.q2fq[q][0] - 1]
+                    kN[:, q, s_], qN[:, q, s_] = P // 2, fq2q[P % 2]
+    Lphi = None
+    if minent:
+        sm = rhoe1(Uq) * POW(Uq[..., 0], -g)
+        lb = np.minimum(sm, sm[kN, qN].min(axis=2))
+        epsk = smooth_factor(param, sigma) if relaxed else np.ones(K)
+        Lphi = epsk[:, None] * lb + (1 - epsk[:, None]) * smin
+    Lrho, Urho = zeta * uL[..., 0], None
+    if tvd:
+        rhoL = Uq[..., 0] + dt * rhsL[..., 0]
+        nb = rhoL[kN, qN]
+        Lrho, Urho = np.minimum(rhoL, nb.min(axis=2)), np.maximum(rhoL, nb.max(axis=2))
+    Lrhoe = zeta * rhoe1(uL)
+
+    def coef(Pv):
+        with np.errstate(divide="ignore", invalid="ignore"):
+            l = np.where(uL[..., 0] + Pv[..., 0] < Lrho, np.maximum((Lrho - uL[..., 0]) / Pv[..., 0], 0.0), 1.0)
+            if Urho is not None:
+                l = np.where(uL[..., 0] + Pv[..., 0] > Urho, np.minimum(l, np.maximum((Urho - uL[..., 0]) / Pv[..., 0], 0.0)), l)
+        l = np.minimum(np.minimum(l, quad1(ZEROTOL, uL, Pv, Lrhoe)), 1.0)
+        if minent:
+            def f(x):
+                with np.errstate(all="ignore"):
+                    w = uL + x[..., None] * Pv
+                    return rhoe1(w) * POW(w[..., 0], -g) >= Lphi - POSTOL
+            top = f(l)
+            xv, xi = np.zeros_like(l), l.copy()
+            for _ in range(21):
+                xn = 0.5 * (xv + xi)
+                good = f(xn)
+                xv, xi = np.where(good, xn, xv), np.where(good, xi, xn)
+            l = np.where(top, l, xv)
+        return l
     fH, fL = np.zeros((K, Nq + 1, 3)), np.zeros((K, Nq + 1, 3))       # accumulate_f_bar!(::Dim1) :144-161
     fH[:, 0], fL[:, 0] = BF_H[:, 0], BF_L[:, 0]
     for i in range(1, Nq + 1):
         fH[:, i] = fH[:, i - 1] + wJ[:, i - 1, None] * rhsH[:, i - 1]
         fL[:, i] = fL[:, i - 1] + wJ[:, i - 1, None] * rhsL[:, i - 1]
     df = fH - fL
-    Lrho, Lrhoe = zeta * uL[..., 0], zeta * rhoe1(uL)
     Ll = np.ones((K, Nq + 1))                                         # subcell_bound_limiter!(::Dim1) :208-246
-    Ll[:, :Nq] = np.minimum(Ll[:, :Nq], lim1(ZEROTOL, uL, -2 * dt * df[:, :Nq] / wJ[..., None], Lrho, Lrhoe))
-    Ll[:, 1:] = np.minimum(Ll[:, 1:], lim1(ZEROTOL, uL, 2 * dt * df[:, 1:] / wJ[..., None], Lrho, Lrhoe))
+    Ll[:, :Nq] = np.minimum(Ll[:, :Nq], coef(-2 * dt * df[:, :Nq] / wJ[..., None]))
+    Ll[:, 1:] = np.minimum(Ll[:, 1:], coef(2 * dt * df[:, 1:] / wJ[..., None]))
+    Ll = np.minimum(Ll, blend[:, None])
+    if cell:                                                          # enforce_ES_subcell!(::Dim1) :468-506, 567-628
+        epsk = smooth_factor(param, sigma) if relaxed_cell else np.zeros(K)
+        psif = (g - 1.0) * Uq[:, fq2q][..., 1]
+        for k in range(K):
+            sB = 0.0
+            for f in range(2):
+                sB += Bx[k, f] * psif[k, f]
+            dv = {e: vq[k, e] - vq[k, e + 1] for e in range(Nq - 1)}                     # interior face e + 1 between nodes e, e + 1
+            dvdf = {e: float(np.sum(dv[e] * (fH[k, e + 1] - fL[k, e + 1]))) for e in dv}
+            sdvfL = 0.0
+            for e in dv:
+                sdvfL += float(np.sum(dv[e] * fL[k, e + 1]))
+            spos = 0.0
+            for e in dv:
+                spos += Ll[k, e + 1] * dvdf[e]
+            budget = sB - sdvfL
+            rhs_ = (1 - lim.bound.beta * epsk[k]) * budget if relaxed_cell else budget
+            tol = max(0.0, sdvfL - sB)
+            if spos - rhs_ > tol:
+                lhs, taken = spos, []
+                for e in sorted(dvdf, key=lambda e_: (dvdf[e_], e_), reverse=True):
+                    if not lhs > rhs_ + tol or dvdf[e] < ZEROTOL:
+                        break
+                    lhs -= Ll[k, e + 1] * dvdf[e]
+                    taken.append(e)
+                for m, e in enumerate(taken):
+                    l_new = max((rhs_ + tol - lhs) / dvdf[e], 0.0) if m == len(taken) - 1 else 0.0
+                    Ll[k, e + 1] = min(Ll[k, e + 1], l_new)
     first, last = Ll[:, 0].copy(), Ll[:, Nq].copy()                   # symmetrize_limiting_parameters!(::Dim1) :405-416
     l = np.minimum(first, np.roll(last, 1))
     Ll[:, 0] = l

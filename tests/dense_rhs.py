@@ -14,7 +14,7 @@ TVD bounds and their combinations, with or without Hennemann shock capturing, as
 symmetrisation and the low-order stencils through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
 filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  The four cell-entropy bounds on Lobatto
 nodes are restated element by element (`es_volume`).  Not covered: the interface part of the cell-entropy bounds on Gauss nodes
-(order-dependent in the reference itself, oracle deviation D5) and the bounds other than PositivityBound in 1D.
+(order-dependent in the reference itself, oracle deviation D5).  `dense_limited_rhs_1d` does all of this for the Dim1 methods.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math

@@ -397,3 +397,103 @@ def test_oracle_time_loop_agrees_with_the_dense_restatement(name):
     Uo = orc.get_state()
     assert rel(U, Uo) < 1e-11, name
     assert np.array_equal(np.sign(U[..., 0]), np.sign(Uo[..., 0]))
+
+
+def _variants_1d():
+    from p2de_b200 import (HennemannShockCapture, PositivityAndCellEntropyBound, PositivityAndMinEntropyBound,
+                           PositivityAndRelaxedCellEntropyBound, PositivityAndRelaxedMinEntropyBound, PositivityBound, SubcellLimiter,
+                           TVDAndMinEntropyBound, TVDAndRelaxedCellEntropyBound, TVDBound)
+    return {
+        "hennemann": SubcellLimiter(bound=PositivityBound(), shockcapture=HennemannShockCapture()),
+        "minentropy": SubcellLimiter(bound=PositivityAndMinEntropyBound()),
+        "relaxed-minentropy": SubcellLimiter(bound=PositivityAndRelaxedMinEntropyBound()),
+        "tvd": SubcellLimiter(bound=TVDBound()),
+        "tvd-minentropy": SubcellLimiter(bound=TVDAndMinEntropyBound()),
+        "cell-entropy": SubcellLimiter(bound=PositivityAndCellEntropyBound()),
+        "relaxed-cell-entropy": SubcellLimiter(bound=PositivityAndRelaxedCellEntropyBound()),
+        "tvd-relaxed-cell-entropy-hennemann": SubcellLimiter(bound=TVDAndRelaxedCellEntropyBound(beta=0.3), shockcapture=HennemannShockCapture()),
+        "zhangshu-hennemann": ZhangShuLimiter(shockcapture=HennemannShockCapture()),
+    }
+
+
+PROBLEMS_1D = {
+    "sod-N3": (lambda lim: P.sod(N=3, K=40, limiter=lim), 20),
+    "shu-osher-N3": (lambda lim: P.shu_osher(N=3, K=64, limiter=lim), 30),
+    "leblanc-N2": (lambda lim: P.leblanc(N=2, K=100, limiter=lim), 5),
+}
+
+
+def _smin_1d(param, U0):
+    g = param.equation.gamma
+    return float(((U0[..., 2] - 0.5 * U0[..., 1] ** 2 / U0[..., 0]) * U0[..., 0] ** (-g)).min())
+
+
+@pytest.mark.parametrize("variant", sorted(_variants_1d()))
+@pytest.mark.parametrize("problem", sorted(PROBLEMS_1D))
+def test_oracle_1d_bounds_agree_with_the_dense_restatement(problem, variant):
+    """All ten subcell bounds and Hennemann shock capturing in 1D (the Dim1 methods of subcell.jl:37-55, 86-110, 208-246, 352-377,
+    468-506, 567-628; shock_capture.jl:14-45) on shock-tube states the oracle has advanced."""
+    from dense_rhs import dense_limited_rhs_1d
+    make, nsteps = PROBLEMS_1D[problem]
+    param, rd, md, dd, bc, U0 = P.setup(make(_variants_1d()[variant]))
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    smin = _smin_1d(param, U0)
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, Nq = dd.sizes.K, dd.sizes.Nq
+    for nstage in (1, 2):
+        dt_in = tp.CFL * tp.dt0
+        orc.rhs(t, dt_in, nstage)
+        with np.errstate(divide="ignore", invalid="ignore"):      # (log10 of a zero smoothness indicator on constant elements, as in the reference)
+            d = dense_limited_rhs_1d(param, dd, bc, U, t, dt_in, nstage, smin=smin)
+        assert rel(d["rhsU"], orc.field("rhsU")) < 1e-12, (problem, variant, nstage)
+        if "L" in d:
+            mine, ref = d["L"], orc.field("L").reshape(3, K)[nstage - 1]
+        else:
+            mine, ref = d["Ll"], orc.field("L_local").reshape(3, K, -1)[nstage - 1][:, :Nq + 1]
+            assert (ref < 1.0).any()
+        assert (np.abs(mine - ref) > 1e-12).mean() < 0.01 and np.abs(mine - ref).max() < 1e-5, (problem, variant, nstage)
+        assert np.array_equal(mine == 0.0, ref == 0.0)
+
+
+NW_1D = {
+    "sod-N3": (lambda nw: P.sod(N=3, K=40, **nw), 30),
+    "sod-N2": (lambda nw: P.sod(N=2, K=50, **nw), 15),
+    "shu-osher-N3": (lambda nw: P.shu_osher(N=3, K=64, **nw), 30),
+    "leblanc-N2": (lambda nw: P.leblanc(N=2, K=100, **nw), 30),
+}
+
+
+@pytest.mark.parametrize("name", sorted(NW_1D))
+def test_oracle_1d_nodewise_agrees_with_the_dense_restatement(name):
+    """NodewiseScaledExtrapolation on 1D Gauss nodes (filter.jl:6-130 with the line element's Vf, Vf_low): theta per face node, the
+    projection with theta, find_alpha on the limited face state, the limited face matrix, the limiter on top."""
+    from dense_rhs import dense_limited_rhs_1d, dense_theta_1d
+    make, nsteps = NW_1D[name]
+    param, rd, md, dd, bc, U0 = P.setup(make(dict(NW, entropyproj_limiter=_nodewise())))
+    orc = Oracle(param, dd, bc)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    K, Nq = dd.sizes.K, dd.sizes.Nq
+    for nstage in (1, 2):
+        dt_in = tp.CFL * tp.dt0
+        dt_o = orc.rhs(t, dt_in, nstage)
+        th_o = orc.field("theta_local").reshape(3, K, 2)[nstage - 1]
+        assert (th_o < 1.0).any(), "the state was chosen because the projection limiter engages"
+        th = dense_theta_1d(param, dd, U)
+        assert np.abs(th - th_o).max() <= 2.0 ** -20 and np.array_equal(th == 1.0, th_o == 1.0)
+        d = dense_limited_rhs_1d(param, dd, bc, U, t, dt_in, nstage, theta_local=th_o)
+        for f in ("rhsL", "rhsH", "rhsU"):
+            assert rel(d[f], orc.field(f)) < 1e-12, (name, nstage, f)
+        if nstage == 1:
+            assert abs(d["dt"] - dt_o) <= 1e-13 * dt_o
+        assert np.abs(d["Ll"] - orc.field("L_local").reshape(3, K, -1)[nstage - 1][:, :Nq + 1]).max() < 1e-12

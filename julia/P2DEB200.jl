@@ -141,4 +141,30 @@ function P2DE.SSP33!(s::B200State, solver, state_param)
     return P2DE.DataHistory{Nc}(Uhist, Lhist, thetahist, thist, dthist)
 end
 
+# check_conservation(state, solver)                              (src/dg/utils.jl:1-12), reduced on the device
+function P2DE.check_conservation(s::B200State, solver)
+    out = Ref{Float64}(0.0)
+    check(s.handle, ccall((:p2de_reduce, lib), Int32, (Ptr{Cvoid}, Int32, Ref{Float64}), s.handle, Int32(0), out))
+    return out[]
+end
+
+# calculate_error(state, solver, exact_sol) -> ErrorData          (src/dg/postprocess.jl:1-46): the caller's exact_sol
+# callback is evaluated on the host at every node exactly as the reference does, the weighted sums are formed on the device
+function P2DE.calculate_error(s::B200State, solver, exact_sol)
+    (; K, Nq, Nc) = solver.discrete_data.sizes
+    T = solver.param.timestepping_param.T
+    exact = [P2DE.exact_solution(P2DE.equation(solver), i, k, T, solver.md, exact_sol) for i = 1:Nq, k = 1:K]
+    sums = zeros(Float64, Nc, 6)      # C: double[6][Nc] = L1err, L2err, Linferr, L1exact, L2exact, Linfexact
+    flat = reinterpret(Float64, vec(exact))
+    GC.@preserve exact check(s.handle, ccall((:p2de_calculate_error, lib), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        s.handle, pointer(flat), pointer(sums)))
+    L1, L2, Linf = 0.0, 0.0, 0.0
+    for c = 1:Nc
+        if sums[c, 6] > 1e-14
+            L1 += sums[c, 1] / sums[c, 4]; L2 += sqrt(sums[c, 2]) / sqrt(sums[c, 5]); Linf += sums[c, 3] / sums[c, 6]
+        end
+    end
+    return P2DE.ErrorData(L1, L2, Linf)
+end
+
 end # module

@@ -63,3 +63,33 @@ def test_gpu_reproduces_golden(path):
         t += dt
         assert abs(dt - g["dthist"][i]) <= 1e-10 * dt
     assert rel(st.preallocation.Uq, g["U_final"]) < 1e-8
+
+
+@pytest.mark.parametrize("path", GOLD, ids=[os.path.basename(p)[:-4] for p in GOLD])
+def test_dense_restatement_reproduces_golden(path):
+    """The committed vectors against the SECOND restatement (tests/dense_rhs.py, written independently of the oracle that generated
+    them): what the GPU tests are held to is what two differently written readings of the reference agree on."""
+    from dense_rhs import dense_limited_rhs, dense_ssp33_step, s_modified
+    name = os.path.basename(path)[:-4]
+    g = np.load(path)
+    factory, nsteps = CASES[name]
+    param, rd, md, dd, bc, U0 = P.setup(factory())
+    assert np.array_equal(U0, g["U0"])
+    tp = param.timestepping_param
+    smin = float(s_modified(param.equation.gamma, U0).min())
+    d = dense_limited_rhs(param, dd, bc, U0, tp.t0, tp.CFL * tp.dt0, 1, smin=smin)
+    assert rel(d["rhsU"], g["rhsU_stage1"]) < 1e-12
+    assert abs(d["dt"] - float(g["dt_stage1"])) <= 1e-13 * d["dt"]
+    if "L_stage1" in g.files:
+        assert np.abs(d["L"] - g["L_stage1"]).max() < 1e-12
+    else:
+        K, n = dd.sizes.K, param.N + 1
+        Lg = g["L_local_stage1"].reshape(K, 2, n * (n + 1))
+        assert np.abs(d["Lx"] - Lg[:, 0].reshape(K, n, n + 1)).max() < 1e-12
+        assert np.abs(d["Ly"] - Lg[:, 1].reshape(K, n + 1, n)).max() < 1e-12
+    U, t = U0, tp.t0
+    for i in range(len(g["dthist"])):
+        U, dt = dense_ssp33_step(param, dd, bc, U, t, smin=smin)
+        assert abs(dt - g["dthist"][i]) <= 1e-12 * dt
+        t += dt
+    assert rel(U, g["U_final"]) < 1e-11

@@ -106,3 +106,28 @@ def test_ncu_capture_is_of_the_kernels_this_library_holds():
     assert len(want) == 3
     plib.load()
     assert bench.kernel_sass_hashes(plib.SO_PATH, sorted(want)) == want
+
+
+def test_header_is_plain_c_and_every_entry_point_links(tmp_path):
+    """include/p2de_b200.h compiles as C99 (no C++, no torch types in the signatures) and a C program that takes the address of
+    every declared entry point links against the built library -- the binding a cgo / ccall / ctypes user gets."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    plib.load()
+    names = header_functions()
+    src = tmp_path / "abi_link.c"
+    src.write_text('#include "p2de_b200.h"\n#include <stdio.h>\ntypedef void (*fn_t)(void);\nint main(void) {\n  fn_t f[] = {\n'
+                   + "".join(f"    (fn_t)&{n},\n" for n in names)
+                   + '  };\n  printf("%d %s\\n", (int)(sizeof f / sizeof f[0]), p2de_last_error(0) ? "ok" : "null");\n'
+                   '  return p2de_destroy(0);\n}\n')
+    exe = tmp_path / "abi_link"
+    libdir = os.path.dirname(plib.SO_PATH)
+    cmd = [gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", libdir, "-l:" + os.path.basename(plib.SO_PATH), "-Wl,-rpath," + libdir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and run.stdout.split()[0] == str(len(names)), (run.stdout, run.stderr)

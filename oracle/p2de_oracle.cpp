@@ -9,7 +9,10 @@
 // PARITY STATUS: "parity unpinned".  Julia is not installed here and the reference's own
 // tests hold no numeric pins (test/test_smoke.jl:44-81 only checks that nothing throws),
 // so this restatement is validated by analytic invariants instead (tests/test_oracle_*.py:
-// free stream, conservation, positivity, vortex convergence order) and pinned for later
+// free stream, conservation, positivity, vortex convergence order), cross-checked against a second
+// restatement written independently in another form (dense operators, whole-array numpy:
+// tests/dense_rhs.py, tests/test_oracle_crosscheck.py -- every RHS type, flux option, limiter, bound,
+// Hennemann, Nodewise, 1D and 2D agree to round-off, coefficients bit for bit) and pinned for later
 // rounds by golden vectors it generates itself (tests/golden/, oracle/make_golden.py).
 //
 // Each function cites the reference file:line it follows (paths relative to the

@@ -12,9 +12,8 @@ Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!
 and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with the positivity, minimum-entropy (plain / relaxed) and
 TVD bounds and their combinations, with or without Hennemann shock capturing, as whole-array operations with the interface
 symmetrisation and the low-order stencils through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
-filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  The four cell-entropy bounds on Lobatto
-nodes are restated element by element (`es_volume`).  Not covered: the interface part of the cell-entropy bounds on Gauss nodes
-(order-dependent in the reference itself, oracle deviation D5).  `dense_limited_rhs_1d` does all of this for the Dim1 methods.
+filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  The four cell-entropy bounds are restated element by element (`es_volume`; on Gauss nodes also the interface part, `es_interface`,
+in element order: the reference's own result depends on its thread interleaving there, oracle deviation D5).  `dense_limited_rhs_1d` does all of this for the Dim1 methods.
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math
@@ -252,6 +251,9 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1, theta_local=None):
     fstar_L = 0.5 * (flux_f + fluxes(g, uP))
     BF_L = Bxy[..., None] * fstar_L                                            # [K, Nfp, 2, 4]
     lf = lamB[..., None] * (uP - Uf)
+    fstar_L = fstar_L.copy()                                                   # apply_LF_dissipation_to_fstar, rhs_utils.jl:93-102
+    fstar_L[:, xface, 0] -= lf[:, xface] / Bxy[:, xface, 0:1]
+    fstar_L[:, ~xface, 1] -= lf[:, ~xface] / Bxy[:, ~xface, 1:2]
     BF_L[:, xface, 0] -= lf[:, xface]
     BF_L[:, ~xface, 1] -= lf[:, ~xface]
     for f in range(Nfp):
@@ -310,6 +312,9 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1, theta_local=None):
         fstar_H = 0.5 * (fluxes(g, utf) + fluxes(g, uPh))
     BF_H = Bxy[..., None] * fstar_H
     lfh = LFc[..., None] * (uPh - utf)
+    fstar_H = fstar_H.copy()
+    fstar_H[:, xface, 0] -= lfh[:, xface] / Bxy[:, xface, 0:1]
+    fstar_H[:, ~xface, 1] -= lfh[:, ~xface] / Bxy[:, ~xface, 1:2]
     BF_H[:, xface, 0] -= lfh[:, xface]
     BF_H[:, ~xface, 1] -= lfh[:, ~xface]
     if (theta_local == 1.0).all():
@@ -319,7 +324,7 @@ def dense_rhs(param, dd, bc, Uq, t, nstage=1, theta_local=None):
             / np.asarray(ops.wq)[None, :, None, None]
     rhsxyH = -proj / np.asarray(geom.Jq, dtype=float)[:, :, None, None]        # assemble_rhs! :331-361
     return {"rhsL": rhsL, "rhsxyL": rhsxyL, "rhsH": rhsxyH.sum(axis=2), "rhsxyH": rhsxyH, "dt": dt, "u_tilde_f": utf,
-            "BF_L": BF_L, "BF_H": BF_H, "wJ": wJ, "theta_local": theta_local}
+            "BF_L": BF_L, "BF_H": BF_H, "wJ": wJ, "theta_local": theta_local, "fstar_L": fstar_L, "fstar_H": fstar_H}
 
 
 # ---- limiter_utils.jl:26-95, vectorised (IEEE semantics kept: a == 0 gives infinite / NaN roots, which fail every comparison)
@@ -480,6 +485,49 @@ def es_volume(param, dd, Uq, d, fb, Lx, Ly, epsk, bound):
                 L[where[e]] = min(L[where[e]], l_new)
 
 
+def es_interface(param, dd, bc, Uq, d, Lx, Ly):
+    """enforce_ES_subcell_interface!(::Dim2, ::GaussCollocation) subcell.jl:759-823, in element order (what one thread of the
+    reference does; with several threads its result depends on their interleaving, oracle deviation D5): per element face node,
+    the largest l <= min(own, partner's CURRENT coefficient) with l dv.f*_H + (1 - l) dv.f*_L <= dpsi by the 21-step bisection; only
+    the own entry is written.  Lx, Ly updated in place."""
+    g = param.equation.gamma
+    K, Nq, Nfp = dd.sizes.K, dd.sizes.Nq, dd.sizes.Nfp
+    n = param.N + 1
+    fq2q = np.asarray(dd.ops.fq2q) - 1
+    mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
+    vf = v_ufun(g, Uq[:, fq2q])                                                # at the face nodes' volume nodes (:508-530)
+    psif = (g - 1.0) * Uq[:, fq2q][..., 1:3]
+    fH, fL = d["fstar_H"], d["fstar_L"]                                        # [K, Nfp, 2, 4]
+
+    def solve(l, dvfH, dvfL, dpsi):                                            # solve_l_es_interface! :818-823
+        ok = lambda x: x * dvfH + (1 - x) * dvfL <= dpsi
+        if ok(l):
+            return l
+        xv, xi = 0.0, l
+        for _ in range(21):
+            xn = 0.5 * (xv + xi)
+            if ok(xn):
+                xv = xn
+            else:
+                xi = xn
+        return xv
+    for k in range(K):
+        for dirn, L in ((0, Lx), (1, Ly)):
+            for line in range(n):
+                for e, pos in ((0, 0), (1, n)):
+                    f = (2 * dirn + e) * n + line
+                    P = mapP[k, f]
+                    kP, iP = P // Nfp, P % Nfp
+                    if dirn == 0:
+                        own, partner = (k, line, pos), (kP, iP % n, 0 if iP // n == 0 else n)
+                    else:
+                        own, partner = (k, pos, line), (kP, 0 if iP // n == 2 else n, iP % n)
+                    dv = vf[k, f] - vf[kP, iP]
+                    dpsi = psif[k, f, dirn] - psif[kP, iP, dirn]
+                    dvfH, dvfL = float(np.sum(dv * fH[k, f, dirn])), float(np.sum(dv * fL[k, f, dirn]))
+                    L[own] = solve(min(L[own], L[partner]), dvfH, dvfL, dpsi)
+
+
 def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin=None):
     """rhs!(::LimitedDG): dense_rhs + apply_rhs_limiter! (limiter.jl:8-56) -- Zhang-Shu (zhangshu.jl:4-45) or the subcell limiter
     (subcell.jl:4-349, 418-456, 841-924) with PositivityBound, the minimum-entropy bounds (plain / relaxed), the TVD bounds and their
@@ -498,8 +546,6 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin
     bcode = lim.bound.code if subcell else T.BOUND_POSITIVITY
     cell = bcode in (T.BOUND_POS_CELL_ENTROPY, T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
     relaxed_cell = bcode in (T.BOUND_POS_RELAXED_CELL_ENTROPY, T.BOUND_TVD_RELAXED_CELL_ENTROPY)
-    if cell and param.approximation_basis.code == T.BASIS_GAUSS:
-        raise NotImplementedError("cell-entropy bounds on Gauss nodes (enforce_ES_subcell_interface!, subcell.jl:759-805)")
     tvd = bcode >= T.BOUND_TVD
     minent = bcode in (T.BOUND_POS_MIN_ENTROPY, T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
     relaxed = bcode in (T.BOUND_POS_RELAXED_MIN_ENTROPY, T.BOUND_TVD_RELAXED_MIN_ENTROPY)
@@ -566,6 +612,8 @@ def dense_limited_rhs(param, dd, bc, Uq, t, dt, nstage=1, theta_local=None, smin
     Lx, Ly = np.minimum(Lx, blend[:, None, None]), np.minimum(Ly, blend[:, None, None])       # "Apply shock capturing" :344-347
     if cell:
         es_volume(param, dd, Uq, d, fb, Lx, Ly, smooth_factor(param, sigma) if relaxed_cell else np.zeros(K), lim.bound)
+        if param.approximation_basis.code == T.BASIS_GAUSS:
+            es_interface(param, dd, bc, Uq, d, Lx, Ly)
     # symmetrize_limiting_parameters! :418-456, partner faces through mapP (limiter_utils.jl:122-181)
     mapP = np.asarray(bc.mapP).reshape(K, Nfp) - 1
     Lx0, Ly0 = Lx.copy(), Ly.copy()

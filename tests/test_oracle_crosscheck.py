@@ -497,3 +497,43 @@ def test_oracle_1d_nodewise_agrees_with_the_dense_restatement(name):
         if nstage == 1:
             assert abs(d["dt"] - dt_o) <= 1e-13 * dt_o
         assert np.abs(d["Ll"] - orc.field("L_local").reshape(3, K, -1)[nstage - 1][:, :Nq + 1]).max() < 1e-12
+
+
+GAUSS_CELL = {
+    "kh-N3-gauss": (lambda lim: P.kelvin_helmholtz(N=3, K=(5, 5), limiter=lim, **NW), 3, False),
+    "kh-N2-gauss-nodewise": (lambda lim: P.kelvin_helmholtz(N=2, K=(6, 6), limiter=lim, **dict(NW, entropyproj_limiter=_nodewise())), 4, True),
+    "wave-N3-gauss": (lambda lim: P.wave2d(N=3, K=(5, 4), limiter=lim, **NW), 2, False),
+    "sedov-N3-gauss-nodewise": (lambda lim: P.sedov(N=3, K=(8, 8), limiter=lim, **dict(NW, entropyproj_limiter=_nodewise())), 4, True),
+}
+
+
+@pytest.mark.parametrize("variant", ["cell-entropy", "relaxed-cell-entropy", "tvd-cell-entropy"])
+@pytest.mark.parametrize("problem", sorted(GAUSS_CELL))
+def test_oracle_cell_entropy_on_gauss_nodes_agrees_with_the_dense_restatement(problem, variant):
+    """Cell-entropy bounds on Gauss nodes: the volume part as on Lobatto nodes plus enforce_ES_subcell_interface!
+    (subcell.jl:759-823: per element face node a bisection against the partner's current coefficient), both restatements in element
+    order (the reference's result depends on its thread interleaving there, oracle deviation D5)."""
+    from dense_rhs import dense_limited_rhs
+    make, nsteps, nodewise = GAUSS_CELL[problem]
+    param, rd, md, dd, bc, U0 = P.setup(make(_cell_variants()[variant]))
+    orc = Oracle(param, dd, bc, threads=1)
+    orc.set_state(U0)
+    tp = param.timestepping_param
+    t = tp.t0
+    for _ in range(nsteps):
+        t += orc.ssp33_step(t)
+    U = orc.get_state().copy()
+    assert np.isfinite(U).all() and (U[..., 0] > 0).all()
+    K, n = dd.sizes.K, param.N + 1
+    dt_in = tp.CFL * tp.dt0
+    for nstage in (1, 2):
+        orc.rhs(t, dt_in, nstage)
+        th_o = orc.field("theta_local").reshape(3, K, 4 * n)[nstage - 1] if nodewise else None
+        d = dense_limited_rhs(param, dd, bc, U, t, dt_in, nstage, theta_local=th_o)
+        assert rel(d["rhsU"], orc.field("rhsU")) < 1e-12, (problem, variant, nstage)
+        Lo = orc.field("L_local").reshape(3, K, 2, n * (n + 1))[nstage - 1]
+        assert (Lo == 0.0).any() and (Lo < 1.0).any()
+        for mine, ref in ((d["Lx"], Lo[:, 0].reshape(K, n, n + 1)), (d["Ly"], Lo[:, 1].reshape(K, n + 1, n))):
+            # (the fractional last face of the greedy step divides by its own entropy production: 1e-16 in, up to 1e-11 out)
+            assert np.abs(mine - ref).max() < 1e-9, (problem, variant, nstage)
+            assert np.array_equal(mine == 0.0, ref == 0.0)

@@ -7,13 +7,16 @@ the C++ oracle (tests/test_oracle_crosscheck.py).  It shares no code and no stru
   gathered through the caller's linear `mapP`, boundary conditions through `mapI / mapO / Ival`;
 * no line structure, no tensor-product knowledge, no special case for Lobatto nodes.
 
-Covered: entropy projection with theta = 1 (rhs.jl:59-133), `rhs_low_graph_visc!` including the CFL dt and `find_alpha`
-(low_order_graph_viscosity.jl:4-327), `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361),
-and `apply_rhs_limiter!` for Zhang-Shu and for the subcell limiter with the positivity, minimum-entropy (plain / relaxed) and
-TVD bounds and their combinations, with or without Hennemann shock capturing, as whole-array operations with the interface
-symmetrisation and the low-order stencils through `mapP` (`dense_limited_rhs`), and `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`:
-filter.jl:6-130, the projection with theta, the limited face matrix of flux_differencing.jl:288-319); the 1D path the same way (`dense_limited_rhs_1d`).  The four cell-entropy bounds are restated element by element (`es_volume`; on Gauss nodes also the interface part, `es_interface`,
-in element order: the reference's own result depends on its thread interleaving there, oracle deviation D5).  `dense_limited_rhs_1d` does all of this for the Dim1 methods.
+Covered (2D: `dense_rhs`, `dense_limited_rhs`, `dense_ssp33_step`; 1D: `dense_limited_rhs_1d`):
+* entropy projection (rhs.jl:59-133), with `NodewiseScaledExtrapolation` on Gauss nodes (`dense_theta`: filter.jl:6-130, the projection
+  with theta, the limited face matrix of flux_differencing.jl:288-319);
+* `rhs_low_graph_visc!` including the CFL dt and `find_alpha` (low_order_graph_viscosity.jl:4-327);
+* `rhs_fluxdiff!` with both volume fluxes and both surface fluxes (flux_differencing.jl:4-361);
+* `apply_rhs_limiter!` (limiter.jl:8-56): Zhang-Shu, the subcell limiter with all ten bounds of Solver.jl:47-63 and Hennemann shock
+  capturing, as whole-array operations with the interface symmetrisation and the low-order stencils through `mapP`; the cell-entropy
+  bounds element by element (`es_volume`; on Gauss nodes also the interface part, `es_interface`, in element order: the reference's
+  own result depends on its thread interleaving there, oracle deviation D5);
+* the `SSP33!` loop (SSPRK33.jl:28-40).
 
 Test infrastructure; nothing under p2de_b200/ imports it."""
 import math

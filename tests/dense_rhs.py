@@ -35,7 +35,9 @@ def LOG(x):
     logmean's `-da / (logL - logR)` amplifies one ulp of a logarithm by 1 / |da / a| (up to 1e4), the near-cancelling sum of
     S_ij f_ij by another ~1e2: with np.log this restatement and the C++ oracle agree to 2e-11 on a developed Kelvin-Helmholtz
     state, with the same libm logarithm to 2e-13 (the reference formulation's own sensitivity)."""
-    return _mlog(np.asarray(x, dtype=float)).astype(float)
+    x = np.asarray(x, dtype=float)
+    good = x > 0
+    return np.where(good, _mlog(np.where(good, x, 1.0)).astype(float), np.where(x == 0, -np.inf, np.nan))   # (C's log: -inf at 0, NaN below)
 
 
 def EXP(x):

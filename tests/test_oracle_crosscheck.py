@@ -537,3 +537,62 @@ def test_oracle_cell_entropy_on_gauss_nodes_agrees_with_the_dense_restatement(pr
             # (the fractional last face of the greedy step divides by its own entropy production: 1e-16 in, up to 1e-11 out)
             assert np.abs(mine - ref).max() < 1e-9, (problem, variant, nstage)
             assert np.array_equal(mine == 0.0, ref == 0.0)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_oracle_against_the_dense_restatement_on_random_configurations(seed):
+    """Differential fuzzing: random degree, mesh, collocation, flux options, limiter, bound, shock capturing, projection limiter,
+    boundary set, stage index, dt and a random (rough, positive) state per draw; `rhsU` of the two restatements to 1e-11, and where a
+    state is invalid for the scheme (NaN) both must be non-finite at the same entries."""
+    from dense_rhs import dense_limited_rhs, s_modified
+    from p2de_b200 import (HennemannShockCapture, NodewiseScaledExtrapolation, NoShockCapture, PositivityAndCellEntropyBound,
+                           PositivityAndMinEntropyBound, PositivityAndRelaxedCellEntropyBound, PositivityAndRelaxedMinEntropyBound,
+                           PositivityBound, SubcellLimiter, TVDAndCellEntropyBound, TVDAndMinEntropyBound, TVDAndRelaxedCellEntropyBound,
+                           TVDAndRelaxedMinEntropyBound, TVDBound)
+    rng = np.random.default_rng(seed)
+    bounds = [PositivityBound(), PositivityAndMinEntropyBound(), PositivityAndRelaxedMinEntropyBound(), PositivityAndCellEntropyBound(),
+              PositivityAndRelaxedCellEntropyBound(beta=0.4), TVDBound(), TVDAndMinEntropyBound(), TVDAndRelaxedMinEntropyBound(),
+              TVDAndCellEntropyBound(), TVDAndRelaxedCellEntropyBound(beta=0.7)]
+    compared = 0
+    for it in range(40):
+        N, K = int(rng.integers(1, 5)), (int(rng.integers(2, 6)), int(rng.integers(2, 6)))
+        gauss = bool(rng.integers(0, 2))
+        if rng.integers(0, 4) == 0:
+            lim = ZhangShuLimiter(shockcapture=HennemannShockCapture() if rng.integers(0, 2) else NoShockCapture())
+        else:
+            sc = HennemannShockCapture(a=float(rng.uniform(0.2, 1)), c=float(rng.uniform(1, 2.5))) if rng.integers(0, 3) == 0 else NoShockCapture()
+            lim = SubcellLimiter(bound=bounds[int(rng.integers(0, 10))], shockcapture=sc)
+        low = PROJ if (gauss or rng.integers(0, 2)) else LaxFriedrichsOnNodalVal()
+        high = ChandrashekarOnProjectedVal() if rng.integers(0, 3) == 0 else PROJ
+        kw = dict(limiter=lim, rhs=ESLimitedLowOrderPos(low, high) if rng.integers(0, 4) else StdDGLimitedLowOrderPos(low, high))
+        if gauss:
+            kw["basis"] = GaussCollocation()
+        nodewise = gauss and bool(rng.integers(0, 2))
+        if nodewise:
+            kw["entropyproj_limiter"] = NodewiseScaledExtrapolation()
+        problem = P.dmr(N=N, K=K, **kw) if rng.integers(0, 3) == 0 else P.kelvin_helmholtz(N=N, K=K, **kw)
+        param, rd, md, dd, bc, _ = P.setup(problem)
+        Kt, Nq, g = dd.sizes.K, dd.sizes.Nq, param.equation.gamma
+        amp = 10.0 ** rng.uniform(-6, -0.3)
+        rho = np.abs(1.0 + 0.5 * np.sin(rng.uniform(0, 6) + np.arange(Kt)[:, None] * 0.7) + amp * rng.standard_normal((Kt, Nq))) + 1e-3
+        u = 0.3 * rng.standard_normal() + amp * rng.standard_normal((Kt, Nq))
+        v = 0.3 * rng.standard_normal() + amp * rng.standard_normal((Kt, Nq))
+        p = np.abs(1.0 + 0.3 * np.cos(np.arange(Kt)[:, None] * 0.4) + amp * rng.standard_normal((Kt, Nq))) + 1e-3
+        U = np.stack([rho, rho * u, rho * v, p / (g - 1) + 0.5 * rho * (u * u + v * v)], axis=-1)
+        orc = Oracle(param, dd, bc, threads=1)
+        orc.set_state(U)
+        tp = param.timestepping_param
+        dt_in, nstage = float(10.0 ** rng.uniform(-4, -2)), int(rng.integers(1, 4))
+        orc.rhs(tp.t0, dt_in, 1)               # (stage 1 at t0 records the global minimum of s_modified, subcell.jl:31-34)
+        if nstage != 1:
+            orc.rhs(tp.t0, dt_in, nstage)
+        th_o = orc.field("theta_local").reshape(3, Kt, 4 * (N + 1))[nstage - 1] if nodewise else None
+        with np.errstate(all="ignore"):
+            d = dense_limited_rhs(param, dd, bc, U, tp.t0, dt_in, nstage, theta_local=th_o, smin=float(s_modified(g, U).min()))
+        ro = orc.field("rhsU")
+        tag = (seed, it, N, K, gauss, nodewise, lim, nstage)
+        assert np.array_equal(np.isfinite(ro), np.isfinite(d["rhsU"])), tag
+        if np.isfinite(ro).all():
+            assert rel(d["rhsU"], ro) < 1e-11, tag
+            compared += 1
+    assert compared >= 30

@@ -596,3 +596,55 @@ def test_oracle_against_the_dense_restatement_on_random_configurations(seed):
             assert rel(d["rhsU"], ro) < 1e-11, tag
             compared += 1
     assert compared >= 30
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_1d_against_the_dense_restatement_on_random_configurations(seed):
+    """The same differential fuzzing for the Dim1 methods (Sod boundary set or periodic; no cell-entropy bounds on 1D Gauss nodes: the
+    reference has no interface method for them)."""
+    from dense_rhs import dense_limited_rhs_1d
+    from p2de_b200 import HennemannShockCapture, NodewiseScaledExtrapolation, NoShockCapture, PositivityBound, SubcellLimiter
+    rng = np.random.default_rng(seed)
+    bounds = [v.bound for k, v in sorted(_variants_1d().items()) if hasattr(v, "bound")]
+    compared = 0
+    for it in range(50):
+        N, K, gauss = int(rng.integers(1, 5)), int(rng.integers(3, 30)), bool(rng.integers(0, 2))
+        b = bounds[int(rng.integers(0, len(bounds)))]
+        if gauss and "CellEntropy" in type(b).__name__:
+            b = PositivityBound()
+        if rng.integers(0, 4) == 0:
+            lim = ZhangShuLimiter(shockcapture=HennemannShockCapture() if rng.integers(0, 2) else NoShockCapture())
+        else:
+            lim = SubcellLimiter(bound=b, shockcapture=HennemannShockCapture() if rng.integers(0, 3) == 0 else NoShockCapture())
+        low = PROJ if (gauss or rng.integers(0, 2)) else LaxFriedrichsOnNodalVal()
+        high = ChandrashekarOnProjectedVal() if rng.integers(0, 3) == 0 else PROJ
+        kw = dict(limiter=lim, rhs=ESLimitedLowOrderPos(low, high) if rng.integers(0, 4) else StdDGLimitedLowOrderPos(low, high))
+        if gauss:
+            kw["basis"] = GaussCollocation()
+        nodewise = gauss and bool(rng.integers(0, 2))
+        if nodewise:
+            kw["entropyproj_limiter"] = NodewiseScaledExtrapolation()
+        param, rd, md, dd, bc, _ = P.setup(P.sod(N=N, K=K, **kw) if rng.integers(0, 2) else P.density_wave_1d(N=N, K=K, **kw))
+        Kt, Nq, g = dd.sizes.K, dd.sizes.Nq, param.equation.gamma
+        amp = 10.0 ** rng.uniform(-6, -0.3)
+        rho = np.abs(1 + 0.5 * np.sin(rng.uniform(0, 6) + np.arange(Kt)[:, None] * 0.7) + amp * rng.standard_normal((Kt, Nq))) + 1e-3
+        u = 0.3 * rng.standard_normal() + amp * rng.standard_normal((Kt, Nq))
+        p = np.abs(1 + 0.3 * np.cos(np.arange(Kt)[:, None] * 0.4) + amp * rng.standard_normal((Kt, Nq))) + 1e-3
+        U = np.stack([rho, rho * u, p / (g - 1) + 0.5 * rho * u * u], axis=-1)
+        orc = Oracle(param, dd, bc, threads=1)
+        orc.set_state(U)
+        tp = param.timestepping_param
+        dt_in, nstage = float(10.0 ** rng.uniform(-4, -2)), int(rng.integers(1, 4))
+        orc.rhs(tp.t0, dt_in, 1)
+        if nstage != 1:
+            orc.rhs(tp.t0, dt_in, nstage)
+        th_o = orc.field("theta_local").reshape(3, Kt, 2)[nstage - 1] if nodewise else None
+        with np.errstate(all="ignore"):
+            d = dense_limited_rhs_1d(param, dd, bc, U, tp.t0, dt_in, nstage, theta_local=th_o, smin=_smin_1d(param, U))
+        ro = orc.field("rhsU")
+        tag = (seed, it, N, K, gauss, nodewise, lim, nstage)
+        assert np.array_equal(np.isfinite(ro), np.isfinite(d["rhsU"])), tag
+        if np.isfinite(ro).all():
+            assert rel(d["rhsU"], ro) < 1e-11, tag
+            compared += 1
+    assert compared >= 40
